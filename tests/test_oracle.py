@@ -1,0 +1,127 @@
+"""CPU tests pinning the oracle: against committed golden vectors (made from the live reference by
+tests/golden/make_golden.py) and, where /root/reference exists, against the reference itself."""
+import copy
+import os
+import warnings
+
+import pytest
+import torch
+
+from oracle import live_reference as lr, nets, step
+
+
+def _sample(t, k=257):
+    f = t.detach().reshape(-1).float()
+    return f[:: max(1, f.numel() // k)][:k]
+
+
+def _rel(a, b):
+    return float((a.detach() - b).norm() / b.norm().clamp_min(1e-12))
+
+
+@pytest.fixture(scope="module")
+def gold_nets(golden_dir):
+    return torch.load(os.path.join(golden_dir, "golden_nets_n2.pt"))
+
+
+@pytest.fixture(scope="module")
+def gold_step(golden_dir):
+    return torch.load(os.path.join(golden_dir, "golden_step_n2.pt"))
+
+
+def test_oracle_networks_match_golden(gold_nets):
+    g = gold_nets
+    state = nets.init_model_state(seed=g["seed_w"], perturb=g["perturb"])
+    a, b, z = step.synthetic_batch(g["n"], seed=g["seed_x"])
+    om = step.OracleModel(state=state)
+    gn = g["nets"]
+    ar = a.clone().requires_grad_(True); zr = z.clone().requires_grad_(True)
+    y = om.G_A_B(ar, zr)
+    assert _rel(y, gn["G_A_B"]["out"]) < 1e-5
+    (y * torch.linspace(-1, 1, y.numel()).view_as(y)).sum().backward()
+    assert _rel(_sample(ar.grad), gn["G_A_B"]["dx"]) < 1e-4
+    assert _rel(zr.grad, gn["G_A_B"]["dz"]) < 1e-4
+    for k, v in om.params("netG_A_B"):
+        ref = gn["G_A_B"]["dw_norm"][k]
+        if nets.is_noise_grad("netG_A_B", k):
+            assert float(v.grad.norm()) < 1e-3 and ref < 1e-3, k
+            continue
+        assert abs(float(v.grad.norm()) - ref) <= 1e-4 * ref + 1e-6, k
+    assert _rel(om.G_B_A(b), gn["G_B_A"]["out"]) < 1e-5
+    assert _rel(om.D_A(a), gn["D_A"]["out"]) < 1e-5
+    assert _rel(om.D_B(b), gn["D_B"]["out"]) < 1e-5
+    mu, lv = om.E_B(torch.cat((a, b), 1))
+    assert _rel(mu, gn["E_B"]["mu"]) < 1e-5 and _rel(lv, gn["E_B"]["logvar"]) < 1e-5
+    assert _rel(om.nets["netE_B"]["conv_modules.3.running_mean"], gn["E_B"]["running_mean_3"]) < 1e-5
+    assert _rel(om.nets["netE_B"]["conv_modules.12.running_var"], gn["E_B"]["running_var_12"]) < 1e-5
+    assert _rel(om.D_z_B(z), gn["D_z_B"]["out"]) < 1e-5
+
+
+def test_oracle_train_instance_matches_golden(gold_step):
+    g = gold_step
+    state = nets.init_model_state(seed=g["seed_w"], perturb=g["perturb"])
+    a, b, z = step.synthetic_batch(g["n"], seed=g["seed_x"])
+    om = step.OracleModel(state=state)
+    for it, rec in enumerate(g["steps"]):
+        losses, visuals, gnorms = om.train_instance(a, b, z)
+        # step 2 runs on Adam-updated weights; Adam turns rounding-noise gradients (biases that feed
+        # an instance norm) into +-lr moves, so tolerances loosen after the first update.
+        tol = 2e-5 if it == 0 else 2e-3
+        for k, v in rec["losses"].items():
+            assert abs(losses[k] - v) <= tol * max(1.0, abs(v)), (it, k, losses[k], v)
+        for k, v in rec["gnorms"].items():
+            assert abs(gnorms[k] - v) <= max(tol, 1e-4) * max(1.0, abs(v)), (it, k, gnorms[k], v)
+        for k, v in rec["visuals"].items():
+            assert _rel(_sample(visuals[k], 1025), v) < (1e-4 if it == 0 else 1e-2), (it, k)
+        if it == 0:
+            for key, v in rec["grad_norm"].items():
+                name, k = key.split("/")
+                gr = om.nets[name][k].grad
+                if nets.is_noise_grad(name, k):
+                    assert float(gr.norm()) < 1e-3 and v < 1e-3, key
+                    continue
+                assert abs(float(gr.double().norm()) - v) <= 1e-3 * v + 1e-6, key
+
+
+@pytest.mark.skipif(not lr.available(), reason="/root/reference not present (GPU box)")
+def test_oracle_matches_live_reference_step():
+    warnings.simplefilter("ignore")
+    opt = step.default_opt()
+    state = nets.init_model_state(seed=7, perturb=0.03)
+    ref = lr.build_reference_model(copy.deepcopy(opt), state)
+    om = step.OracleModel(opt, state)
+    a, b, z = step.synthetic_batch(3, seed=99)
+    lo, vo, go = om.train_instance(a, b, z)
+    lr_, vr, gr = ref.train_instance(a, b, z)
+    for k in lo:
+        assert abs(lo[k] - float(lr_[k])) < 2e-5 * max(1.0, abs(lo[k])), k
+    for k in vo:
+        assert (vo[k] - vr[k]).abs().max() < 1e-4, k
+    for k in go:
+        assert abs(go[k] - float(gr[k])) < 1e-4 * max(1.0, abs(go[k])), k
+    # G-side gradients are still in .grad after the step on both sides
+    for name in ("netG_A_B", "netG_B_A", "netE_B"):
+        rp = dict(getattr(ref, name).named_parameters())
+        for k, v in om.params(name):
+            if v.grad is None:
+                assert rp[k].grad is None
+                continue
+            if nets.is_noise_grad(name, k):
+                assert float(v.grad.norm()) < 1e-3 and float(rp[k].grad.norm()) < 1e-3, (name, k)
+                continue
+            scale = float(v.grad.norm()) + 1e-12
+            assert float((v.grad - rp[k].grad).norm()) <= 1e-3 * scale + 1e-6, (name, k)
+
+
+@pytest.mark.skipif(not lr.available(), reason="/root/reference not present (GPU box)")
+def test_state_dict_keys_match_reference():
+    warnings.simplefilter("ignore")
+    opt = step.default_opt()
+    state = nets.init_model_state(seed=1)
+    ref = lr.build_reference_model(copy.deepcopy(opt), state)
+    for name in nets.NET_NAMES:
+        full = set(getattr(ref, name).state_dict().keys())
+        ours = set(state[name].keys())
+        assert ours <= full
+        for k in full - ours:   # only the CINResnetBlock alias keys may be missing
+            assert name == "netG_A_B" and k.split(".")[1] in ("10", "11", "12"), (name, k)
