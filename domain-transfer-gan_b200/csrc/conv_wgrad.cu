@@ -1,0 +1,344 @@
+// Weight gradient as a tcgen05 GEMM whose K dimension is the pixel axis.
+//
+//   dW[a][b][tap] += sum_pixels P[pix][a] * Q[pix*stride + tap - pad][b]
+//
+// Both operands are read straight from the NHWC planes by TMA: a tile of 64 pixels x 128 bytes of
+// channels lands in smem as 64 rows of 128 B (SWIZZLE_128B) = an MN-major UMMA operand (pixels are
+// the K rows).  M = 128 P-channels (two/four 128-byte channel blocks, LBO apart), N = Q channels,
+// one TMEM accumulator [128 x N] per filter tap; a CTA owns a group of taps (<= 512 TMEM columns),
+// one 128-channel M block and a contiguous range of pixel tiles (split-K).  Partial tiles go to a
+// workspace with plain coalesced stores; wgrad_reduce_kernel sums the splits in a fixed order and
+// accumulates into the fp32 PyTorch-layout gradient (deterministic, no atomics).
+#include <algorithm>
+#include <mutex>
+
+#include "common.cuh"
+
+namespace dtg {
+
+constexpr int kWMaxTaps = 64;
+constexpr int kKP = 64;                 // pixels (K rows) per stage
+constexpr int kBlkBytes = kKP * 128;    // one 128-byte-wide channel block of a tile: 8 KB
+constexpr int kWThreads = 192;
+
+struct WgradParams {
+  CUtensorMap tmP;
+  CUtensorMap tmQ[4];
+  int bw, bh, bn;
+  int tiles_w, tiles_h, tiles_n;
+  int tiles_per_split;
+  int ntaps, tpg;
+  short tap_dh[kWMaxTaps], tap_dw[kWMaxTaps];
+  unsigned char tap_map[kWMaxTaps];
+  int nblkA, nblkB;
+  int n_umma;
+  int mtot;  // mblocks * 128
+  int stages, tmem_cols;
+  float* ws;
+};
+
+template <bool TF32>
+__global__ void __launch_bounds__(kWThreads, 1) wgrad_kernel(const __grid_constant__ WgradParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  constexpr int CH = TF32 ? 32 : 64;   // channels per 128-byte row
+  constexpr int UK = TF32 ? 8 : 16;    // pixels consumed per MMA
+  const int split = blockIdx.x, group = blockIdx.y, mblock = blockIdx.z;
+  const int tap0 = group * p.tpg;
+  const int ntl = min(p.tpg, p.ntaps - tap0);
+  const int a_bytes = p.nblkA * kBlkBytes;
+  const int stage_bytes = a_bytes + p.tpg * p.nblkB * kBlkBytes;
+  const int S = p.stages;
+  uint64_t* bar_full = reinterpret_cast<uint64_t*>(smem + S * stage_bytes);
+  uint64_t* bar_empty = bar_full + S;
+  uint64_t* bar_done = bar_empty + S;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bar_done + 1);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&p.tmP);
+    for (int i = 0; i < 4; ++i) tma_prefetch_desc(&p.tmQ[i]);
+  }
+  if (warp == 1) {
+    if (lane == 0) {
+      for (int i = 0; i < S; ++i) {
+        mbar_init(&bar_full[i], 1);
+        mbar_init(&bar_empty[i], 1);
+      }
+      mbar_init(bar_done, 1);
+      mbar_fence_init();
+    }
+    __syncwarp();
+    tmem_alloc(tmem_slot, p.tmem_cols);
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  const int T = p.tiles_w * p.tiles_h * p.tiles_n;
+  const int t_begin = split * p.tiles_per_split;
+  const int t_end = min(T, t_begin + p.tiles_per_split);
+  const uint32_t tx_bytes = (p.nblkA + ntl * p.nblkB) * kBlkBytes;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int tile = t_begin; tile < t_end; ++tile) {
+        int r = tile;
+        const int tw = r % p.tiles_w;
+        r /= p.tiles_w;
+        const int th = r % p.tiles_h;
+        const int tn = r / p.tiles_h;
+        const int a0 = th * p.bh, b0 = tw * p.bw, n0 = tn * p.bn;
+        mbar_wait(&bar_empty[stage], phase ^ 1);
+        uint8_t* s = smem + stage * stage_bytes;
+        mbar_expect_tx(&bar_full[stage], tx_bytes);
+        for (int blk = 0; blk < p.nblkA; ++blk)
+          tma_load_4d(s + blk * kBlkBytes, &p.tmP, &bar_full[stage], mblock * 128 + blk * CH, b0, a0, n0);
+        for (int tl = 0; tl < ntl; ++tl) {
+          const int t = tap0 + tl;
+          for (int blk = 0; blk < p.nblkB; ++blk)
+            tma_load_4d(s + a_bytes + (tl * p.nblkB + blk) * kBlkBytes, &p.tmQ[p.tap_map[t]], &bar_full[stage],
+                        blk * CH, b0 + p.tap_dw[t], a0 + p.tap_dh[t], n0);
+        }
+        if (++stage == S) {
+          stage = 0;
+          phase ^= 1;
+        }
+      }
+    }
+  } else if (warp == 1) {
+    const uint32_t idesc = umma_idesc(TF32 ? 2u : 1u, 1u, 1u, 128, p.n_umma);
+    int stage = 0;
+    uint32_t phase = 0;
+    for (int tile = t_begin; tile < t_end; ++tile) {
+      mbar_wait(&bar_full[stage], phase);
+      tc_fence_after();
+      if (lane == 0) {
+        const uint32_t sa = smem_u32(smem + stage * stage_bytes);
+        for (int tl = 0; tl < ntl; ++tl) {
+          const uint32_t sb = sa + a_bytes + tl * p.nblkB * kBlkBytes;
+#pragma unroll
+          for (int j = 0; j < kKP / UK; ++j) {
+            const uint64_t ad = umma_desc_sw128(sa + j * UK * 128, kBlkBytes, 1024);
+            const uint64_t bd = umma_desc_sw128(sb + j * UK * 128, kBlkBytes, 1024);
+            tc_mma<TF32>(tmem_base + tl * p.n_umma, ad, bd, idesc, (tile > t_begin || j > 0) ? 1u : 0u);
+          }
+        }
+        tc_commit(&bar_empty[stage]);
+      }
+      __syncwarp();
+      if (++stage == S) {
+        stage = 0;
+        phase ^= 1;
+      }
+    }
+    if (lane == 0) tc_commit(bar_done);
+    __syncwarp();
+  } else {
+    const int quad = warp & 3;
+    const int row = quad * 32 + lane;
+    mbar_wait(bar_done, 0);
+    tc_fence_after();
+    const bool any = t_end > t_begin;
+    for (int tl = 0; tl < ntl; ++tl) {
+      const int t = tap0 + tl;
+      float* dst = p.ws + ((static_cast<size_t>(split) * p.ntaps + t) * p.mtot + mblock * 128 + row) * p.n_umma;
+      const uint32_t taddr = tmem_base + (static_cast<uint32_t>(quad * 32) << 16) + tl * p.n_umma;
+      for (int c0 = 0; c0 < p.n_umma; c0 += 16) {
+        uint32_t v[16];
+        tmem_ld16(taddr + c0, v);
+        tmem_ld_wait();
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          float4 o = any ? make_float4(__uint_as_float(v[4 * q]), __uint_as_float(v[4 * q + 1]),
+                                       __uint_as_float(v[4 * q + 2]), __uint_as_float(v[4 * q + 3]))
+                         : make_float4(0.f, 0.f, 0.f, 0.f);
+          reinterpret_cast<float4*>(dst + c0)[q] = o;
+        }
+      }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, p.tmem_cols);
+  }
+}
+
+// dw[(a*qb + b)*ntaps + t] += sum_s ws[((s*ntaps + t)*mtot + a)*n_umma + b]
+__global__ void wgrad_reduce_kernel(const float* __restrict__ ws, float* __restrict__ dw, int splits, int ntaps,
+                                    int mtot, int n_umma, int pa, int qb) {
+  const int total = ntaps * pa * qb;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
+    const int b = i % qb;
+    const int a = (i / qb) % pa;
+    const int t = i / (qb * pa);
+    float acc = 0.f;
+    for (int s = 0; s < splits; ++s) acc += ws[((static_cast<size_t>(s) * ntaps + t) * mtot + a) * n_umma + b];
+    dw[(static_cast<size_t>(a) * qb + b) * ntaps + t] += acc;
+  }
+}
+
+struct WgradPlan {
+  int bw, bh, bn, tiles_w, tiles_h, tiles_n, T;
+  int ntaps, tpg, ngroups, mblocks, nblkA, nblkB, n_umma, stages, tmem_cols, splits, tiles_per_split;
+  size_t ws_bytes;
+};
+
+static int pow2ceil(int v) {
+  int r = 1;
+  while (r < v) r <<= 1;
+  return r;
+}
+
+static int make_plan(const dtg_wgrad_args* a, const dtg_plane* pp, const dtg_plane* q, WgradPlan* pl) {
+  const bool tf32 = pp->dtype == DTG_F32;
+  const int CH = tf32 ? 32 : 64;
+  DTG_REQUIRE(pp->dtype == q->dtype, "wgrad: dtype mismatch");
+  DTG_REQUIRE(a->kh * a->kw <= kWMaxTaps, "wgrad: too many taps");
+  DTG_REQUIRE(a->stride == 1 || a->stride == 2, "wgrad: stride");
+  DTG_REQUIRE(pp->halo == 0, "wgrad: p plane must have halo 0");
+  DTG_REQUIRE(pp->n == q->n, "wgrad: batch mismatch");
+  DTG_REQUIRE((q->h + 2 * a->pad - a->kh) / a->stride + 1 == pp->h && (q->w + 2 * a->pad - a->kw) / a->stride + 1 == pp->w,
+              "wgrad: p extent %dx%d inconsistent with q %dx%d k%d s%d p%d", pp->h, pp->w, q->h, q->w, a->kh, a->stride, a->pad);
+  DTG_REQUIRE(q->halo == 0 || q->halo >= a->pad, "wgrad: q halo %d < pad %d", q->halo, a->pad);
+  DTG_REQUIRE(a->pa <= pp->c && a->qb <= q->c, "wgrad: valid channels exceed plane channels");
+  pl->ntaps = a->kh * a->kw;
+  pl->bw = std::min(pow2ceil(pp->w), kKP);
+  pl->bh = std::min(pow2ceil(pp->h), kKP / pl->bw);
+  pl->bn = kKP / (pl->bw * pl->bh);
+  pl->tiles_w = (pp->w + pl->bw - 1) / pl->bw;
+  pl->tiles_h = (pp->h + pl->bh - 1) / pl->bh;
+  pl->tiles_n = (pp->n + pl->bn - 1) / pl->bn;
+  pl->T = pl->tiles_w * pl->tiles_h * pl->tiles_n;
+  pl->mblocks = (a->pa + 127) / 128;
+  pl->nblkA = 128 / CH;
+  pl->n_umma = (a->qb + CH - 1) / CH * CH;
+  DTG_REQUIRE(pl->n_umma <= 256, "wgrad: q channels %d > 256", a->qb);
+  pl->nblkB = pl->n_umma / CH;
+  const int tmem_max = 512 / pl->n_umma;
+  const int smem_max = (100 * 1024 - pl->nblkA * kBlkBytes) / (pl->nblkB * kBlkBytes);
+  const int tpg_max = std::max(1, std::min(tmem_max, smem_max));
+  pl->ngroups = (pl->ntaps + tpg_max - 1) / tpg_max;
+  pl->tpg = (pl->ntaps + pl->ngroups - 1) / pl->ngroups;
+  pl->ngroups = (pl->ntaps + pl->tpg - 1) / pl->tpg;
+  const int stage_bytes = (pl->nblkA + pl->tpg * pl->nblkB) * kBlkBytes;
+  pl->stages = std::max(2, std::min(6, (200 * 1024) / stage_bytes));
+  int cols = 32;
+  while (cols < pl->tpg * pl->n_umma) cols <<= 1;
+  pl->tmem_cols = cols;
+  int want = std::max(1, 148 / (pl->ngroups * pl->mblocks));
+  want = std::min(want, pl->T);
+  pl->tiles_per_split = (pl->T + want - 1) / want;
+  pl->splits = (pl->T + pl->tiles_per_split - 1) / pl->tiles_per_split;
+  pl->ws_bytes = static_cast<size_t>(pl->splits) * pl->ntaps * pl->mblocks * 128 * pl->n_umma * sizeof(float);
+  return DTG_OK;
+}
+
+static int floordiv2w(int e) { return (e - (e & 1)) / 2; }
+
+}  // namespace dtg
+
+using namespace dtg;
+
+extern "C" size_t dtg_conv_wgrad_workspace_bytes(const dtg_wgrad_args* a, const dtg_plane* p, const dtg_plane* q) {
+  WgradPlan pl;
+  if (!a || !p || !q || make_plan(a, p, q, &pl) != DTG_OK) return 0;
+  return pl.ws_bytes;
+}
+
+extern "C" int dtg_conv_wgrad(const dtg_wgrad_args* a, const dtg_plane* pp, const dtg_plane* q, float* dw,
+                              void* workspace, size_t workspace_bytes, void* stream_) {
+  DTG_REQUIRE(a && pp && q && dw && pp->ptr && q->ptr, "dtg_conv_wgrad: null argument");
+  WgradPlan pl;
+  int rc = make_plan(a, pp, q, &pl);
+  if (rc != DTG_OK) return rc;
+  DTG_REQUIRE(workspace && workspace_bytes >= pl.ws_bytes, "dtg_conv_wgrad: workspace %zu < %zu bytes", workspace_bytes, pl.ws_bytes);
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  const bool tf32 = pp->dtype == DTG_F32;
+  const int es = elem_size(pp->dtype);
+  const int CH = 128 / es;
+
+  WgradParams p;
+  memset(&p, 0, sizeof(p));
+  p.bw = pl.bw; p.bh = pl.bh; p.bn = pl.bn;
+  p.tiles_w = pl.tiles_w; p.tiles_h = pl.tiles_h; p.tiles_n = pl.tiles_n;
+  p.tiles_per_split = pl.tiles_per_split;
+  p.ntaps = pl.ntaps; p.tpg = pl.tpg;
+  p.nblkA = pl.nblkA; p.nblkB = pl.nblkB; p.n_umma = pl.n_umma;
+  p.mtot = pl.mblocks * 128;
+  p.stages = pl.stages; p.tmem_cols = pl.tmem_cols;
+  p.ws = reinterpret_cast<float*>(workspace);
+
+  const int s = a->stride, hl = q->halo;
+  for (int kh = 0; kh < a->kh; ++kh)
+    for (int kw = 0; kw < a->kw; ++kw) {
+      const int t = kh * a->kw + kw;
+      const int eh = kh - a->pad + hl, ew = kw - a->pad + hl;
+      if (s == 1) {
+        p.tap_dh[t] = static_cast<short>(eh);
+        p.tap_dw[t] = static_cast<short>(ew);
+        p.tap_map[t] = 0;
+      } else {
+        p.tap_dh[t] = static_cast<short>(floordiv2w(eh));
+        p.tap_dw[t] = static_cast<short>(floordiv2w(ew));
+        p.tap_map[t] = static_cast<unsigned char>((eh & 1) * 2 + (ew & 1));
+      }
+    }
+  uint32_t box[4] = {static_cast<uint32_t>(CH), static_cast<uint32_t>(pl.bw), static_cast<uint32_t>(pl.bh),
+                     static_cast<uint32_t>(pl.bn)};
+  {
+    uint64_t dims[4] = {static_cast<uint64_t>(pp->c), static_cast<uint64_t>(pp->w), static_cast<uint64_t>(pp->h),
+                        static_cast<uint64_t>(pp->n)};
+    uint64_t strides[3] = {static_cast<uint64_t>(pp->c) * es, static_cast<uint64_t>(pp->w) * pp->c * es,
+                           static_cast<uint64_t>(pp->h) * pp->w * pp->c * es};
+    rc = encode_tiled(&p.tmP, pp->dtype, 4, pp->ptr, dims, strides, box, true);
+    if (rc != DTG_OK) return rc;
+  }
+  const int Hb = q->h + 2 * hl, Wb = q->w + 2 * hl;
+  for (int m = 0; m < 4; ++m) {
+    const int ph = s == 2 ? (m >> 1) : 0, pw = s == 2 ? (m & 1) : 0;
+    uint64_t dims[4] = {static_cast<uint64_t>(q->c), static_cast<uint64_t>(std::max(1, (Wb - pw + s - 1) / s)),
+                        static_cast<uint64_t>(std::max(1, (Hb - ph + s - 1) / s)), static_cast<uint64_t>(q->n)};
+    uint64_t strides[3] = {static_cast<uint64_t>(s) * q->c * es, static_cast<uint64_t>(s) * Wb * q->c * es,
+                           static_cast<uint64_t>(Hb) * Wb * q->c * es};
+    uint8_t* base = reinterpret_cast<uint8_t*>(q->ptr) + (static_cast<size_t>(ph) * Wb + pw) * q->c * es;
+    rc = encode_tiled(&p.tmQ[m], q->dtype, 4, base, dims, strides, box, true);
+    if (rc != DTG_OK) return rc;
+    if (s == 1) {
+      for (int k = 1; k < 4; ++k) p.tmQ[k] = p.tmQ[0];
+      break;
+    }
+  }
+
+  static bool attr_set[2] = {false, false};
+  static std::mutex mu;
+  {
+    std::lock_guard<std::mutex> lk(mu);
+    if (!attr_set[tf32 ? 1 : 0]) {
+      if (tf32)
+        DTG_CHECK_CUDA(cudaFuncSetAttribute(wgrad_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+      else
+        DTG_CHECK_CUDA(cudaFuncSetAttribute(wgrad_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+      attr_set[tf32 ? 1 : 0] = true;
+    }
+  }
+  const int stage_bytes = (pl.nblkA + pl.tpg * pl.nblkB) * kBlkBytes;
+  const size_t smem = static_cast<size_t>(pl.stages) * stage_bytes + 1024 + 256;
+  dim3 grid(pl.splits, pl.ngroups, pl.mblocks);
+  if (tf32)
+    wgrad_kernel<true><<<grid, kWThreads, smem, stream>>>(p);
+  else
+    wgrad_kernel<false><<<grid, kWThreads, smem, stream>>>(p);
+  DTG_CHECK_CUDA(cudaGetLastError());
+  const int total = pl.ntaps * a->pa * a->qb;
+  const int rgrid = std::max(1, std::min((total + 255) / 256, 148 * 8));
+  wgrad_reduce_kernel<<<rgrid, 256, 0, stream>>>(p.ws, dw, pl.splits, pl.ntaps, p.mtot, pl.n_umma, a->pa, a->qb);
+  DTG_CHECK_CUDA(cudaGetLastError());
+  return DTG_OK;
+}

@@ -1,0 +1,210 @@
+// Layout kernels: weight packing for the implicit-GEMM operands, NCHW fp32 <-> NHWC plane
+// conversion at network entry/exit (with reflection halo), gradient fan-in gather (+tanh backward),
+// per-channel sums (bias gradients).  All HBM-bound, coalesced along the contiguous axis.
+#include "common.cuh"
+
+namespace dtg {
+
+template <typename T>
+__device__ __forceinline__ T to_elem(float v);
+template <>
+__device__ __forceinline__ float to_elem<float>(float v) { return v; }
+template <>
+__device__ __forceinline__ __nv_bfloat16 to_elem<__nv_bfloat16>(float v) { return __float2bfloat16_rn(v); }
+
+__device__ __forceinline__ float ld_elem(const void* base, size_t idx, int dtype) {
+  return dtype == DTG_BF16 ? __bfloat162float(reinterpret_cast<const __nv_bfloat16*>(base)[idx])
+                           : reinterpret_cast<const float*>(base)[idx];
+}
+__device__ __forceinline__ void st_elem(void* base, size_t idx, int dtype, float v) {
+  if (dtype == DTG_BF16)
+    reinterpret_cast<__nv_bfloat16*>(base)[idx] = __float2bfloat16_rn(v);
+  else
+    reinterpret_cast<float*>(base)[idx] = v;
+}
+
+// one block-row (blockIdx.y) per item; threads stride over the padded destination
+__global__ void pack_weights_kernel(const dtg_pack_item* items) {
+  const dtg_pack_item it = items[blockIdx.y];
+  const int total = it.taps * it.rows_p * it.cols_p;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
+    const int c = i % it.cols_p;
+    const int r = (i / it.cols_p) % it.rows_p;
+    const int t = i / (it.cols_p * it.rows_p);
+    float v = 0.f;
+    if (r < it.rows && c < it.cols) v = it.src[(static_cast<size_t>(r) * it.srs + static_cast<size_t>(c) * it.scs) * it.taps + t];
+    st_elem(it.dst, i, it.dtype, v);
+  }
+}
+
+// NCHW fp32 -> plane channels [c_off, c_off+c), mirrored into the halo.  One thread per (n,h,w).
+__global__ void pack_nchw_kernel(const float* __restrict__ src, int n, int c, int h, int w, dtg_plane dst, int c_off) {
+  const size_t total = static_cast<size_t>(n) * h * w;
+  const int Hb = dst.h + 2 * dst.halo, Wb = dst.w + 2 * dst.halo;
+  for (size_t i = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; i < total;
+       i += static_cast<size_t>(gridDim.x) * blockDim.x) {
+    const int x = i % w;
+    const int y = (i / w) % h;
+    const int b = i / (static_cast<size_t>(w) * h);
+    int hts[3], wts[3];
+    const int nh = reflect_targets(y, h, dst.halo, hts), nw = reflect_targets(x, w, dst.halo, wts);
+    for (int ch = 0; ch < c; ++ch) {
+      const float v = src[((static_cast<size_t>(b) * c + ch) * h + y) * w + x];
+      for (int a = 0; a < nh; ++a)
+        for (int q = 0; q < nw; ++q) {
+          const size_t pix = (static_cast<size_t>(b) * Hb + hts[a] + dst.halo) * Wb + wts[q] + dst.halo;
+          st_elem(dst.ptr, pix * dst.c + c_off + ch, dst.dtype, v);
+        }
+    }
+  }
+}
+
+__global__ void unpack_nchw_kernel(dtg_plane src, int c_off, int c, float* __restrict__ dst) {
+  const size_t total = static_cast<size_t>(src.n) * src.h * src.w;
+  const int Hb = src.h + 2 * src.halo, Wb = src.w + 2 * src.halo;
+  for (size_t i = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; i < total;
+       i += static_cast<size_t>(gridDim.x) * blockDim.x) {
+    const int x = i % src.w;
+    const int y = (i / src.w) % src.h;
+    const int b = i / (static_cast<size_t>(src.w) * src.h);
+    const size_t pix = (static_cast<size_t>(b) * Hb + y + src.halo) * Wb + x + src.halo;
+    for (int ch = 0; ch < c; ++ch)
+      dst[((static_cast<size_t>(b) * c + ch) * src.h + y) * src.w + x] = ld_elem(src.ptr, pix * src.c + c_off + ch, src.dtype);
+  }
+}
+
+// value of a gradient plane at interior pixel (y,x) channel ch with its halo folded back
+__device__ __forceinline__ float folded_load(const dtg_plane& s, int b, int y, int x, int ch) {
+  const int Hb = s.h + 2 * s.halo, Wb = s.w + 2 * s.halo;
+  int hts[3], wts[3];
+  const int nh = reflect_targets(y, s.h, s.halo, hts), nw = reflect_targets(x, s.w, s.halo, wts);
+  float acc = 0.f;
+  for (int a = 0; a < nh; ++a)
+    for (int q = 0; q < nw; ++q) {
+      const size_t pix = (static_cast<size_t>(b) * Hb + hts[a] + s.halo) * Wb + wts[q] + s.halo;
+      acc += ld_elem(s.ptr, pix * s.c + ch, s.dtype);
+    }
+  return acc;
+}
+
+struct GatherArgs {
+  dtg_plane src[3];
+  int c_off[3];
+  int nsrc;
+};
+
+__global__ void grad_gather_kernel(GatherArgs g, const float* __restrict__ tanh_y, int c, dtg_plane out,
+                                   float* __restrict__ out_nchw) {
+  const int h = out.h, w = out.w;
+  const size_t total = static_cast<size_t>(out.n) * h * w;
+  for (size_t i = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; i < total;
+       i += static_cast<size_t>(gridDim.x) * blockDim.x) {
+    const int x = i % w;
+    const int y = (i / w) % h;
+    const int b = i / (static_cast<size_t>(w) * h);
+    for (int ch = 0; ch < c; ++ch) {
+      float acc = 0.f;
+      for (int k = 0; k < g.nsrc; ++k) acc += folded_load(g.src[k], b, y, x, g.c_off[k] + ch);
+      const size_t di = ((static_cast<size_t>(b) * c + ch) * h + y) * w + x;
+      if (out_nchw) out_nchw[di] = acc;
+      if (tanh_y) {
+        const float t = tanh_y[di];
+        acc *= (1.f - t * t);
+      }
+      if (out.ptr) {
+        const size_t pix = (static_cast<size_t>(b) * (h + 2 * out.halo) + y + out.halo) * (w + 2 * out.halo) + x + out.halo;
+        st_elem(out.ptr, pix * out.c + ch, out.dtype, acc);
+      }
+    }
+  }
+}
+
+// d_bias[c] += sum over pixels; one block per 32 channels x pixel-slab, warp shuffle + atomics-free
+// final pass through a second tiny kernel would be overkill: the tensors this runs on are small
+// (network heads), so a single block per channel group does a fixed-order tree reduction.
+__global__ void channel_sum_kernel(dtg_plane x, int c, float* __restrict__ d_bias) {
+  const int ch = blockIdx.x;
+  if (ch >= c) return;
+  const int Hb = x.h + 2 * x.halo, Wb = x.w + 2 * x.halo;
+  const size_t total = static_cast<size_t>(x.n) * x.h * x.w;
+  float acc = 0.f;
+  for (size_t i = threadIdx.x; i < total; i += blockDim.x) {
+    const int xx = i % x.w;
+    const int yy = (i / x.w) % x.h;
+    const int b = i / (static_cast<size_t>(x.w) * x.h);
+    const size_t pix = (static_cast<size_t>(b) * Hb + yy + x.halo) * Wb + xx + x.halo;
+    acc += ld_elem(x.ptr, pix * x.c + ch, x.dtype);
+  }
+  __shared__ float red[32];
+  for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = acc;
+  __syncthreads();
+  if (threadIdx.x < 32) {
+    float v = threadIdx.x < (blockDim.x >> 5) ? red[threadIdx.x] : 0.f;
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    if (threadIdx.x == 0) d_bias[ch] += v;
+  }
+}
+
+static inline int grid_for(size_t total, int block, int cap = 148 * 16) {
+  size_t g = (total + block - 1) / block;
+  if (g < 1) g = 1;
+  if (g > static_cast<size_t>(cap)) g = cap;
+  return static_cast<int>(g);
+}
+
+}  // namespace dtg
+
+using namespace dtg;
+
+extern "C" int dtg_pack_weights(const dtg_pack_item* items_dev, int nitems, int max_elems, void* stream) {
+  DTG_REQUIRE(items_dev && nitems > 0, "dtg_pack_weights: no items");
+  dim3 grid(grid_for(static_cast<size_t>(max_elems), 256, 64), nitems);
+  pack_weights_kernel<<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(items_dev);
+  DTG_CHECK_CUDA(cudaGetLastError());
+  return DTG_OK;
+}
+
+extern "C" int dtg_pack_nchw(const float* src, int n, int c, int h, int w, const dtg_plane* dst, int c_off, void* stream) {
+  DTG_REQUIRE(src && dst && dst->ptr, "dtg_pack_nchw: null");
+  DTG_REQUIRE(dst->n == n && dst->h == h && dst->w == w && c_off + c <= dst->c, "dtg_pack_nchw: shape mismatch");
+  const size_t total = static_cast<size_t>(n) * h * w;
+  pack_nchw_kernel<<<grid_for(total, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(src, n, c, h, w, *dst, c_off);
+  DTG_CHECK_CUDA(cudaGetLastError());
+  return DTG_OK;
+}
+
+extern "C" int dtg_unpack_nchw(const dtg_plane* src, int c_off, int c, float* dst, void* stream) {
+  DTG_REQUIRE(src && src->ptr && dst && c_off + c <= src->c, "dtg_unpack_nchw: bad args");
+  const size_t total = static_cast<size_t>(src->n) * src->h * src->w;
+  unpack_nchw_kernel<<<grid_for(total, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(*src, c_off, c, dst);
+  DTG_CHECK_CUDA(cudaGetLastError());
+  return DTG_OK;
+}
+
+extern "C" int dtg_grad_gather(const dtg_plane* const* srcs, const int* c_off, int nsrc, const float* tanh_y, int c,
+                               const dtg_plane* out, float* out_nchw, void* stream) {
+  DTG_REQUIRE(srcs && nsrc >= 1 && nsrc <= 3 && out, "dtg_grad_gather: bad args");
+  GatherArgs g;
+  memset(&g, 0, sizeof(g));
+  g.nsrc = nsrc;
+  for (int k = 0; k < nsrc; ++k) {
+    DTG_REQUIRE(srcs[k] && srcs[k]->ptr, "dtg_grad_gather: null source");
+    DTG_REQUIRE(srcs[k]->n == out->n && srcs[k]->h == out->h && srcs[k]->w == out->w && c_off[k] + c <= srcs[k]->c,
+                "dtg_grad_gather: source %d shape mismatch", k);
+    g.src[k] = *srcs[k];
+    g.c_off[k] = c_off[k];
+  }
+  DTG_REQUIRE(out->ptr == nullptr || c <= out->c, "dtg_grad_gather: out channels");
+  const size_t total = static_cast<size_t>(out->n) * out->h * out->w;
+  grad_gather_kernel<<<grid_for(total, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(g, tanh_y, c, *out, out_nchw);
+  DTG_CHECK_CUDA(cudaGetLastError());
+  return DTG_OK;
+}
+
+extern "C" int dtg_channel_sum(const dtg_plane* x, int c, float* d_bias, void* stream) {
+  DTG_REQUIRE(x && x->ptr && d_bias && c <= x->c, "dtg_channel_sum: bad args");
+  channel_sum_kernel<<<c, 256, 0, static_cast<cudaStream_t>(stream)>>>(*x, c, d_bias);
+  DTG_CHECK_CUDA(cudaGetLastError());
+  return DTG_OK;
+}

@@ -1,0 +1,138 @@
+"""Thin Python wrappers over the C ABI: plane tensors, weight packing, conv / wgrad / norm calls.
+
+Everything here only marshals pointers; all arithmetic happens in libdtg_b200.so on the current
+CUDA stream.  Nothing falls back to torch ops.
+"""
+import ctypes as C
+
+import torch
+
+from . import _lib as L
+
+_DT = {torch.bfloat16: L.BF16, torch.float32: L.F32}
+
+
+def _stream():
+    return C.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def _ptr(t):
+    return C.c_void_p(t.data_ptr()) if t is not None else C.c_void_p(0)
+
+
+def cpad(c, dtype):
+    """stored channel count: multiple of 16 bytes, at least 16 channels (UMMA N granularity)."""
+    return max(16, (c + 15) // 16 * 16)
+
+
+class PlaneT:
+    """NHWC activation / gradient buffer with optional halo ring: tensor [n, h+2*halo, w+2*halo, c]."""
+
+    __slots__ = ("t", "n", "h", "w", "c", "halo", "dtype", "_s")
+
+    def __init__(self, n, h, w, c, halo=0, dtype=torch.bfloat16, device="cuda"):
+        self.n, self.h, self.w, self.c, self.halo, self.dtype = n, h, w, c, halo, dtype
+        self.t = torch.zeros(n, h + 2 * halo, w + 2 * halo, c, dtype=dtype, device=device)
+        self._s = L.Plane(self.t.data_ptr(), n, h, w, c, halo, _DT[dtype])
+
+    @property
+    def s(self):
+        return C.byref(self._s)
+
+    def interior(self):
+        hl = self.halo
+        return self.t[:, hl:hl + self.h, hl:hl + self.w, :]
+
+    def to_nchw(self, c=None):
+        return self.interior()[..., :c].permute(0, 3, 1, 2).float().contiguous()
+
+    @staticmethod
+    def from_nchw(x, halo=0, dtype=torch.bfloat16, c_store=None, reflect=True):
+        """test helper: build a plane from an NCHW tensor through the library's own pack kernel."""
+        n, c, h, w = x.shape
+        p = PlaneT(n, h, w, c_store or cpad(c, dtype), halo, dtype, x.device)
+        pack_nchw(x.float().contiguous(), p, 0)
+        return p
+
+
+NULL_PLANE = C.POINTER(L.Plane)()
+
+
+def pack_nchw(src, dst, c_off=0):
+    n, c, h, w = src.shape
+    assert src.dtype == torch.float32 and src.is_contiguous()
+    L.check(L.lib().dtg_pack_nchw(_ptr(src), n, c, h, w, dst.s, c_off, _stream()), "pack_nchw")
+
+
+def unpack_nchw(src, c, c_off=0, out=None):
+    if out is None:
+        out = torch.empty(src.n, c, src.h, src.w, dtype=torch.float32, device=src.t.device)
+    L.check(L.lib().dtg_unpack_nchw(src.s, c_off, c, _ptr(out), _stream()), "unpack_nchw")
+    return out
+
+
+class PackTable:
+    """Device-resident table of weight-pack items; one launch repacks every conv weight of a network."""
+
+    def __init__(self, device="cuda"):
+        self.items = []
+        self.keep = []
+        self.dev = None
+        self.max_elems = 0
+        self.device = device
+
+    def add(self, src, rows, cols, taps, srs, scs, dtype):
+        """src: fp32 tensor (PyTorch layout, contiguous).  Returns the packed destination tensor
+        [taps, rows_p, cols_p] with dst[t][r][c] = src.flat[(r*srs + c*scs)*taps + t]."""
+        rows_p = max(16, (rows + 15) // 16 * 16)
+        q = 8 if dtype == torch.bfloat16 else 4
+        cols_p = (cols + q - 1) // q * q
+        dst = torch.zeros(taps, rows_p, cols_p, dtype=dtype, device=self.device)
+        self.items.append(L.PackItem(src.data_ptr(), dst.data_ptr(), rows, rows_p, cols, cols_p, taps, srs, scs,
+                                     _DT[dtype]))
+        self.keep.append((src, dst))
+        self.max_elems = max(self.max_elems, dst.numel())
+        self.dev = None
+        return dst
+
+    def run(self):
+        if not self.items:
+            return
+        if self.dev is None:
+            arr = (L.PackItem * len(self.items))(*self.items)
+            raw = torch.frombuffer(bytearray(bytes(arr)), dtype=torch.uint8).clone()
+            self.dev = raw.to(self.device)
+        L.check(L.lib().dtg_pack_weights(_ptr(self.dev), len(self.items), self.max_elems, _stream()), "pack_weights")
+
+
+def pack_conv_weight(w, dtype, kind):
+    """Convenience (tests / small modules): pack one weight immediately.
+    kind: 'fwd'   conv weight [co,ci,kh,kw]  -> rows co, cols ci        (Conv2d forward)
+          'dgrad' conv weight [co,ci,kh,kw]  -> rows ci, cols co        (Conv2d data gradient)
+          'tfwd'  convT weight [ci,co,kh,kw] -> rows co, cols ci        (ConvTranspose2d forward)
+          'tdgrad' convT weight [ci,co,kh,kw]-> rows ci, cols co        (ConvTranspose2d data gradient)"""
+    tab = PackTable(w.device)
+    dst = add_packed(tab, w, dtype, kind)
+    tab.run()
+    return dst
+
+
+def add_packed(tab, w, dtype, kind):
+    d0, d1, kh, kw = w.shape
+    taps = kh * kw
+    if kind in ("fwd", "tdgrad"):      # rows = dim0, cols = dim1
+        return tab.add(w, d0, d1, taps, d1, 1, dtype)
+    if kind in ("dgrad", "tfwd"):      # rows = dim1, cols = dim0
+        return tab.add(w, d1, d0, taps, 1, d1, dtype)
+    raise ValueError(kind)
+
+
+def conv(x, wp, bias, out, *, mode=L.CONV_FWD, kh, kw, stride=1, pad=0, ring=0, act=L.ACT_NONE, cout,
+         out_h, out_w, out_reflect=False, out_nchw=None):
+    """x: PlaneT; wp: packed weight [taps, rows_p, cols_p]; out: PlaneT or None with out_nchw fp32 tensor."""
+    a = L.ConvArgs(mode, kh, kw, stride, pad, ring, act, cout, 1 if out_nchw is not None else 0,
+                   1 if out_reflect else 0, out_h, out_w)
+    assert wp.shape[0] == kh * kw
+    rc = L.lib().dtg_conv(C.byref(a), x.s, _ptr(wp), wp.shape[1], wp.shape[2], _ptr(bias),
+                          out.s if out is not None else NULL_PLANE, _ptr(out_nchw), _stream())
+    L.check(rc, "conv")

@@ -1,0 +1,222 @@
+/* dtg_b200.h -- C ABI of the B200-native (sm_100a) Augmented-CycleGAN hot-path kernels.
+ *
+ * The reference (adrianalbert/domain-transfer-GAN) has NO FFI / plugin interface: its seam is the
+ * Python nn.Module API and every arithmetic op is a PyTorch library call.  Each entry point below
+ * names the reference call site(s) whose library kernel it replaces (paths relative to
+ * /root/reference/augmented_cyclegan/).  The Python modules in domain-transfer-gan_b200/ bind these
+ * with ctypes (see INTEGRATION.md for the stub a reference maintainer would add).
+ *
+ * Conventions
+ *  - extern "C", plain structs, raw device pointers, no C++ types; every function returns int:
+ *    0 = DTG_OK, <0 = error; message via dtg_last_error().  Never aborts, never throws.
+ *  - The caller owns ALL device memory (activations, workspaces, statistics).  The library keeps no
+ *    device state; work is enqueued on the caller's stream without synchronisation, so every call
+ *    is CUDA-graph capturable.  `stream` is a cudaStream_t passed as void*.
+ *  - Activations are "planes": NHWC with an optional halo ring, element type bf16 or fp32
+ *    (fp32 planes feed tcgen05 kind::tf32).  Buffer shape [n][h+2*halo][w+2*halo][c]; c*elsize must
+ *    be a multiple of 16 bytes and ptr 128-byte aligned.  A halo > 0 holds MATERIALISED padding
+ *    (reflection padding written by the producer); zero padding needs no halo (TMA out-of-bounds
+ *    fill).
+ */
+#ifndef DTG_B200_H_
+#define DTG_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define DTG_VERSION 100
+
+enum { DTG_OK = 0, DTG_ERR_INVALID = -1, DTG_ERR_CUDA = -2, DTG_ERR_UNSUPPORTED = -3 };
+enum { DTG_BF16 = 0, DTG_F32 = 1 };
+enum { DTG_ACT_NONE = 0, DTG_ACT_RELU = 1, DTG_ACT_LRELU = 2, DTG_ACT_TANH = 3 };
+/* DTG_NORM_INSTANCE: biased variance (modules.py:83-97); DTG_NORM_COND_INSTANCE: unbiased variance,
+ * per-sample affine (modules.py:120-132); DTG_NORM_BATCH: nn.BatchNorm{1,2}d training mode
+ * (networks.py:407-415,450-462); DTG_NORM_NONE: activation only. */
+enum { DTG_NORM_NONE = 0, DTG_NORM_INSTANCE = 1, DTG_NORM_COND_INSTANCE = 2, DTG_NORM_BATCH = 3 };
+enum { DTG_CONV_FWD = 0, DTG_CONV_DGRAD = 1 };
+
+typedef struct dtg_plane {
+  void* ptr;
+  int32_t n, h, w, c; /* interior extents; c = stored (padded) channels */
+  int32_t halo;
+  int32_t dtype; /* DTG_BF16 / DTG_F32 */
+} dtg_plane;
+
+int dtg_version(void);
+/* copies the calling thread's last error message (NUL terminated) into buf; returns its length */
+int dtg_last_error(char* buf, size_t cap);
+
+/* ---------------------------------------------------------------------------------------------
+ * Weight packing.  Replaces cuDNN's internal filter transforms for nn.Conv2d / nn.ConvTranspose2d /
+ * nn.Linear weights (networks.py:159-188,211-243,322-337,366-381,405-419,446-471).
+ * dst[t][r][c] (rows padded to rows_p with zeros, cols to cols_p) = src[(r*srs + c*scs)*taps + t]
+ * for r < rows, c < cols.  One item per launch-y; items live in DEVICE memory.
+ * ------------------------------------------------------------------------------------------- */
+typedef struct dtg_pack_item {
+  const float* src;
+  void* dst;
+  int32_t rows, rows_p, cols, cols_p, taps, srs, scs, dtype;
+} dtg_pack_item;
+int dtg_pack_weights(const dtg_pack_item* items_dev, int nitems, int max_elems, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * Implicit-GEMM convolution on tcgen05 tensor cores (TMA-staged NHWC tiles, TMEM accumulators).
+ *   DTG_CONV_FWD  : y = act(conv(x, w) + bias)            nn.Conv2d forward
+ *                   (modules.py:162,180,211,227; networks.py:160-187,212-242,322-337,366-381,446-471)
+ *                   and the data gradient of nn.ConvTranspose2d.
+ *   DTG_CONV_DGRAD: dx = conv_transpose(dy, w)            cuDNN dgrad of the above, and the FORWARD
+ *                   of nn.ConvTranspose2d(k3,s2,p1,op1) (networks.py:178-179,231-234); stride-2 is
+ *                   computed as 4 output-parity sub-convolutions (no zero insertion).
+ * `w` is packed by dtg_pack_weights as [kh*kw][w_rows][w_cols]: rows = GEMM-N (output channels of
+ * THIS call, multiple of 16), cols = GEMM-K per tap (input channels of this call).  The tap index
+ * is always kh*KW+kw of the underlying correlation (no flipping in memory).
+ * in.halo > 0 means the padding is materialised in the halo (must be >= pad for FWD).
+ * DGRAD `ring`: also compute `ring` halo rings of the output (gradient w.r.t. a reflect-padded
+ * input; the consumer folds them back); out.halo must be >= ring.
+ * Output: a plane (dtype of `in`), optionally mirrored into its halo (out_reflect, reflection
+ * padding for the next conv), or a dense fp32 NCHW tensor [n][cout][oh][ow] (out_nchw_f32 = 1,
+ * cout <= 16).
+ * ------------------------------------------------------------------------------------------- */
+typedef struct dtg_conv_args {
+  int32_t mode; /* DTG_CONV_FWD / DTG_CONV_DGRAD */
+  int32_t kh, kw, stride, pad;
+  int32_t ring;         /* DGRAD only */
+  int32_t act;          /* DTG_ACT_* applied after bias */
+  int32_t cout;         /* valid output channels (<= w_rows) */
+  int32_t out_nchw_f32; /* 1: `out_nchw` is used instead of `out` */
+  int32_t out_reflect;  /* 1: mirror results into out.halo */
+  int32_t out_h, out_w; /* interior output extents (validated against the geometry) */
+} dtg_conv_args;
+int dtg_conv(const dtg_conv_args* a, const dtg_plane* in, const void* w, int w_rows, int w_cols,
+             const float* bias, const dtg_plane* out, float* out_nchw, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * Weight gradient (cuDNN wgrad of nn.Conv2d / nn.ConvTranspose2d / nn.Linear backward):
+ *   dw[a][b][kh][kw] += sum_{n,oh,ow} p[n,oh,ow,a] * q[n, oh*stride+kh-pad, ow*stride+kw-pad, b]
+ * p = low-resolution side (dy of a conv; x of a transposed conv), q = high-resolution side
+ * (x of a conv incl. its materialised halo; dy of a transposed conv).  a < pa, b < qb valid channels.
+ * tcgen05 GEMM with pixels as the K dimension (both operands MN-major), split-K over pixel tiles into
+ * `workspace`, then a deterministic fixed-order reduction that accumulates into dw (fp32, PyTorch
+ * layout [a][b][kh][kw]).
+ * ------------------------------------------------------------------------------------------- */
+typedef struct dtg_wgrad_args {
+  int32_t kh, kw, stride, pad;
+  int32_t pa, qb; /* valid channel counts */
+} dtg_wgrad_args;
+size_t dtg_conv_wgrad_workspace_bytes(const dtg_wgrad_args* a, const dtg_plane* p, const dtg_plane* q);
+int dtg_conv_wgrad(const dtg_wgrad_args* a, const dtg_plane* p, const dtg_plane* q, float* dw,
+                   void* workspace, size_t workspace_bytes, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * Fused normalisation + affine + activation (+ residual add) forward.  Replaces the ~9-12 ATen
+ * kernels per layer of InstanceNorm.forward (modules.py:83-97), CondInstanceNorm.forward
+ * (modules.py:120-132), nn.BatchNorm{1,2}d, the following ReLU / LeakyReLU(0.2), the residual
+ * `relu(x + out)` (modules.py:186-187,233-234) and nn.ReflectionPad2d of the next conv's input
+ * (modules.py:152,172,203,219).
+ *   x      : conv output plane (halo 0)
+ *   gamma / beta: INSTANCE: [c] params (scale, shift); COND_INSTANCE: [n][c] post-ReLU affine from
+ *            dtg_cin_affine_fwd; BATCH: [c] (weight, bias); NONE: ignored
+ *   stats  : out, [n][c][2] fp32 (mean, rstd) saved for backward (BATCH: replicated over n)
+ *   coef   : out, [n][c][2] fp32 workspace (a, b) with y = act(x*a + b (+ residual))
+ *   partial: workspace, dtg_norm_workspace_bytes()
+ *   bn_running: BATCH only, [2][c] (running_mean, running_var) updated with `momentum`
+ *   phase  : 0 = everything; 1 = statistics partial sums only (BATCH: leaves [c][2] (sum, sumsq)
+ *            in `partial` for a cross-GPU all-reduce); 2 = finalise + apply (count_scale = world size)
+ * out: plane of the same dtype; if out.halo > 0 the result is mirrored into the halo (reflection).
+ * ------------------------------------------------------------------------------------------- */
+typedef struct dtg_norm_args {
+  int32_t mode; /* DTG_NORM_* */
+  int32_t act;  /* DTG_ACT_NONE / RELU / LRELU */
+  float eps;
+  float momentum;     /* BATCH */
+  int32_t phase;      /* 0 / 1 / 2 */
+  int32_t world_size; /* BATCH phase 2: statistics were summed over this many ranks */
+} dtg_norm_args;
+size_t dtg_norm_workspace_bytes(const dtg_plane* x);
+int dtg_norm_fwd(const dtg_norm_args* a, const dtg_plane* x, const dtg_plane* residual, const float* gamma,
+                 const float* beta, float* bn_running, float* stats, float* coef, float* partial,
+                 const dtg_plane* out, void* stream);
+
+/* Backward of dtg_norm_fwd.  g = (fold(dy) + dy2) * act'(y);  dx = rstd*gamma*(g - mean(g) -
+ * xhat*sum(g*xhat)/d)  (SURVEY.md 9.1);  d_residual = g.
+ *   dy     : gradient w.r.t. the output plane; if dy.halo > 0 the halo holds gradient of the
+ *            reflect-padded copy and is folded back (reflection_pad2d_backward)
+ *   dy2    : optional second gradient contribution (halo 0), e.g. the residual branch
+ *   y      : saved forward output (interior is read for the activation mask)
+ *   x      : saved conv output; stats: saved (mean, rstd)
+ *   sums   : out [n][c][2] fp32: (sum g, sum g*xhat) per (n,c)  -> COND_INSTANCE d_shift/d_scale;
+ *            INSTANCE / BATCH / NONE additionally accumulate d_beta[c] += sum_n, d_gamma[c] += sum_n
+ *            (NONE: d_beta only = bias gradient of the preceding conv)
+ *   dx     : out plane (halo 0); d_res: optional out plane (halo 0)
+ *   phase  : as in forward (BATCH: 1 leaves per-channel sums in `partial` for all-reduce)
+ * ------------------------------------------------------------------------------------------- */
+int dtg_norm_bwd(const dtg_norm_args* a, const dtg_plane* dy, const dtg_plane* dy2, const dtg_plane* y,
+                 const dtg_plane* x, const float* stats, const float* gamma, float* sums, float* d_gamma,
+                 float* d_beta, float* partial, const dtg_plane* dx, const dtg_plane* d_res, void* stream);
+
+/* CondInstanceNorm z-projections (modules.py:111-118,123-124): gamma = relu(Ws z + bs),
+ * beta = relu(Wb z + bb), z [n][nz], W [c][nz], out [n][c].  Backward consumes `sums` of
+ * dtg_norm_bwd and accumulates dWs, dbs, dWb, dbb and dz (+=). */
+int dtg_cin_affine_fwd(const float* z, const float* ws, const float* bs, const float* wb, const float* bb,
+                       int n, int c, int nz, float* gamma, float* beta, void* stream);
+int dtg_cin_affine_bwd(const float* z, const float* ws, const float* wb, const float* gamma, const float* beta,
+                       const float* sums, int n, int c, int nz, float* d_ws, float* d_bs, float* d_wb,
+                       float* d_bb, float* d_z, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * Layout conversion at network entry/exit (the reference tensors are fp32 NCHW, dataloader.py:33):
+ * dtg_pack_nchw writes channels [c_off, c_off+c) of `dst` from a dense NCHW fp32 tensor (this is
+ * also torch.cat on channels, model.py:410,472) and mirrors them into dst.halo (ReflectionPad2d(3),
+ * networks.py:159,211).  dtg_unpack_nchw is the inverse for the interior.
+ * ------------------------------------------------------------------------------------------- */
+int dtg_pack_nchw(const float* src, int n, int c, int h, int w, const dtg_plane* dst, int c_off, void* stream);
+int dtg_unpack_nchw(const dtg_plane* src, int c_off, int c, float* dst, void* stream);
+
+/* Sum of up to 3 gradient planes (each optionally with a halo to fold, channel offset c_off[i]),
+ * optionally multiplied by tanh'(y) = 1 - y^2 (y dense NCHW fp32, the generator output), written to
+ * `out` channels [0,c).  Implements autograd's fan-in accumulation for fake_A / fake_B
+ *  fused with Tanh backward (networks.py:188,243).  Also emits the dense NCHW fp32
+ * gradient if out_nchw != NULL. */
+int dtg_grad_gather(const dtg_plane* const* srcs, const int* c_off, int nsrc, const float* tanh_y, int c,
+                    const dtg_plane* out, float* out_nchw, void* stream);
+
+/* per-channel sum over (n,h,w) of a plane's interior: d_bias[c] += sum  (conv bias gradients) */
+int dtg_channel_sum(const dtg_plane* x, int c, float* d_bias, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * Fused losses (model.py:56-72, 327-334, 432-439, 458-505): each call reduces one term into
+ * `scalars` (device fp32 vector) and writes the seed gradient for the backward pass.
+ *   dtg_loss_lsgan : scalars[slot_loss] = mean((pred-target)^2), scalars[slot_mean] = mean(pred)
+ *                    (slot < 0 skips);  dpred(plane, channel 0) = grad_scale * 2 (pred-target) / count
+ *   dtg_loss_l1    : scalars[slot_loss] = mean|a-b|;  da(plane, channels [0,c)) =
+ *                    grad_scale * sign(a-b)/count * (tanh_bwd ? 1-a^2 : 1); a, b dense NCHW fp32.
+ *                    slot_aux >= 0: scalars[slot_aux] = mean over n of 0.5*sum_c a^2 (kld_std_guss with
+ *                    logvar = 0, model.py:45-53,419,490), slots aux+1 / aux+2 = min(a) / max(a).
+ * `workspace`: >= 4 KB zero-initialised once by the caller (self-resetting).
+ * ------------------------------------------------------------------------------------------- */
+int dtg_loss_lsgan(const float* pred, int n, int h, int w, float target, float grad_scale, float* scalars,
+                   int slot_loss, int slot_mean, const dtg_plane* dpred, void* workspace, void* stream);
+int dtg_loss_l1(const float* a, const float* b, int n, int c, int h, int w, float grad_scale, int tanh_bwd,
+                float* scalars, int slot_loss, int slot_aux, const dtg_plane* da, void* workspace, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * clip_grad_norm + Adam over one flat fp32 arena (model.py:447-452,510-515; torch.optim.Adam,
+ * betas (beta1, 0.999), eps 1e-8):  dtg_grad_sumsq writes sum(g^2) to *out_sumsq (deterministic
+ * two-stage); dtg_adam_clip scales g by min(1, max_norm/(sqrt(sumsq)+1e-6)) IN PLACE (so .grad holds
+ * the clipped gradient like the reference) and applies Adam.  hyper (device): [lr, beta1, beta2, eps,
+ * max_norm]; step_dev: device int32 step counter (already incremented for this step).
+ * grad_scale multiplies g before everything (1/world_size after an all-reduce SUM).
+ * ------------------------------------------------------------------------------------------- */
+int dtg_grad_sumsq(const float* g, size_t count, float grad_scale, float* out_sumsq, void* workspace, void* stream);
+int dtg_adam_clip(float* p, float* g, float* m, float* v, size_t count, const float* hyper, const float* sumsq,
+                  const int32_t* step_dev, float grad_scale, void* stream);
+int dtg_step_increment(int32_t* step_dev, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* DTG_B200_H_ */
