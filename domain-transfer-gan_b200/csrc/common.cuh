@@ -36,7 +36,7 @@ int cu_fail(CUresult e, const char* what);
 // Tensor-map encode through the driver entry point (no link-time libcuda dependency).
 int encode_tiled(CUtensorMap* map, int dtype, int rank, void* base, const uint64_t* dims,
                  const uint64_t* strides_bytes /* rank-1 entries */, const uint32_t* box,
-                 bool swizzle128);
+                 int swizzle /* 0 none, 1 = 128B (16-byte atoms), 2 = 128B with 32-byte atoms */);
 
 static inline int elem_size(int dtype) { return dtype == DTG_BF16 ? 2 : 4; }
 
@@ -161,13 +161,16 @@ __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.
 // K-major operand (rows = M/N index, 128 B of K per row): SBO = 1024 between 8-row groups.
 // MN-major operand (rows = K index, 128 B of M/N per row): LBO = byte stride between 128-B-wide
 // M/N blocks, SBO = 1024 between 8-row (K) groups.
-__device__ __forceinline__ uint64_t umma_desc_sw128(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+// layout_type: 2 = SWIZZLE_128B (16-byte swizzle atoms); 1 = SWIZZLE_128B_BASE32B (32-byte atoms, the
+// only layout tcgen05 accepts for MN-major 32-bit (tf32) operands: 4-row K groups, SBO = 512).
+__device__ __forceinline__ uint64_t umma_desc_sw128(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes,
+                                                    uint32_t layout_type = 2) {
   uint64_t d = 0;
   d |= static_cast<uint64_t>((saddr & 0x3FFFF) >> 4);
   d |= static_cast<uint64_t>((lbo_bytes >> 4) & 0x3FFF) << 16;
   d |= static_cast<uint64_t>((sbo_bytes >> 4) & 0x3FFF) << 32;
   d |= 1ull << 46;  // descriptor version (Blackwell)
-  d |= 2ull << 61;  // layout type SWIZZLE_128B
+  d |= static_cast<uint64_t>(layout_type) << 61;
   return d;
 }
 // instruction descriptor: fp32 accumulate, A/B format (1 = bf16, 2 = tf32), majors (0 = K, 1 = MN)

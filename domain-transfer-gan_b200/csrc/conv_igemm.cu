@@ -455,7 +455,7 @@ extern "C" int dtg_conv(const dtg_conv_args* a, const dtg_plane* in, const void*
     uint32_t box[4] = {static_cast<uint32_t>(KC), static_cast<uint32_t>(p.bw), static_cast<uint32_t>(p.bh),
                        static_cast<uint32_t>(p.bn)};
     uint8_t* base = reinterpret_cast<uint8_t*>(in->ptr) + (static_cast<size_t>(ph) * Wb + pw) * in->c * es;
-    int rc = encode_tiled(&p.tmA[m], in->dtype, 4, base, dims, strides, box, true);
+    int rc = encode_tiled(&p.tmA[m], in->dtype, 4, base, dims, strides, box, 1);
     if (rc != DTG_OK) return rc;
     if (!fwd_s2) {
       for (int k = 1; k < 4; ++k) p.tmA[k] = p.tmA[0];
@@ -466,7 +466,7 @@ extern "C" int dtg_conv(const dtg_conv_args* a, const dtg_plane* in, const void*
     uint64_t dims[2] = {static_cast<uint64_t>(w_cols), static_cast<uint64_t>(w_rows) * a->kh * a->kw};
     uint64_t strides[1] = {static_cast<uint64_t>(w_cols) * es};
     uint32_t box[2] = {static_cast<uint32_t>(KC), static_cast<uint32_t>(w_rows)};
-    int rc = encode_tiled(&p.tmB, in->dtype, 2, const_cast<void*>(w), dims, strides, box, true);
+    int rc = encode_tiled(&p.tmB, in->dtype, 2, const_cast<void*>(w), dims, strides, box, 1);
     if (rc != DTG_OK) return rc;
   }
 

@@ -122,8 +122,8 @@ __global__ void __launch_bounds__(kWThreads, 1) wgrad_kernel(const __grid_consta
           const uint32_t sb = sa + a_bytes + tl * p.nblkB * kBlkBytes;
 #pragma unroll
           for (int j = 0; j < kKP / UK; ++j) {
-            const uint64_t ad = umma_desc_sw128(sa + j * UK * 128, kBlkBytes, 1024);
-            const uint64_t bd = umma_desc_sw128(sb + j * UK * 128, kBlkBytes, 1024);
+            const uint64_t ad = umma_desc_sw128(sa + j * UK * 128, kBlkBytes, TF32 ? 512 : 1024, TF32 ? 1 : 2);
+            const uint64_t bd = umma_desc_sw128(sb + j * UK * 128, kBlkBytes, TF32 ? 512 : 1024, TF32 ? 1 : 2);
             tc_mma<TF32>(tmem_base + tl * p.n_umma, ad, bd, idesc, (tile > t_begin || j > 0) ? 1u : 0u);
           }
         }
@@ -297,7 +297,7 @@ extern "C" int dtg_conv_wgrad(const dtg_wgrad_args* a, const dtg_plane* pp, cons
                         static_cast<uint64_t>(pp->n)};
     uint64_t strides[3] = {static_cast<uint64_t>(pp->c) * es, static_cast<uint64_t>(pp->w) * pp->c * es,
                            static_cast<uint64_t>(pp->h) * pp->w * pp->c * es};
-    rc = encode_tiled(&p.tmP, pp->dtype, 4, pp->ptr, dims, strides, box, true);
+    rc = encode_tiled(&p.tmP, pp->dtype, 4, pp->ptr, dims, strides, box, tf32 ? 2 : 1);
     if (rc != DTG_OK) return rc;
   }
   const int Hb = q->h + 2 * hl, Wb = q->w + 2 * hl;
@@ -308,7 +308,7 @@ extern "C" int dtg_conv_wgrad(const dtg_wgrad_args* a, const dtg_plane* pp, cons
     uint64_t strides[3] = {static_cast<uint64_t>(s) * q->c * es, static_cast<uint64_t>(s) * Wb * q->c * es,
                            static_cast<uint64_t>(Hb) * Wb * q->c * es};
     uint8_t* base = reinterpret_cast<uint8_t*>(q->ptr) + (static_cast<size_t>(ph) * Wb + pw) * q->c * es;
-    rc = encode_tiled(&p.tmQ[m], q->dtype, 4, base, dims, strides, box, true);
+    rc = encode_tiled(&p.tmQ[m], q->dtype, 4, base, dims, strides, box, tf32 ? 2 : 1);
     if (rc != DTG_OK) return rc;
     if (s == 1) {
       for (int k = 1; k < 4; ++k) p.tmQ[k] = p.tmQ[0];

@@ -1,8 +1,6 @@
 // TEMPORARY stubs while kernels are being brought up (removed once implemented).
 #include "common.cuh"
 #define STUB(name, ...) extern "C" int name(__VA_ARGS__) { dtg::set_error(#name ": not implemented yet"); return DTG_ERR_UNSUPPORTED; }
-extern "C" size_t dtg_conv_wgrad_workspace_bytes(const dtg_wgrad_args*, const dtg_plane*, const dtg_plane*) { return 0; }
-STUB(dtg_conv_wgrad, const dtg_wgrad_args*, const dtg_plane*, const dtg_plane*, float*, void*, size_t, void*)
 extern "C" size_t dtg_norm_workspace_bytes(const dtg_plane*) { return 0; }
 STUB(dtg_norm_fwd, const dtg_norm_args*, const dtg_plane*, const dtg_plane*, const float*, const float*, float*, float*, float*, float*, const dtg_plane*, void*)
 STUB(dtg_norm_bwd, const dtg_norm_args*, const dtg_plane*, const dtg_plane*, const dtg_plane*, const dtg_plane*, const float*, const float*, float*, float*, float*, float*, const dtg_plane*, const dtg_plane*, void*)

@@ -136,3 +136,28 @@ def conv(x, wp, bias, out, *, mode=L.CONV_FWD, kh, kw, stride=1, pad=0, ring=0, 
     rc = L.lib().dtg_conv(C.byref(a), x.s, _ptr(wp), wp.shape[1], wp.shape[2], _ptr(bias),
                           out.s if out is not None else NULL_PLANE, _ptr(out_nchw), _stream())
     L.check(rc, "conv")
+
+
+_ws_cache = {}
+
+
+def workspace(nbytes, device="cuda", tag="default"):
+    """Grow-only scratch buffer per (device, tag); contents are never assumed to persist."""
+    key = (str(device), tag)
+    t = _ws_cache.get(key)
+    if t is None or t.numel() < nbytes:
+        t = torch.empty(max(nbytes, 1 << 20), dtype=torch.uint8, device=device)
+        _ws_cache[key] = t
+    return t
+
+
+def conv_wgrad(p, q, dw, *, kh, kw, stride=1, pad=0, pa, qb, ws=None):
+    """dw[a][b][kh][kw] += sum_pix p[pix][a] * q[pix*stride + tap - pad][b]; dw fp32 contiguous."""
+    a = L.WgradArgs(kh, kw, stride, pad, pa, qb)
+    need = L.lib().dtg_conv_wgrad_workspace_bytes(C.byref(a), p.s, q.s)
+    if need == 0:
+        raise RuntimeError("dtg_b200 conv_wgrad: invalid geometry: " + L.last_error())
+    if ws is None:
+        ws = workspace(need, dw.device, "wgrad")
+    assert dw.dtype == torch.float32 and dw.is_contiguous() and dw.numel() == pa * qb * kh * kw
+    L.check(L.lib().dtg_conv_wgrad(C.byref(a), p.s, q.s, _ptr(dw), _ptr(ws), ws.numel(), _stream()), "conv_wgrad")
