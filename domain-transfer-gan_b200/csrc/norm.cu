@@ -1,0 +1,606 @@
+// Fused (conditional) instance / batch normalisation + affine + activation (+ residual, + reflect
+// halo) forward and backward on NHWC planes.  HBM-bound: every pass streams 16-byte vectors along the
+// contiguous channel axis; statistics are reduced with a fixed-order block reduction (deterministic,
+// no atomics).  Formulas: SURVEY.md 9.1 (verified against autograd in fp64).
+//
+// forward : stats pass (read x) -> finalize ([n][c] coefficients) -> apply pass (read x, write y)
+// backward: reduce pass (read dy,y,x) -> finalize -> apply pass (read dy,y,x, write dx [, d_res])
+#include <algorithm>
+
+#include "common.cuh"
+
+namespace dtg {
+
+constexpr int kNormThreads = 256;
+constexpr int kMaxSplits = 16;
+
+template <typename T>
+struct Vec;
+template <>
+struct Vec<__nv_bfloat16> {
+  static constexpr int N = 8;
+  __device__ static __forceinline__ void load(const void* p, float (&f)[8]) {
+    const uint4 u = *reinterpret_cast<const uint4*>(p);
+    const uint32_t w[4] = {u.x, u.y, u.z, u.w};
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      f[2 * i] = __uint_as_float(w[i] << 16);
+      f[2 * i + 1] = __uint_as_float(w[i] & 0xFFFF0000u);
+    }
+  }
+  __device__ static __forceinline__ void store(void* p, const float (&f)[8]) {
+    uint32_t w[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      __nv_bfloat162 h = __floats2bfloat162_rn(f[2 * i], f[2 * i + 1]);
+      w[i] = *reinterpret_cast<uint32_t*>(&h);
+    }
+    *reinterpret_cast<uint4*>(p) = make_uint4(w[0], w[1], w[2], w[3]);
+  }
+};
+template <>
+struct Vec<float> {
+  static constexpr int N = 4;
+  __device__ static __forceinline__ void load(const void* p, float (&f)[4]) {
+    const float4 u = *reinterpret_cast<const float4*>(p);
+    f[0] = u.x; f[1] = u.y; f[2] = u.z; f[3] = u.w;
+  }
+  __device__ static __forceinline__ void store(void* p, const float (&f)[4]) {
+    *reinterpret_cast<float4*>(p) = make_float4(f[0], f[1], f[2], f[3]);
+  }
+};
+
+__device__ __forceinline__ size_t plane_pix(const dtg_plane& p, int n, int y, int x) {
+  return (static_cast<size_t>(n) * (p.h + 2 * p.halo) + y + p.halo) * (p.w + 2 * p.halo) + x + p.halo;
+}
+
+__device__ __forceinline__ float act_grad(float y, int act) {
+  if (act == DTG_ACT_RELU) return y > 0.f ? 1.f : 0.f;
+  if (act == DTG_ACT_LRELU) return y > 0.f ? 1.f : 0.2f;
+  return 1.f;
+}
+
+// g = (fold(dy) + dy2) * act'(y) for one pixel / channel vector
+template <typename T>
+__device__ __forceinline__ void load_g(const dtg_plane& dy, const dtg_plane& dy2, const dtg_plane& yp, int act, int n,
+                                       int y, int x, int c, float (&g)[Vec<T>::N]) {
+  constexpr int V = Vec<T>::N;
+  const int es = sizeof(T);
+  int hts[3], wts[3];
+  const int nh = reflect_targets(y, dy.h, dy.halo, hts), nw = reflect_targets(x, dy.w, dy.halo, wts);
+#pragma unroll
+  for (int i = 0; i < V; ++i) g[i] = 0.f;
+  for (int a = 0; a < nh; ++a)
+    for (int q = 0; q < nw; ++q) {
+      float t[V];
+      Vec<T>::load(reinterpret_cast<const uint8_t*>(dy.ptr) + (plane_pix(dy, n, hts[a], wts[q]) * dy.c + c) * es, t);
+#pragma unroll
+      for (int i = 0; i < V; ++i) g[i] += t[i];
+    }
+  if (dy2.ptr) {
+    float t[V];
+    Vec<T>::load(reinterpret_cast<const uint8_t*>(dy2.ptr) + (plane_pix(dy2, n, y, x) * dy2.c + c) * es, t);
+#pragma unroll
+    for (int i = 0; i < V; ++i) g[i] += t[i];
+  }
+  if (act != DTG_ACT_NONE) {
+    float t[V];
+    Vec<T>::load(reinterpret_cast<const uint8_t*>(yp.ptr) + (plane_pix(yp, n, y, x) * yp.c + c) * es, t);
+#pragma unroll
+    for (int i = 0; i < V; ++i) g[i] *= act_grad(t[i], act);
+  }
+}
+
+// Block-level fixed-order reduction of per-thread (s1[V], s2[V]) over the pixel lanes.
+// Thread t owns vector column v = t % nv; result for (v, i) written by thread (v*V + i) < nv*V.
+template <int V>
+__device__ __forceinline__ void block_reduce_store(float (&s1)[V], float (&s2)[V], int nv, float* smem, float* out_c0,
+                                                   int cbase) {
+  const int t = threadIdx.x;
+  const int lanes = kNormThreads / nv;
+#pragma unroll
+  for (int i = 0; i < V; ++i) {
+    smem[(t * V + i) * 2] = s1[i];
+    smem[(t * V + i) * 2 + 1] = s2[i];
+  }
+  __syncthreads();
+  if (t < nv * V) {
+    const int v = t / V, i = t % V;
+    float a = 0.f, b = 0.f;
+    for (int l = 0; l < lanes; ++l) {
+      const int src = l * nv + v;
+      a += smem[(src * V + i) * 2];
+      b += smem[(src * V + i) * 2 + 1];
+    }
+    out_c0[(cbase + t) * 2] = a;
+    out_c0[(cbase + t) * 2 + 1] = b;
+  }
+}
+
+// forward statistics: partial[s][n][c] = (sum(x-K), sum((x-K)^2)), K = x[n,0,0,c] (0 for batch norm)
+template <typename T>
+__global__ void __launch_bounds__(kNormThreads) norm_stats_kernel(dtg_plane x, int cg, int splits, int use_shift,
+                                                                  float* __restrict__ partial) {
+  constexpr int V = Vec<T>::N;
+  __shared__ float smem[kNormThreads * V * 2];
+  const int nv = cg / V;
+  const int v = threadIdx.x % nv, lane = threadIdx.x / nv, lanes = kNormThreads / nv;
+  const int n = blockIdx.y, s = blockIdx.z;
+  const int c = blockIdx.x * cg + v * V;
+  const int hw = x.h * x.w;
+  const int chunk = (hw + splits - 1) / splits;
+  const int p0 = s * chunk, p1 = min(hw, p0 + chunk);
+  const uint8_t* base = reinterpret_cast<const uint8_t*>(x.ptr);
+  float K[V], s1[V], s2[V];
+#pragma unroll
+  for (int i = 0; i < V; ++i) K[i] = s1[i] = s2[i] = 0.f;
+  if (use_shift) Vec<T>::load(base + (plane_pix(x, n, 0, 0) * x.c + c) * sizeof(T), K);
+  for (int p = p0 + lane; p < p1; p += lanes) {
+    float f[V];
+    Vec<T>::load(base + (plane_pix(x, n, p / x.w, p % x.w) * x.c + c) * sizeof(T), f);
+#pragma unroll
+    for (int i = 0; i < V; ++i) {
+      const float d = f[i] - K[i];
+      s1[i] += d;
+      s2[i] += d * d;
+    }
+  }
+  block_reduce_store<V>(s1, s2, nv, smem, partial + (static_cast<size_t>(s) * x.n + n) * x.c * 2, blockIdx.x * cg);
+}
+
+// backward sums: partial[s][n][c] = (sum g, sum g*xhat)
+template <typename T>
+__global__ void __launch_bounds__(kNormThreads) norm_bwd_reduce_kernel(dtg_plane dy, dtg_plane dy2, dtg_plane yp,
+                                                                       dtg_plane x, const float* __restrict__ stats,
+                                                                       int mode, int act, int cg, int splits,
+                                                                       float* __restrict__ partial) {
+  constexpr int V = Vec<T>::N;
+  __shared__ float smem[kNormThreads * V * 2];
+  const int nv = cg / V;
+  const int v = threadIdx.x % nv, lane = threadIdx.x / nv, lanes = kNormThreads / nv;
+  const int n = blockIdx.y, s = blockIdx.z;
+  const int c = blockIdx.x * cg + v * V;
+  const int hw = x.h * x.w;
+  const int chunk = (hw + splits - 1) / splits;
+  const int p0 = s * chunk, p1 = min(hw, p0 + chunk);
+  float mean[V], rstd[V], s1[V], s2[V];
+#pragma unroll
+  for (int i = 0; i < V; ++i) {
+    s1[i] = s2[i] = 0.f;
+    mean[i] = 0.f;
+    rstd[i] = 0.f;
+    if (mode != DTG_NORM_NONE) {
+      mean[i] = stats[(static_cast<size_t>(n) * x.c + c + i) * 2];
+      rstd[i] = stats[(static_cast<size_t>(n) * x.c + c + i) * 2 + 1];
+    }
+  }
+  for (int p = p0 + lane; p < p1; p += lanes) {
+    const int py = p / x.w, px = p % x.w;
+    float g[V];
+    load_g<T>(dy, dy2, yp, act, n, py, px, c, g);
+    if (mode != DTG_NORM_NONE) {
+      float f[V];
+      Vec<T>::load(reinterpret_cast<const uint8_t*>(x.ptr) + (plane_pix(x, n, py, px) * x.c + c) * sizeof(T), f);
+#pragma unroll
+      for (int i = 0; i < V; ++i) {
+        s1[i] += g[i];
+        s2[i] += g[i] * (f[i] - mean[i]) * rstd[i];
+      }
+    } else {
+#pragma unroll
+      for (int i = 0; i < V; ++i) s1[i] += g[i];
+    }
+  }
+  block_reduce_store<V>(s1, s2, nv, smem, partial + (static_cast<size_t>(s) * x.n + n) * x.c * 2, blockIdx.x * cg);
+}
+
+// batch norm: collapse partial[s][n][c] over (s, n) -> bnsum[c][2]
+__global__ void bn_collapse_kernel(const float* __restrict__ partial, int splits, int n, int c, float* __restrict__ bnsum) {
+  const int ch = blockIdx.x * blockDim.x + threadIdx.x;
+  if (ch >= c) return;
+  float a = 0.f, b = 0.f;
+  for (int s = 0; s < splits; ++s)
+    for (int i = 0; i < n; ++i) {
+      const size_t o = ((static_cast<size_t>(s) * n + i) * c + ch) * 2;
+      a += partial[o];
+      b += partial[o + 1];
+    }
+  bnsum[ch * 2] = a;
+  bnsum[ch * 2 + 1] = b;
+}
+
+// forward finalize: stats[n][c] = (mean, rstd); coef[n][c] = (a, b) with y = x*a + b
+__global__ void norm_fwd_finalize_kernel(const float* __restrict__ partial, const float* __restrict__ bnsum,
+                                         const void* xptr, int dtype, int splits, int n, int c, int hw, int mode,
+                                         float eps, float momentum, int world, const float* __restrict__ gamma,
+                                         const float* __restrict__ beta, float* __restrict__ bn_running,
+                                         float* __restrict__ stats, float* __restrict__ coef) {
+  const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+  if (mode == DTG_NORM_BATCH) {
+    if (idx >= c) return;
+    const float m = static_cast<float>(hw) * n * world;
+    const float mean = bnsum[idx * 2] / m;
+    float var = bnsum[idx * 2 + 1] / m - mean * mean;
+    var = var < 0.f ? 0.f : var;
+    const float rstd = rsqrtf(var + eps);
+    if (bn_running) {
+      const float unb = m > 1.f ? var * m / (m - 1.f) : var;
+      bn_running[idx] = (1.f - momentum) * bn_running[idx] + momentum * mean;
+      bn_running[c + idx] = (1.f - momentum) * bn_running[c + idx] + momentum * unb;
+    }
+    const float a = rstd * gamma[idx], b = beta[idx] - mean * a;
+    for (int i = 0; i < n; ++i) {
+      stats[(static_cast<size_t>(i) * c + idx) * 2] = mean;
+      stats[(static_cast<size_t>(i) * c + idx) * 2 + 1] = rstd;
+      coef[(static_cast<size_t>(i) * c + idx) * 2] = a;
+      coef[(static_cast<size_t>(i) * c + idx) * 2 + 1] = b;
+    }
+    return;
+  }
+  if (idx >= n * c) return;
+  const int ch = idx % c, i = idx / c;
+  float s1 = 0.f, s2 = 0.f;
+  for (int s = 0; s < splits; ++s) {
+    const size_t o = ((static_cast<size_t>(s) * n + i) * c + ch) * 2;
+    s1 += partial[o];
+    s2 += partial[o + 1];
+  }
+  const size_t first = static_cast<size_t>(i) * hw * c + ch;  // x has halo 0
+  const float K = dtype == DTG_BF16 ? __bfloat162float(reinterpret_cast<const __nv_bfloat16*>(xptr)[first])
+                                    : reinterpret_cast<const float*>(xptr)[first];
+  const float m = static_cast<float>(hw);
+  const float mean = K + s1 / m;
+  const float d = mode == DTG_NORM_COND_INSTANCE ? m - 1.f : m;
+  float var = (s2 - s1 * s1 / m) / d;
+  var = var < 0.f ? 0.f : var;
+  const float rstd = rsqrtf(var + eps);
+  stats[idx * 2] = mean;
+  stats[idx * 2 + 1] = rstd;
+  const float ga = mode == DTG_NORM_COND_INSTANCE ? gamma[idx] : gamma[ch];
+  const float be = mode == DTG_NORM_COND_INSTANCE ? beta[idx] : beta[ch];
+  const float a = rstd * ga;
+  coef[idx * 2] = a;
+  coef[idx * 2 + 1] = be - mean * a;
+}
+
+// forward apply: y = act(x*a + b (+ residual)), mirrored into the output halo
+template <typename T>
+__global__ void __launch_bounds__(kNormThreads) norm_apply_kernel(dtg_plane x, dtg_plane res, const float* __restrict__ coef,
+                                                                  int has_coef, int act, dtg_plane out) {
+  constexpr int V = Vec<T>::N;
+  const int nvc = x.c / V;
+  const size_t total = static_cast<size_t>(x.n) * x.h * x.w * nvc;
+  for (size_t idx = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; idx < total;
+       idx += static_cast<size_t>(gridDim.x) * blockDim.x) {
+    const int c = static_cast<int>(idx % nvc) * V;
+    size_t r = idx / nvc;
+    const int px = r % x.w;
+    r /= x.w;
+    const int py = r % x.h;
+    const int n = r / x.h;
+    float f[V];
+    Vec<T>::load(reinterpret_cast<const uint8_t*>(x.ptr) + (plane_pix(x, n, py, px) * x.c + c) * sizeof(T), f);
+    if (has_coef) {
+      const float2* cf = reinterpret_cast<const float2*>(coef) + static_cast<size_t>(n) * x.c + c;
+#pragma unroll
+      for (int i = 0; i < V; ++i) {
+        const float2 ab = __ldg(cf + i);
+        f[i] = f[i] * ab.x + ab.y;
+      }
+    }
+    if (res.ptr) {
+      float t[V];
+      Vec<T>::load(reinterpret_cast<const uint8_t*>(res.ptr) + (plane_pix(res, n, py, px) * res.c + c) * sizeof(T), t);
+#pragma unroll
+      for (int i = 0; i < V; ++i) f[i] += t[i];
+    }
+#pragma unroll
+    for (int i = 0; i < V; ++i) f[i] = apply_act(f[i], act);
+    int hts[3], wts[3];
+    const int nh = reflect_targets(py, out.h, out.halo, hts), nw = reflect_targets(px, out.w, out.halo, wts);
+    for (int a = 0; a < nh; ++a)
+      for (int q = 0; q < nw; ++q)
+        Vec<T>::store(reinterpret_cast<uint8_t*>(out.ptr) + (plane_pix(out, n, hts[a], wts[q]) * out.c + c) * sizeof(T), f);
+  }
+}
+
+// backward finalize: sums[n][c] = (A, B); kcoef[n][c] = (k0, kA, kB, 0); d_gamma / d_beta accumulation
+__global__ void norm_bwd_finalize_kernel(const float* __restrict__ partial, const float* __restrict__ bnsum, int splits,
+                                         int n, int c, int hw, int mode, int world, const float* __restrict__ stats,
+                                         const float* __restrict__ gamma, float* __restrict__ sums,
+                                         float* __restrict__ d_gamma, float* __restrict__ d_beta,
+                                         float* __restrict__ kcoef) {
+  const int ch = blockIdx.x * blockDim.x + threadIdx.x;
+  if (ch >= c) return;
+  float accA = 0.f, accB = 0.f;
+  for (int i = 0; i < n; ++i) {
+    float A = 0.f, B = 0.f;
+    for (int s = 0; s < splits; ++s) {
+      const size_t o = ((static_cast<size_t>(s) * n + i) * c + ch) * 2;
+      A += partial[o];
+      B += partial[o + 1];
+    }
+    accA += A;
+    accB += B;
+    const size_t o = static_cast<size_t>(i) * c + ch;
+    if (sums) {
+      sums[o * 2] = A;
+      sums[o * 2 + 1] = B;
+    }
+    if (mode == DTG_NORM_INSTANCE || mode == DTG_NORM_COND_INSTANCE) {
+      const float m = static_cast<float>(hw);
+      const float d = mode == DTG_NORM_COND_INSTANCE ? m - 1.f : m;
+      const float ga = mode == DTG_NORM_COND_INSTANCE ? gamma[o] : gamma[ch];
+      kcoef[o * 4] = stats[o * 2 + 1] * ga;
+      kcoef[o * 4 + 1] = A / m;
+      kcoef[o * 4 + 2] = B / d;
+    }
+  }
+  if (mode == DTG_NORM_BATCH) {
+    // bnsum holds the (possibly all-reduced) per-channel sums
+    const float A = bnsum[ch * 2], B = bnsum[ch * 2 + 1];
+    const float m = static_cast<float>(hw) * n * world;
+    for (int i = 0; i < n; ++i) {
+      const size_t o = static_cast<size_t>(i) * c + ch;
+      kcoef[o * 4] = stats[o * 2 + 1] * gamma[ch];
+      kcoef[o * 4 + 1] = A / m;
+      kcoef[o * 4 + 2] = B / m;
+    }
+    // parameter gradients use the LOCAL sums (the caller all-reduces parameter gradients)
+  }
+  if (mode != DTG_NORM_COND_INSTANCE) {
+    if (d_beta) d_beta[ch] += accA;
+    if (d_gamma && mode != DTG_NORM_NONE) d_gamma[ch] += accB;
+  }
+}
+
+// backward apply: dx = k0*(g - kA - xhat*kB)  (NONE: dx = g); d_res = g
+template <typename T>
+__global__ void __launch_bounds__(kNormThreads) norm_bwd_apply_kernel(dtg_plane dy, dtg_plane dy2, dtg_plane yp, dtg_plane x,
+                                                                      const float* __restrict__ stats,
+                                                                      const float* __restrict__ kcoef, int mode, int act,
+                                                                      dtg_plane dx, dtg_plane dres) {
+  constexpr int V = Vec<T>::N;
+  const int nvc = dx.c / V;
+  const size_t total = static_cast<size_t>(dx.n) * dx.h * dx.w * nvc;
+  for (size_t idx = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; idx < total;
+       idx += static_cast<size_t>(gridDim.x) * blockDim.x) {
+    const int c = static_cast<int>(idx % nvc) * V;
+    size_t r = idx / nvc;
+    const int px = r % dx.w;
+    r /= dx.w;
+    const int py = r % dx.h;
+    const int n = r / dx.h;
+    float g[V];
+    load_g<T>(dy, dy2, yp, act, n, py, px, c, g);
+    if (dres.ptr)
+      Vec<T>::store(reinterpret_cast<uint8_t*>(dres.ptr) + (plane_pix(dres, n, py, px) * dres.c + c) * sizeof(T), g);
+    if (mode != DTG_NORM_NONE) {
+      float f[V];
+      Vec<T>::load(reinterpret_cast<const uint8_t*>(x.ptr) + (plane_pix(x, n, py, px) * x.c + c) * sizeof(T), f);
+      const float2* st = reinterpret_cast<const float2*>(stats) + static_cast<size_t>(n) * x.c + c;
+      const float4* kc = reinterpret_cast<const float4*>(kcoef) + static_cast<size_t>(n) * x.c + c;
+#pragma unroll
+      for (int i = 0; i < V; ++i) {
+        const float2 mr = __ldg(st + i);
+        const float4 k = __ldg(kc + i);
+        const float xh = (f[i] - mr.x) * mr.y;
+        g[i] = k.x * (g[i] - k.y - xh * k.z);
+      }
+    }
+    Vec<T>::store(reinterpret_cast<uint8_t*>(dx.ptr) + (plane_pix(dx, n, py, px) * dx.c + c) * sizeof(T), g);
+  }
+}
+
+// ---- CondInstanceNorm z projections ----------------------------------------------------------
+__global__ void cin_affine_fwd_kernel(const float* __restrict__ z, const float* __restrict__ ws, const float* __restrict__ bs,
+                                      const float* __restrict__ wb, const float* __restrict__ bb, int n, int c, int nz,
+                                      float* __restrict__ gamma, float* __restrict__ beta) {
+  const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= n * c) return;
+  const int ch = idx % c, i = idx / c;
+  float s = bs[ch], b = bb[ch];
+  for (int k = 0; k < nz; ++k) {
+    const float zz = z[i * nz + k];
+    s += ws[ch * nz + k] * zz;
+    b += wb[ch * nz + k] * zz;
+  }
+  gamma[idx] = s > 0.f ? s : 0.f;
+  beta[idx] = b > 0.f ? b : 0.f;
+}
+
+// one thread per (c, k) for weights (+ bias when k == 0); then one thread per (n, k) for dz
+__global__ void cin_affine_bwd_kernel(const float* __restrict__ z, const float* __restrict__ ws, const float* __restrict__ wb,
+                                      const float* __restrict__ gamma, const float* __restrict__ beta,
+                                      const float* __restrict__ sums, int n, int c, int nz, float* __restrict__ d_ws,
+                                      float* __restrict__ d_bs, float* __restrict__ d_wb, float* __restrict__ d_bb,
+                                      float* __restrict__ d_z) {
+  const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+  const int nw = c * nz;
+  if (idx < nw) {
+    const int ch = idx / nz, k = idx % nz;
+    float aw = 0.f, ab = 0.f, sw = 0.f, sb = 0.f;
+    for (int i = 0; i < n; ++i) {
+      const size_t o = static_cast<size_t>(i) * c + ch;
+      const float ds = gamma[o] > 0.f ? sums[o * 2 + 1] : 0.f;  // d_scale = sum g*xhat
+      const float db = beta[o] > 0.f ? sums[o * 2] : 0.f;       // d_shift = sum g
+      const float zz = z[i * nz + k];
+      aw += ds * zz;
+      ab += db * zz;
+      sw += ds;
+      sb += db;
+    }
+    d_ws[idx] += aw;
+    d_wb[idx] += ab;
+    if (k == 0) {
+      d_bs[ch] += sw;
+      d_bb[ch] += sb;
+    }
+  } else if (idx < nw + n * nz && d_z != nullptr) {
+    const int j = idx - nw;
+    const int i = j / nz, k = j % nz;
+    float acc = 0.f;
+    for (int ch = 0; ch < c; ++ch) {
+      const size_t o = static_cast<size_t>(i) * c + ch;
+      const float ds = gamma[o] > 0.f ? sums[o * 2 + 1] : 0.f;
+      const float db = beta[o] > 0.f ? sums[o * 2] : 0.f;
+      acc += ds * ws[ch * nz + k] + db * wb[ch * nz + k];
+    }
+    d_z[j] += acc;
+  }
+}
+
+static int pick_splits(int n, int c, int cg, int hw) {
+  const int ctas = n * (c / cg);
+  int s = (2 * 148 + ctas - 1) / ctas;
+  s = std::min(s, kMaxSplits);
+  s = std::min(s, std::max(1, hw / 64));
+  return std::max(1, s);
+}
+
+static int elemwise_grid(size_t total) {
+  size_t g = (total + kNormThreads - 1) / kNormThreads;
+  return static_cast<int>(std::max<size_t>(1, std::min<size_t>(g, 148 * 8)));
+}
+
+static const dtg_plane kNullPlane = {nullptr, 0, 0, 0, 0, 0, 0};
+
+}  // namespace dtg
+
+using namespace dtg;
+
+extern "C" size_t dtg_norm_workspace_bytes(const dtg_plane* x) {
+  if (!x) return 0;
+  const size_t nc = static_cast<size_t>(x->n) * x->c;
+  return (2 * static_cast<size_t>(x->c) + kMaxSplits * nc * 2 + nc * 4) * sizeof(float);
+}
+
+extern "C" int dtg_norm_fwd(const dtg_norm_args* a, const dtg_plane* x, const dtg_plane* residual, const float* gamma,
+                            const float* beta, float* bn_running, float* stats, float* coef, float* partial,
+                            const dtg_plane* out, void* stream_) {
+  DTG_REQUIRE(a && x && out && x->ptr && out->ptr, "dtg_norm_fwd: null argument");
+  DTG_REQUIRE(x->halo == 0, "dtg_norm_fwd: x must have halo 0");
+  DTG_REQUIRE(x->dtype == out->dtype && x->n == out->n && x->h == out->h && x->w == out->w && x->c == out->c,
+              "dtg_norm_fwd: out plane mismatch");
+  DTG_REQUIRE(!residual || !residual->ptr || (residual->c == x->c && residual->h == x->h && residual->dtype == x->dtype),
+              "dtg_norm_fwd: residual mismatch");
+  const bool bf = x->dtype == DTG_BF16;
+  const int V = bf ? 8 : 4;
+  DTG_REQUIRE(x->c % V == 0, "dtg_norm_fwd: channels %d not a multiple of %d", x->c, V);
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  const int hw = x->h * x->w;
+  const int mode = a->mode;
+  if (mode != DTG_NORM_NONE) {
+    DTG_REQUIRE(gamma && beta && stats && coef && partial, "dtg_norm_fwd: missing buffers");
+    DTG_REQUIRE(mode != DTG_NORM_COND_INSTANCE || hw > 1, "dtg_norm_fwd: conditional instance norm needs H*W > 1");
+    const int cg = std::min(x->c, 8 * V);
+    DTG_REQUIRE(x->c % cg == 0, "dtg_norm_fwd: channels %d not a multiple of the channel group %d", x->c, cg);
+    const int splits = pick_splits(x->n, x->c, cg, hw);
+    float* bnsum = partial;
+    float* part = partial + 2 * x->c;
+    if (a->phase == 0 || a->phase == 1) {
+      dim3 grid(x->c / cg, x->n, splits);
+      if (bf)
+        norm_stats_kernel<__nv_bfloat16><<<grid, kNormThreads, 0, stream>>>(*x, cg, splits, mode != DTG_NORM_BATCH, part);
+      else
+        norm_stats_kernel<float><<<grid, kNormThreads, 0, stream>>>(*x, cg, splits, mode != DTG_NORM_BATCH, part);
+      DTG_CHECK_CUDA(cudaGetLastError());
+      if (mode == DTG_NORM_BATCH) {
+        bn_collapse_kernel<<<(x->c + 127) / 128, 128, 0, stream>>>(part, splits, x->n, x->c, bnsum);
+        DTG_CHECK_CUDA(cudaGetLastError());
+      }
+      if (a->phase == 1) return DTG_OK;
+    }
+    const int world = a->world_size > 0 ? a->world_size : 1;
+    const int cnt = mode == DTG_NORM_BATCH ? x->c : x->n * x->c;
+    norm_fwd_finalize_kernel<<<(cnt + 127) / 128, 128, 0, stream>>>(part, bnsum, x->ptr, x->dtype, splits, x->n, x->c, hw,
+                                                                   mode, a->eps, a->momentum, world, gamma, beta,
+                                                                   bn_running, stats, coef);
+    DTG_CHECK_CUDA(cudaGetLastError());
+  } else if (a->phase == 1) {
+    return DTG_OK;
+  }
+  const dtg_plane res = (residual && residual->ptr) ? *residual : kNullPlane;
+  const size_t total = static_cast<size_t>(x->n) * hw * (x->c / V);
+  if (bf)
+    norm_apply_kernel<__nv_bfloat16><<<elemwise_grid(total), kNormThreads, 0, stream>>>(*x, res, coef, mode != DTG_NORM_NONE, a->act, *out);
+  else
+    norm_apply_kernel<float><<<elemwise_grid(total), kNormThreads, 0, stream>>>(*x, res, coef, mode != DTG_NORM_NONE, a->act, *out);
+  DTG_CHECK_CUDA(cudaGetLastError());
+  return DTG_OK;
+}
+
+extern "C" int dtg_norm_bwd(const dtg_norm_args* a, const dtg_plane* dy, const dtg_plane* dy2, const dtg_plane* y,
+                            const dtg_plane* x, const float* stats, const float* gamma, float* sums, float* d_gamma,
+                            float* d_beta, float* partial, const dtg_plane* dx, const dtg_plane* d_res, void* stream_) {
+  DTG_REQUIRE(a && dy && dx && dy->ptr && dx->ptr && partial, "dtg_norm_bwd: null argument");
+  const int mode = a->mode;
+  DTG_REQUIRE(mode == DTG_NORM_NONE || (x && x->ptr && stats && gamma), "dtg_norm_bwd: missing saved tensors");
+  DTG_REQUIRE(a->act == DTG_ACT_NONE || (y && y->ptr), "dtg_norm_bwd: activation needs saved output");
+  DTG_REQUIRE(dx->halo == 0 && dx->n == dy->n && dx->h == dy->h && dx->w == dy->w && dx->c == dy->c && dx->dtype == dy->dtype,
+              "dtg_norm_bwd: dx / dy mismatch");
+  DTG_REQUIRE(!x || !x->ptr || (x->halo == 0 && x->c == dx->c && x->h == dx->h), "dtg_norm_bwd: x mismatch");
+  DTG_REQUIRE(!dy2 || !dy2->ptr || (dy2->c == dx->c && dy2->h == dx->h && dy2->halo == 0), "dtg_norm_bwd: dy2 mismatch");
+  DTG_REQUIRE(!y || !y->ptr || (y->c == dx->c && y->h == dx->h), "dtg_norm_bwd: y mismatch");
+  const bool bf = dx->dtype == DTG_BF16;
+  const int V = bf ? 8 : 4;
+  DTG_REQUIRE(dx->c % V == 0, "dtg_norm_bwd: channels");
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  const int hw = dx->h * dx->w, n = dx->n, c = dx->c;
+  const int cg = std::min(c, 8 * V);
+  DTG_REQUIRE(c % cg == 0, "dtg_norm_bwd: channel group");
+  const int splits = pick_splits(n, c, cg, hw);
+  const dtg_plane p_dy2 = (dy2 && dy2->ptr) ? *dy2 : kNullPlane;
+  const dtg_plane p_y = (y && y->ptr) ? *y : kNullPlane;
+  const dtg_plane p_x = (x && x->ptr) ? *x : *dx;
+  float* bnsum = partial;
+  float* part = partial + 2 * c;
+  float* kcoef = part + static_cast<size_t>(kMaxSplits) * n * c * 2;
+  const bool need_reduce = mode != DTG_NORM_NONE || d_beta != nullptr || sums != nullptr;
+  if ((a->phase == 0 || a->phase == 1) && need_reduce) {
+    dim3 grid(c / cg, n, splits);
+    if (bf)
+      norm_bwd_reduce_kernel<__nv_bfloat16><<<grid, kNormThreads, 0, stream>>>(*dy, p_dy2, p_y, p_x, stats, mode, a->act, cg, splits, part);
+    else
+      norm_bwd_reduce_kernel<float><<<grid, kNormThreads, 0, stream>>>(*dy, p_dy2, p_y, p_x, stats, mode, a->act, cg, splits, part);
+    DTG_CHECK_CUDA(cudaGetLastError());
+    if (mode == DTG_NORM_BATCH) {
+      bn_collapse_kernel<<<(c + 127) / 128, 128, 0, stream>>>(part, splits, n, c, bnsum);
+      DTG_CHECK_CUDA(cudaGetLastError());
+    }
+  }
+  if (a->phase == 1) return DTG_OK;
+  if (need_reduce) {
+    const int world = a->world_size > 0 ? a->world_size : 1;
+    norm_bwd_finalize_kernel<<<(c + 127) / 128, 128, 0, stream>>>(part, bnsum, splits, n, c, hw, mode, world, stats, gamma,
+                                                                 sums, d_gamma, d_beta, kcoef);
+    DTG_CHECK_CUDA(cudaGetLastError());
+  }
+  const dtg_plane p_res = (d_res && d_res->ptr) ? *d_res : kNullPlane;
+  const size_t total = static_cast<size_t>(n) * hw * (c / V);
+  if (bf)
+    norm_bwd_apply_kernel<__nv_bfloat16><<<elemwise_grid(total), kNormThreads, 0, stream>>>(*dy, p_dy2, p_y, p_x, stats, kcoef, mode, a->act, *dx, p_res);
+  else
+    norm_bwd_apply_kernel<float><<<elemwise_grid(total), kNormThreads, 0, stream>>>(*dy, p_dy2, p_y, p_x, stats, kcoef, mode, a->act, *dx, p_res);
+  DTG_CHECK_CUDA(cudaGetLastError());
+  return DTG_OK;
+}
+
+extern "C" int dtg_cin_affine_fwd(const float* z, const float* ws, const float* bs, const float* wb, const float* bb,
+                                  int n, int c, int nz, float* gamma, float* beta, void* stream) {
+  DTG_REQUIRE(z && ws && bs && wb && bb && gamma && beta, "dtg_cin_affine_fwd: null argument");
+  cin_affine_fwd_kernel<<<(n * c + 127) / 128, 128, 0, static_cast<cudaStream_t>(stream)>>>(z, ws, bs, wb, bb, n, c, nz, gamma, beta);
+  DTG_CHECK_CUDA(cudaGetLastError());
+  return DTG_OK;
+}
+
+extern "C" int dtg_cin_affine_bwd(const float* z, const float* ws, const float* wb, const float* gamma, const float* beta,
+                                  const float* sums, int n, int c, int nz, float* d_ws, float* d_bs, float* d_wb,
+                                  float* d_bb, float* d_z, void* stream) {
+  DTG_REQUIRE(z && ws && wb && gamma && beta && sums && d_ws && d_bs && d_wb && d_bb, "dtg_cin_affine_bwd: null argument");
+  const int total = c * nz + n * nz;
+  cin_affine_bwd_kernel<<<(total + 127) / 128, 128, 0, static_cast<cudaStream_t>(stream)>>>(z, ws, wb, gamma, beta, sums, n, c, nz, d_ws,
+                                                                                              d_bs, d_wb, d_bb, d_z);
+  DTG_CHECK_CUDA(cudaGetLastError());
+  return DTG_OK;
+}

@@ -161,3 +161,94 @@ def conv_wgrad(p, q, dw, *, kh, kw, stride=1, pad=0, pa, qb, ws=None):
         ws = workspace(need, dw.device, "wgrad")
     assert dw.dtype == torch.float32 and dw.is_contiguous() and dw.numel() == pa * qb * kh * kw
     L.check(L.lib().dtg_conv_wgrad(C.byref(a), p.s, q.s, _ptr(dw), _ptr(ws), ws.numel(), _stream()), "conv_wgrad")
+
+
+def norm_workspace_floats(x):
+    return L.lib().dtg_norm_workspace_bytes(x.s) // 4
+
+
+class NormState:
+    """Per-layer fp32 side buffers of one norm invocation (saved statistics, coefficients, sums)."""
+
+    __slots__ = ("stats", "coef", "sums", "ws")
+
+    def __init__(self, x):
+        dev = x.t.device
+        self.stats = torch.zeros(x.n, x.c, 2, dtype=torch.float32, device=dev)
+        self.coef = torch.zeros(x.n, x.c, 2, dtype=torch.float32, device=dev)
+        self.sums = torch.zeros(x.n, x.c, 2, dtype=torch.float32, device=dev)
+        self.ws = torch.zeros(norm_workspace_floats(x), dtype=torch.float32, device=dev)
+
+
+def norm_fwd(x, out, st, *, mode, act, gamma=None, beta=None, residual=None, bn_running=None, eps=1e-5,
+             momentum=0.1, phase=0, world_size=1):
+    a = L.NormArgs(mode, act, eps, momentum, phase, world_size)
+    rc = L.lib().dtg_norm_fwd(C.byref(a), x.s, residual.s if residual is not None else NULL_PLANE, _ptr(gamma),
+                              _ptr(beta), _ptr(bn_running), _ptr(st.stats), _ptr(st.coef), _ptr(st.ws), out.s, _stream())
+    L.check(rc, "norm_fwd")
+
+
+def norm_bwd(dy, dx, st, *, mode, act, y=None, x=None, gamma=None, dy2=None, d_res=None, d_gamma=None, d_beta=None,
+             want_sums=False, phase=0, world_size=1):
+    a = L.NormArgs(mode, act, 1e-5, 0.1, phase, world_size)
+    P = lambda p: p.s if p is not None else NULL_PLANE
+    rc = L.lib().dtg_norm_bwd(C.byref(a), dy.s, P(dy2), P(y), P(x), _ptr(st.stats), _ptr(gamma),
+                              _ptr(st.sums) if (want_sums or mode == L.NORM_COND_INSTANCE) else C.c_void_p(0),
+                              _ptr(d_gamma), _ptr(d_beta), _ptr(st.ws), dx.s, P(d_res), _stream())
+    L.check(rc, "norm_bwd")
+
+
+def cin_affine_fwd(z, ws, bs, wb, bb, gamma, beta):
+    n, nz = z.shape[0], z.shape[1]
+    c = ws.shape[0]
+    L.check(L.lib().dtg_cin_affine_fwd(_ptr(z), _ptr(ws), _ptr(bs), _ptr(wb), _ptr(bb), n, c, nz, _ptr(gamma),
+                                       _ptr(beta), _stream()), "cin_affine_fwd")
+
+
+def cin_affine_bwd(z, ws, wb, gamma, beta, sums, d_ws, d_bs, d_wb, d_bb, d_z):
+    n, nz = z.shape[0], z.shape[1]
+    c = ws.shape[0]
+    L.check(L.lib().dtg_cin_affine_bwd(_ptr(z), _ptr(ws), _ptr(wb), _ptr(gamma), _ptr(beta), _ptr(sums), n, c, nz,
+                                       _ptr(d_ws), _ptr(d_bs), _ptr(d_wb), _ptr(d_bb), _ptr(d_z), _stream()),
+            "cin_affine_bwd")
+
+
+def grad_gather(srcs, c_offs, c, out=None, tanh_y=None, out_nchw=None):
+    arr = (C.POINTER(L.Plane) * len(srcs))(*[C.pointer(s._s) for s in srcs])
+    offs = (C.c_int * len(srcs))(*c_offs)
+    if out is None:
+        s0 = srcs[0]
+        dummy = L.Plane(None, s0.n, s0.h, s0.w, c, 0, _DT[s0.dtype])
+        outp = C.byref(dummy)
+    else:
+        outp = out.s
+    L.check(L.lib().dtg_grad_gather(arr, offs, len(srcs), _ptr(tanh_y), c, outp, _ptr(out_nchw), _stream()), "grad_gather")
+
+
+def channel_sum(x, c, d_bias):
+    L.check(L.lib().dtg_channel_sum(x.s, c, _ptr(d_bias), _stream()), "channel_sum")
+
+
+def loss_lsgan(pred, target, grad_scale, scalars, slot_loss, slot_mean, dpred, ws):
+    n, _, h, w = pred.shape
+    L.check(L.lib().dtg_loss_lsgan(_ptr(pred), n, h, w, float(target), float(grad_scale), _ptr(scalars), slot_loss,
+                                   slot_mean, dpred.s if dpred is not None else NULL_PLANE, _ptr(ws), _stream()), "loss_lsgan")
+
+
+def loss_l1(a, b, grad_scale, tanh_bwd, scalars, slot_loss, slot_aux, da, ws):
+    n, c, h, w = a.shape
+    L.check(L.lib().dtg_loss_l1(_ptr(a), _ptr(b), n, c, h, w, float(grad_scale), 1 if tanh_bwd else 0, _ptr(scalars),
+                                slot_loss, slot_aux, da.s if da is not None else NULL_PLANE, _ptr(ws), _stream()), "loss_l1")
+
+
+def grad_sumsq(g, grad_scale, out, ws):
+    L.check(L.lib().dtg_grad_sumsq(_ptr(g), g.numel(), float(grad_scale), _ptr(out), _ptr(ws), _stream()), "grad_sumsq")
+
+
+def adam_clip(p, g, m, v, hyper, sumsq, step_dev, grad_scale=1.0):
+    L.check(L.lib().dtg_adam_clip(_ptr(p), _ptr(g), _ptr(m), _ptr(v), p.numel(), _ptr(hyper), _ptr(sumsq),
+                                  _ptr(step_dev), float(grad_scale), _stream()), "adam_clip")
+
+
+def step_increment(step_dev):
+    L.check(L.lib().dtg_step_increment(_ptr(step_dev), _stream()), "step_increment")

@@ -1,0 +1,198 @@
+"""GPU parity of the fused norm / activation / residual kernels, losses and clip+Adam against torch
+(fp64 autograd of the reference formulas in oracle.functional) on identical inputs.
+fp32 planes: 1e-4 relative (pure fp32 arithmetic, different summation order);
+bf16 planes: inputs are bf16-representable, outputs rounded to bf16 -> 1e-2 relative."""
+import pytest
+import torch
+import torch.nn.functional as F
+
+import dtg  # noqa: F401
+from dtg_b200 import _lib as L, ops
+from oracle import functional as OF
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda"
+
+
+def _rel(a, b):
+    return float((a - b).abs().max() / b.abs().max().clamp_min(1e-9))
+
+
+def _act(t, act):
+    return {L.ACT_NONE: lambda v: v, L.ACT_RELU: F.relu, L.ACT_LRELU: lambda v: F.leaky_relu(v, 0.2)}[act](t)
+
+
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
+@pytest.mark.parametrize("mode,act,residual,halo,shape", [
+    (L.NORM_INSTANCE, L.ACT_RELU, False, 0, (3, 64, 64, 64)),
+    (L.NORM_INSTANCE, L.ACT_RELU, True, 1, (2, 128, 32, 32)),
+    (L.NORM_INSTANCE, L.ACT_LRELU, False, 0, (2, 256, 15, 15)),
+    (L.NORM_COND_INSTANCE, L.ACT_RELU, False, 1, (3, 128, 32, 32)),
+    (L.NORM_COND_INSTANCE, L.ACT_RELU, False, 0, (2, 32, 64, 64)),
+    (L.NORM_BATCH, L.ACT_RELU, False, 0, (5, 64, 16, 16)),
+    (L.NORM_BATCH, L.ACT_LRELU, False, 0, (37, 64, 1, 1)),
+    (L.NORM_NONE, L.ACT_RELU, False, 1, (2, 128, 32, 32)),
+])
+def test_norm_fwd_bwd(mode, act, residual, halo, shape, dtype):
+    n, c, h, w = shape
+    g = torch.Generator().manual_seed(n * 1000 + c + h)
+    q = (lambda t: t.to(torch.bfloat16).float()) if dtype == torch.bfloat16 else (lambda t: t)
+    x = q(torch.randn(n, c, h, w, generator=g) * 1.7 + 0.8).to(DEV)
+    res = q(torch.randn(n, c, h, w, generator=g)).to(DEV) if residual else None
+    # gradient w.r.t. the (reflect-padded) output
+    dyp = q(torch.randn(n, c, h + 2 * halo, w + 2 * halo, generator=g)).to(DEV)
+    dy2 = q(torch.randn(n, c, h, w, generator=g)).to(DEV) if residual else None
+    if mode == L.NORM_COND_INSTANCE:
+        gamma = torch.rand(n, c, generator=g).to(DEV) + 0.1
+        beta = torch.rand(n, c, generator=g).to(DEV)
+    else:
+        gamma = (torch.randn(c, generator=g) * 0.5).to(DEV)
+        beta = torch.randn(c, generator=g).to(DEV)
+
+    # ---- reference in fp64 ----
+    xr = x.double().requires_grad_(True)
+    gr = gamma.double().requires_grad_(True)
+    br = beta.double().requires_grad_(True)
+    rr = res.double().requires_grad_(True) if residual else None
+    if mode == L.NORM_INSTANCE:
+        yn = OF.instance_norm(xr, gr, br)
+    elif mode == L.NORM_COND_INSTANCE:
+        flat = xr.reshape(n, c, h * w)
+        yn = ((flat - flat.mean(2, keepdim=True)) * torch.rsqrt(flat.var(2, keepdim=True) + 1e-5)).reshape(n, c, h, w)
+        yn = yn * gr[:, :, None, None] + br[:, :, None, None]
+    elif mode == L.NORM_BATCH:
+        rm, rv = torch.zeros(c, dtype=torch.float64, device=DEV), torch.ones(c, dtype=torch.float64, device=DEV)
+        yn = F.batch_norm(xr, rm, rv, gr, br, True, 0.1, 1e-5)
+    else:
+        yn = xr
+    yr = _act(yn + rr if residual else yn, act)
+    ypad = F.pad(yr, (halo,) * 4, mode="reflect") if halo else yr
+    loss = (ypad * dyp.double()).sum()
+    if residual:
+        loss = loss + (yr * dy2.double()).sum()   # second gradient contribution
+    loss.backward()
+
+    # ---- ours ----
+    xp = ops.PlaneT.from_nchw(x, dtype=dtype)
+    out = ops.PlaneT(n, h, w, c, halo, dtype)
+    st = ops.NormState(xp)
+    rp = ops.PlaneT.from_nchw(res, dtype=dtype) if residual else None
+    bn_run = torch.cat([torch.zeros(c), torch.ones(c)]).to(DEV) if mode == L.NORM_BATCH else None
+    ops.norm_fwd(xp, out, st, mode=mode, act=act, gamma=gamma, beta=beta, residual=rp, bn_running=bn_run)
+    got = out.t.permute(0, 3, 1, 2).float()
+    tol = 1e-2 if dtype == torch.bfloat16 else 1e-4
+    assert _rel(got, ypad.float()) < tol
+    if mode == L.NORM_BATCH:
+        assert _rel(bn_run[:c], rm.float()) < 1e-4 and _rel(bn_run[c:], rv.float()) < 1e-4
+
+    dyplane = ops.PlaneT(n, h, w, c, halo, dtype)
+    dyplane.t.copy_(dyp.permute(0, 2, 3, 1))
+    dy2p = ops.PlaneT.from_nchw(dy2, dtype=dtype) if residual else None
+    dx = ops.PlaneT(n, h, w, c, 0, dtype)
+    dres = ops.PlaneT(n, h, w, c, 0, dtype) if residual else None
+    dgam = torch.zeros(c, device=DEV)
+    dbet = torch.zeros(c, device=DEV)
+    ops.norm_bwd(dyplane, dx, st, mode=mode, act=act, y=out, x=xp, gamma=gamma, dy2=dy2p, d_res=dres,
+                 d_gamma=dgam, d_beta=dbet, want_sums=True)
+    assert _rel(dx.to_nchw(), xr.grad.float()) < (2e-2 if dtype == torch.bfloat16 else 2e-4)
+    if residual:
+        assert _rel(dres.to_nchw(), rr.grad.float()) < tol
+    gtol = 5e-3 if dtype == torch.bfloat16 else 2e-4
+    if mode == L.NORM_COND_INSTANCE:
+        assert _rel(st.sums[..., 1], gr.grad.float()) < gtol
+        assert _rel(st.sums[..., 0], br.grad.float()) < gtol
+    elif mode != L.NORM_NONE:
+        assert _rel(dgam, gr.grad.float()) < gtol
+        assert _rel(dbet, br.grad.float()) < gtol
+    else:
+        # NONE: d_beta = per-channel sum of g (bias gradient of the preceding conv)
+        gsum = xr.grad.sum(dim=(0, 2, 3)).float()
+        assert _rel(dbet, gsum) < gtol
+
+
+def test_cin_affine():
+    g = torch.Generator().manual_seed(1)
+    n, c, nz = 7, 128, 16
+    z = torch.randn(n, nz, generator=g).to(DEV)
+    ws, wb = (torch.randn(c, nz, generator=g) * 0.3).to(DEV), (torch.randn(c, nz, generator=g) * 0.3).to(DEV)
+    bs, bb = (torch.randn(c, generator=g) * 0.1).to(DEV), (torch.randn(c, generator=g) * 0.1).to(DEV)
+    sums = torch.randn(n, c, 2, generator=g).to(DEV)
+    t = [v.double().requires_grad_(True) for v in (z, ws, bs, wb, bb)]
+    gam = F.relu(t[0] @ t[1].T + t[2]); bet = F.relu(t[0] @ t[3].T + t[4])
+    ((gam * sums[..., 1].double()).sum() + (bet * sums[..., 0].double()).sum()).backward()
+    gamma, beta = torch.empty(n, c, device=DEV), torch.empty(n, c, device=DEV)
+    ops.cin_affine_fwd(z, ws, bs, wb, bb, gamma, beta)
+    assert _rel(gamma, gam.float()) < 1e-5 and _rel(beta, bet.float()) < 1e-5
+    d = [torch.zeros_like(v) for v in (ws, bs, wb, bb, z)]
+    ops.cin_affine_bwd(z, ws, wb, gamma, beta, sums, *d)
+    for got, ref in zip(d, (t[1], t[2], t[3], t[4], t[0])):
+        assert _rel(got, ref.grad.float()) < 1e-4
+
+
+def test_losses_and_gather():
+    g = torch.Generator().manual_seed(2)
+    n = 5
+    pred = torch.randn(n, 1, 13, 13, generator=g).to(DEV)
+    scal = torch.zeros(32, device=DEV)
+    ws = torch.zeros(1024, dtype=torch.float32, device=DEV)
+    dp = ops.PlaneT(n, 13, 13, 16, 0, torch.float32)
+    ops.loss_lsgan(pred, 1.0, 0.5, scal, 0, 1, dp, ws)
+    pr = pred.double().requires_grad_(True)
+    l = OF.lsgan(pr, True); (0.5 * l).backward()
+    assert abs(float(scal[0]) - float(l)) < 1e-5 and abs(float(scal[1]) - float(pred.mean())) < 1e-5
+    assert _rel(dp.to_nchw(1), pr.grad.float()) < 1e-5
+    # L1 + tanh backward
+    pre = torch.randn(n, 3, 64, 64, generator=g).to(DEV)
+    rec = torch.tanh(pre)
+    real = (torch.rand(n, 3, 64, 64, generator=g) * 2 - 1).to(DEV)
+    da = ops.PlaneT(n, 64, 64, 16, 0, torch.float32)
+    ops.loss_l1(rec, real, 0.7, True, scal, 2, 3, da, ws)
+    prr = pre.double().requires_grad_(True)
+    l1 = F.l1_loss(torch.tanh(prr), real.double()); (0.7 * l1).backward()
+    assert abs(float(scal[2]) - float(l1)) < 1e-5
+    assert _rel(da.to_nchw(3), prr.grad.float()) < 1e-4
+    assert abs(float(scal[3]) - float(0.5 * (rec ** 2).sum() / n)) < 1e-2 * float(scal[3])
+    assert float(scal[4]) == float(rec.min()) and float(scal[5]) == float(rec.max())
+    # gather with fold + tanh'
+    a = torch.randn(n, 16, 70, 70, generator=g).to(DEV)     # halo 3 gradient plane (NHWC below)
+    b = torch.randn(n, 16, 64, 64, generator=g).to(DEV)
+    pa = ops.PlaneT(n, 64, 64, 16, 3, torch.float32); pa.t.copy_(a.permute(0, 2, 3, 1))
+    pb = ops.PlaneT(n, 64, 64, 16, 0, torch.float32); pb.t.copy_(b.permute(0, 2, 3, 1))
+    out = ops.PlaneT(n, 64, 64, 16, 0, torch.float32)
+    dense = torch.empty(n, 3, 64, 64, device=DEV)
+    ops.grad_gather([pa, pb], [0, 3], 3, out=out, tanh_y=rec, out_nchw=dense)
+    xin = torch.zeros(n, 16, 64, 64, device=DEV, dtype=torch.float64, requires_grad=True)
+    (F.pad(xin, (3,) * 4, mode="reflect") * a.double()).sum().backward()
+    want = xin.grad[:, 0:3].float() + b[:, 3:6]
+    assert _rel(dense, want) < 1e-5
+    assert _rel(out.to_nchw(3), want * (1 - rec ** 2)) < 1e-5
+    bias = torch.zeros(16, device=DEV)
+    ops.channel_sum(pb, 16, bias)
+    assert _rel(bias, b.sum(dim=(0, 2, 3))) < 1e-4
+
+
+def test_clip_adam_matches_torch():
+    g = torch.Generator().manual_seed(3)
+    cnt = 100003
+    p0 = torch.randn(cnt, generator=g)
+    hyper = torch.tensor([2e-4, 0.5, 0.999, 1e-8, 5.0], device=DEV)
+    p = torch.zeros(100004, device=DEV)[:cnt]; p.copy_(p0)
+    gr = torch.zeros(100004, device=DEV)[:cnt]
+    m, v = torch.zeros_like(p), torch.zeros_like(p)
+    step = torch.zeros(1, dtype=torch.int32, device=DEV)
+    sumsq = torch.zeros(1, device=DEV)
+    ws = torch.zeros(1024, device=DEV)
+    pt = p0.clone().to(DEV).requires_grad_(True)
+    opt = torch.optim.Adam([pt], lr=2e-4, betas=(0.5, 0.999))
+    for it in range(3):
+        gi = torch.randn(cnt, generator=g).to(DEV) * (0.1 if it else 1.0)
+        gr.copy_(gi)
+        ops.step_increment(step)
+        ops.grad_sumsq(gr, 1.0, sumsq, ws)
+        ops.adam_clip(p, gr, m, v, hyper, sumsq, step)
+        pt.grad = gi.clone()
+        tn = torch.nn.utils.clip_grad_norm_([pt], 5.0)
+        opt.step()
+        assert abs(float(sumsq.sqrt()) - float(tn)) < 1e-3 * float(tn)
+        assert float((gr - pt.grad).abs().max()) < 1e-6
+        assert float((p - pt.detach()).abs().max()) < 2e-7
