@@ -55,9 +55,9 @@ _SIGS = {
                                C.POINTER(Plane), _P, _P, _P, _P, _P, _P, C.POINTER(Plane), C.POINTER(Plane), _P]),
     "dtg_cin_affine_fwd": (C.c_int, [_P, _P, _P, _P, _P, C.c_int, C.c_int, C.c_int, _P, _P, _P]),
     "dtg_cin_affine_bwd": (C.c_int, [_P, _P, _P, _P, _P, _P, C.c_int, C.c_int, C.c_int, _P, _P, _P, _P, _P, _P]),
-    "dtg_pack_nchw": (C.c_int, [_P, C.c_int, C.c_int, C.c_int, C.c_int, C.POINTER(Plane), C.c_int, _P]),
+    "dtg_pack_nchw": (C.c_int, [_P, _P, C.c_int, C.c_int, C.c_int, C.c_int, C.POINTER(Plane), C.c_int, _P]),
     "dtg_unpack_nchw": (C.c_int, [C.POINTER(Plane), C.c_int, C.c_int, _P, _P]),
-    "dtg_grad_gather": (C.c_int, [C.POINTER(C.POINTER(Plane)), C.POINTER(C.c_int), C.c_int, _P, C.c_int,
+    "dtg_grad_gather": (C.c_int, [C.POINTER(C.POINTER(Plane)), C.POINTER(C.c_int), C.c_int, _P, _P, C.c_int,
                                   C.POINTER(Plane), _P, _P]),
     "dtg_channel_sum": (C.c_int, [C.POINTER(Plane), C.c_int, _P, _P]),
     "dtg_loss_lsgan": (C.c_int, [_P, C.c_int, C.c_int, C.c_int, C.c_float, C.c_float, _P, C.c_int, C.c_int,

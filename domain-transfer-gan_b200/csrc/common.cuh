@@ -179,6 +179,14 @@ __host__ __device__ __forceinline__ uint32_t umma_idesc(uint32_t fmt, uint32_t a
   return (1u << 4) | (fmt << 7) | (fmt << 10) | (a_mn << 15) | (b_mn << 16) | ((N >> 3) << 17) | ((M >> 4) << 24);
 }
 
+// fp32 planes feed tcgen05 kind::tf32, which TRUNCATES the low 13 mantissa bits of its operands.
+// Producers therefore store round-to-nearest tf32 values, which removes the truncation bias.
+__device__ __forceinline__ float round_tf32(float v) {
+  uint32_t r;
+  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(v));
+  return __uint_as_float(r);
+}
+
 __device__ __forceinline__ float apply_act(float v, int act) {
   switch (act) {
     case DTG_ACT_RELU: return v > 0.f ? v : 0.f;

@@ -249,7 +249,8 @@ __global__ void __launch_bounds__(kThreads, 1) igemm_kernel(const __grid_constan
 #pragma unroll
                 for (int q = 0; q < 4; ++q) {
                   if (c0 + 4 * q < p.out_C)
-                    reinterpret_cast<float4*>(dst)[q] = make_float4(f[4 * q], f[4 * q + 1], f[4 * q + 2], f[4 * q + 3]);
+                    reinterpret_cast<float4*>(dst)[q] = make_float4(round_tf32(f[4 * q]), round_tf32(f[4 * q + 1]),
+                                                                    round_tf32(f[4 * q + 2]), round_tf32(f[4 * q + 3]));
                 }
               }
             }

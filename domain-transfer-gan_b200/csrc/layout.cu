@@ -20,7 +20,7 @@ __device__ __forceinline__ void st_elem(void* base, size_t idx, int dtype, float
   if (dtype == DTG_BF16)
     reinterpret_cast<__nv_bfloat16*>(base)[idx] = __float2bfloat16_rn(v);
   else
-    reinterpret_cast<float*>(base)[idx] = v;
+    reinterpret_cast<float*>(base)[idx] = round_tf32(v);
 }
 
 // one block-row (blockIdx.y) per item; threads stride over the padded destination
@@ -38,7 +38,8 @@ __global__ void pack_weights_kernel(const dtg_pack_item* items) {
 }
 
 // NCHW fp32 -> plane channels [c_off, c_off+c), mirrored into the halo.  One thread per (n,h,w).
-__global__ void pack_nchw_kernel(const float* __restrict__ src, int n, int c, int h, int w, dtg_plane dst, int c_off) {
+__global__ void pack_nchw_kernel(const float* __restrict__ src, const float* __restrict__ tanh_y, int n, int c, int h, int w,
+                                 dtg_plane dst, int c_off) {
   const size_t total = static_cast<size_t>(n) * h * w;
   const int Hb = dst.h + 2 * dst.halo, Wb = dst.w + 2 * dst.halo;
   for (size_t i = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; i < total;
@@ -49,7 +50,12 @@ __global__ void pack_nchw_kernel(const float* __restrict__ src, int n, int c, in
     int hts[3], wts[3];
     const int nh = reflect_targets(y, h, dst.halo, hts), nw = reflect_targets(x, w, dst.halo, wts);
     for (int ch = 0; ch < c; ++ch) {
-      const float v = src[((static_cast<size_t>(b) * c + ch) * h + y) * w + x];
+      const size_t si = ((static_cast<size_t>(b) * c + ch) * h + y) * w + x;
+      float v = src[si];
+      if (tanh_y) {
+        const float t = tanh_y[si];
+        v *= (1.f - t * t);
+      }
       for (int a = 0; a < nh; ++a)
         for (int q = 0; q < nw; ++q) {
           const size_t pix = (static_cast<size_t>(b) * Hb + hts[a] + dst.halo) * Wb + wts[q] + dst.halo;
@@ -93,8 +99,8 @@ struct GatherArgs {
   int nsrc;
 };
 
-__global__ void grad_gather_kernel(GatherArgs g, const float* __restrict__ tanh_y, int c, dtg_plane out,
-                                   float* __restrict__ out_nchw) {
+__global__ void grad_gather_kernel(GatherArgs g, const float* __restrict__ add_nchw, const float* __restrict__ tanh_y, int c,
+                                   dtg_plane out, float* __restrict__ out_nchw) {
   const int h = out.h, w = out.w;
   const size_t total = static_cast<size_t>(out.n) * h * w;
   for (size_t i = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; i < total;
@@ -106,6 +112,7 @@ __global__ void grad_gather_kernel(GatherArgs g, const float* __restrict__ tanh_
       float acc = 0.f;
       for (int k = 0; k < g.nsrc; ++k) acc += folded_load(g.src[k], b, y, x, g.c_off[k] + ch);
       const size_t di = ((static_cast<size_t>(b) * c + ch) * h + y) * w + x;
+      if (add_nchw) acc += add_nchw[di];
       if (out_nchw) out_nchw[di] = acc;
       if (tanh_y) {
         const float t = tanh_y[di];
@@ -165,11 +172,12 @@ extern "C" int dtg_pack_weights(const dtg_pack_item* items_dev, int nitems, int 
   return DTG_OK;
 }
 
-extern "C" int dtg_pack_nchw(const float* src, int n, int c, int h, int w, const dtg_plane* dst, int c_off, void* stream) {
+extern "C" int dtg_pack_nchw(const float* src, const float* tanh_y, int n, int c, int h, int w, const dtg_plane* dst, int c_off,
+                             void* stream) {
   DTG_REQUIRE(src && dst && dst->ptr, "dtg_pack_nchw: null");
   DTG_REQUIRE(dst->n == n && dst->h == h && dst->w == w && c_off + c <= dst->c, "dtg_pack_nchw: shape mismatch");
   const size_t total = static_cast<size_t>(n) * h * w;
-  pack_nchw_kernel<<<grid_for(total, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(src, n, c, h, w, *dst, c_off);
+  pack_nchw_kernel<<<grid_for(total, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(src, tanh_y, n, c, h, w, *dst, c_off);
   DTG_CHECK_CUDA(cudaGetLastError());
   return DTG_OK;
 }
@@ -182,8 +190,8 @@ extern "C" int dtg_unpack_nchw(const dtg_plane* src, int c_off, int c, float* ds
   return DTG_OK;
 }
 
-extern "C" int dtg_grad_gather(const dtg_plane* const* srcs, const int* c_off, int nsrc, const float* tanh_y, int c,
-                               const dtg_plane* out, float* out_nchw, void* stream) {
+extern "C" int dtg_grad_gather(const dtg_plane* const* srcs, const int* c_off, int nsrc, const float* add_nchw,
+                               const float* tanh_y, int c, const dtg_plane* out, float* out_nchw, void* stream) {
   DTG_REQUIRE(srcs && nsrc >= 1 && nsrc <= 3 && out, "dtg_grad_gather: bad args");
   GatherArgs g;
   memset(&g, 0, sizeof(g));
@@ -197,7 +205,7 @@ extern "C" int dtg_grad_gather(const dtg_plane* const* srcs, const int* c_off, i
   }
   DTG_REQUIRE(out->ptr == nullptr || c <= out->c, "dtg_grad_gather: out channels");
   const size_t total = static_cast<size_t>(out->n) * out->h * out->w;
-  grad_gather_kernel<<<grid_for(total, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(g, tanh_y, c, *out, out_nchw);
+  grad_gather_kernel<<<grid_for(total, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(g, add_nchw, tanh_y, c, *out, out_nchw);
   DTG_CHECK_CUDA(cudaGetLastError());
   return DTG_OK;
 }

@@ -59,7 +59,7 @@ __device__ __forceinline__ void st_plane(const dtg_plane& p, size_t idx, float v
   if (p.dtype == DTG_BF16)
     reinterpret_cast<__nv_bfloat16*>(p.ptr)[idx] = __float2bfloat16_rn(v);
   else
-    reinterpret_cast<float*>(p.ptr)[idx] = v;
+    reinterpret_cast<float*>(p.ptr)[idx] = round_tf32(v);
 }
 
 __global__ void __launch_bounds__(kRedThreads) lsgan_kernel(const float* __restrict__ pred, int n, int h, int w, float target,

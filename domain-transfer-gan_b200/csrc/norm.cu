@@ -46,7 +46,7 @@ struct Vec<float> {
     f[0] = u.x; f[1] = u.y; f[2] = u.z; f[3] = u.w;
   }
   __device__ static __forceinline__ void store(void* p, const float (&f)[4]) {
-    *reinterpret_cast<float4*>(p) = make_float4(f[0], f[1], f[2], f[3]);
+    *reinterpret_cast<float4*>(p) = make_float4(round_tf32(f[0]), round_tf32(f[1]), round_tf32(f[2]), round_tf32(f[3]));
   }
 };
 
@@ -493,8 +493,8 @@ extern "C" int dtg_norm_fwd(const dtg_norm_args* a, const dtg_plane* x, const dt
   if (mode != DTG_NORM_NONE) {
     DTG_REQUIRE(gamma && beta && stats && coef && partial, "dtg_norm_fwd: missing buffers");
     DTG_REQUIRE(mode != DTG_NORM_COND_INSTANCE || hw > 1, "dtg_norm_fwd: conditional instance norm needs H*W > 1");
-    const int cg = std::min(x->c, 8 * V);
-    DTG_REQUIRE(x->c % cg == 0, "dtg_norm_fwd: channels %d not a multiple of the channel group %d", x->c, cg);
+    int cg = 8 * V;
+    while (x->c % cg != 0) cg >>= 1;
     const int splits = pick_splits(x->n, x->c, cg, hw);
     float* bnsum = partial;
     float* part = partial + 2 * x->c;
@@ -547,8 +547,8 @@ extern "C" int dtg_norm_bwd(const dtg_norm_args* a, const dtg_plane* dy, const d
   DTG_REQUIRE(dx->c % V == 0, "dtg_norm_bwd: channels");
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
   const int hw = dx->h * dx->w, n = dx->n, c = dx->c;
-  const int cg = std::min(c, 8 * V);
-  DTG_REQUIRE(c % cg == 0, "dtg_norm_bwd: channel group");
+  int cg = 8 * V;
+  while (c % cg != 0) cg >>= 1;
   const int splits = pick_splits(n, c, cg, hw);
   const dtg_plane p_dy2 = (dy2 && dy2->ptr) ? *dy2 : kNullPlane;
   const dtg_plane p_y = (y && y->ptr) ? *y : kNullPlane;

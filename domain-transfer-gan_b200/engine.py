@@ -1,0 +1,352 @@
+"""Execution engine: flat parameter arenas, per-network layer plans, forward/backward drivers.
+
+A network (networks.py) is described as a chain of ``Layer`` specs (conv [+ norm + activation
+(+ residual)]).  ``NetExec`` owns the packed tensor-core operands of one network and runs a plan on a
+``Ctx`` (the saved activations of ONE invocation) purely through the C ABI (ops.py): no torch
+arithmetic happens here.  Gradients are accumulated straight into the flat fp32 gradient arena in
+PyTorch parameter layout, so ``param.grad`` views and the fused clip+Adam kernel see them in place.
+"""
+import torch
+
+from . import _lib as L
+from . import ops
+
+_PRECISION = {"dtype": torch.bfloat16}
+
+
+def set_precision(name):
+    """'bf16' (tcgen05 kind::f16, bf16 planes) or 'tf32' (kind::tf32, fp32 planes)."""
+    _PRECISION["dtype"] = {"bf16": torch.bfloat16, "tf32": torch.float32}[name]
+
+
+def get_dtype():
+    return _PRECISION["dtype"]
+
+
+def running_pair(bn):
+    """running_mean / running_var of a BatchNorm module as rows of ONE [2, c] fp32 buffer (what
+    dtg_norm_fwd updates in place); the module's registered buffers become views of it, so
+    state_dict() / load_state_dict() keep working."""
+    rp = getattr(bn, "_dtg_pair", None)
+    if rp is None or rp.device != bn.running_mean.device or bn.running_mean.data_ptr() != rp.data_ptr():
+        rp = torch.stack([bn.running_mean.detach().float(), bn.running_var.detach().float()]).contiguous()
+        bn.running_mean = rp[0]
+        bn.running_var = rp[1]
+        object.__setattr__(bn, "_dtg_pair", rp)
+    return rp
+
+
+class ParamArena:
+    """All parameters of one network in one contiguous fp32 buffer (+ grad, Adam m / v).
+
+    Each nn.Parameter's ``.data`` becomes a view into ``flat`` (state_dict / load_state_dict keep
+    working in place) and ``.grad`` a view into ``grad``.  Parameters listed in `inactive` (no gradient
+    in the reference, e.g. enc_logvar with stoch_enc=False) are placed last and excluded from
+    clip / Adam, like torch skips ``grad is None`` parameters.
+    """
+
+    def __init__(self, module, inactive=()):
+        seen, plist = set(), []
+        for name, p in module.named_parameters():   # named_parameters de-duplicates aliases
+            if id(p) not in seen:
+                seen.add(id(p))
+                plist.append((name, p))
+        act = [(n, p) for n, p in plist if n not in inactive]
+        ina = [(n, p) for n, p in plist if n in inactive]
+        self.module = module
+        self.entries = act + ina
+        self.inactive_names = set(inactive)
+        self.flat = None
+        self._build()
+
+    def _build(self):
+        dev = self.entries[0][1].device
+        total, offs = 0, []
+        for _, p in self.entries:
+            offs.append(total)
+            total += (p.numel() + 3) // 4 * 4          # keep every tensor 16-byte aligned
+        self.active_count = 0
+        for (n, p), o in zip(self.entries, offs):
+            if n not in self.inactive_names:
+                self.active_count = o + (p.numel() + 3) // 4 * 4
+        self.total = total
+        self.flat = torch.zeros(total, dtype=torch.float32, device=dev)
+        self.grad = torch.zeros(total, dtype=torch.float32, device=dev)
+        self.m = torch.zeros(total, dtype=torch.float32, device=dev)
+        self.v = torch.zeros(total, dtype=torch.float32, device=dev)
+        self.views, self.gviews = {}, {}
+        for (n, p), o in zip(self.entries, offs):
+            v = self.flat[o:o + p.numel()].view(p.shape)
+            v.copy_(p.data)
+            p.data = v
+            g = self.grad[o:o + p.numel()].view(p.shape)
+            p.grad = None if n in self.inactive_names else g
+            self.views[n] = v
+            self.gviews[n] = g
+        self.device = dev
+
+    def ensure(self):
+        """Re-flatten if the module was moved (.cuda()/.to()) after construction."""
+        p0 = self.entries[0][1]
+        if p0.device != self.device or p0.data_ptr() != self.flat.data_ptr():
+            self._build()
+            return True
+        for (n, p) in self.entries:   # .grad may have been reset by zero_grad(set_to_none=True)
+            if n not in self.inactive_names and (p.grad is None or p.grad.data_ptr() != self.gviews[n].data_ptr()):
+                p.grad = self.gviews[n]
+        return False
+
+    def g(self, param):
+        """gradient view of a parameter object"""
+        for (n, p) in self.entries:
+            if p is param:
+                return self.gviews[n]
+        raise KeyError("parameter not in arena")
+
+
+class Layer:
+    """conv (+ norm + act (+ residual)) -> activation plane, or a head conv -> dense NCHW fp32."""
+
+    def __init__(self, name, src, conv, cin, cout, k, stride=1, pad=0, transposed=False, norm=L.NORM_NONE,
+                 act=L.ACT_NONE, norm_mod=None, out_halo=0, residual=None, head=False, use_bias=True,
+                 spatial=None):
+        self.name, self.src, self.conv = name, src, conv
+        self.cin, self.cout, self.k, self.stride, self.pad, self.transposed = cin, cout, k, stride, pad, transposed
+        self.norm, self.act, self.norm_mod = norm, act, norm_mod
+        self.out_halo, self.residual, self.head = out_halo, residual, head
+        # a bias in front of a mean-removing norm is a mathematical no-op: skipped (its gradient is exactly
+        # 0).  Batch norm keeps it in the forward because running_mean must include it.
+        self.use_bias = use_bias and norm == L.NORM_NONE and conv.bias is not None
+        self.fwd_bias = self.use_bias or (norm == L.NORM_BATCH and conv.bias is not None)
+        self.w_f = self.w_d = None
+
+    def out_hw(self, h, w):
+        if self.transposed:       # k3 s2 p1 op1 -> exactly 2x
+            return h * self.stride, w * self.stride
+        return (h + 2 * self.pad - self.k) // self.stride + 1, (w + 2 * self.pad - self.k) // self.stride + 1
+
+
+class Ctx:
+    """Saved state of one forward invocation of a network (static buffers, CUDA-graph friendly)."""
+
+    def __init__(self):
+        self.acts = {}      # index -> PlaneT (0 = packed input)
+        self.yraw = {}      # layer idx -> PlaneT (conv output before the norm)
+        self.nst = {}       # layer idx -> NormState
+        self.cin = {}       # layer idx -> (gamma, beta) [n, c]
+        self.gact = {}      # act index -> gradient plane (ring = act halo)
+        self.dres = {}      # act index -> residual-branch gradient plane
+        self.dyraw = {}     # layer idx -> gradient w.r.t. the conv output
+        self.heads = {}     # layer name -> dense NCHW fp32 output
+        self.z = None       # [n, nz] fp32 (CIN networks)
+        self.dz = None
+
+
+class NetExec:
+    def __init__(self, module, layers, in_channels, in_halo, arena, nz=0):
+        self.module, self.layers, self.arena = module, layers, arena
+        self.in_channels, self.in_halo, self.nz = in_channels, in_halo, nz
+        self.dtype = None
+        self.pack = None
+        self._ctx_cache = {}
+
+    # ---- operands ----------------------------------------------------------------------------
+    def prepare(self, dtype=None):
+        dtype = dtype or get_dtype()
+        rebuilt = self.arena.ensure()
+        if self.pack is None or rebuilt or dtype != self.dtype:
+            self.dtype = dtype
+            self.pack = ops.PackTable(self.arena.device)
+            for ly in self.layers:
+                w = ly.conv.weight
+                w4 = w if w.dim() == 4 else w.view(w.shape[0], w.shape[1], 1, 1)
+                if ly.transposed:
+                    ly.w_f = ops.add_packed(self.pack, w4, dtype, "tfwd")
+                    ly.w_d = ops.add_packed(self.pack, w4, dtype, "tdgrad")
+                else:
+                    ly.w_f = ops.add_packed(self.pack, w4, dtype, "fwd")
+                    ly.w_d = ops.add_packed(self.pack, w4, dtype, "dgrad")
+            self._ctx_cache = {}
+            self.repack()
+
+    def repack(self):
+        """refresh the packed bf16/tf32 operands from the fp32 master weights (after an optimizer step)"""
+        self.pack.run()
+
+    # ---- contexts ----------------------------------------------------------------------------
+    def new_ctx(self, n, h, w, tag=0):
+        key = (n, h, w, tag)
+        if key in self._ctx_cache:
+            return self._ctx_cache[key]
+        dt, dev = self.dtype, self.arena.device
+        c = Ctx()
+        c.n = n
+        c.acts[0] = ops.PlaneT(n, h, w, ops.cpad(self.in_channels, dt), self.in_halo, dt, dev)
+        dims = {0: (h, w)}
+        for i, ly in enumerate(self.layers):
+            ih, iw = dims[ly.src]
+            oh, ow = ly.out_hw(ih, iw)
+            cs = ops.cpad(ly.cout, dt)
+            if ly.head:
+                c.heads[ly.name] = torch.zeros(n, ly.cout, oh, ow, dtype=torch.float32, device=dev)
+                c.dyraw[i] = ops.PlaneT(n, oh, ow, cs, 0, dt, dev)      # seed gradient plane
+                continue
+            dims[i + 1] = (oh, ow)
+            c.acts[i + 1] = ops.PlaneT(n, oh, ow, cs, ly.out_halo, dt, dev)
+            if ly.norm != L.NORM_NONE:
+                c.yraw[i] = ops.PlaneT(n, oh, ow, cs, 0, dt, dev)
+                c.nst[i] = ops.NormState(c.yraw[i])
+                if ly.norm == L.NORM_COND_INSTANCE:
+                    c.cin[i] = (torch.zeros(n, cs, device=dev), torch.zeros(n, cs, device=dev))
+            else:
+                c.nst[i] = ops.NormState(c.acts[i + 1])
+            c.dyraw[i] = ops.PlaneT(n, oh, ow, cs, 0, dt, dev)
+        c.dims = dims
+        if self.nz:
+            c.z = torch.zeros(n, self.nz, dtype=torch.float32, device=dev)
+            c.dz = torch.zeros(n, self.nz, dtype=torch.float32, device=dev)
+        self._ctx_cache[key] = c
+        return c
+
+    def _gact(self, c, idx, consumer):
+        """gradient plane of activation `idx` produced by the dgrad of layer `consumer`"""
+        key = (idx, consumer)
+        if key not in c.gact:
+            a = c.acts[idx]
+            c.gact[key] = ops.PlaneT(a.n, a.h, a.w, a.c, a.halo, a.dtype, a.t.device)
+        return c.gact[key]
+
+    def _dres(self, c, idx):
+        if idx not in c.dres:
+            a = c.acts[idx]
+            c.dres[idx] = ops.PlaneT(a.n, a.h, a.w, a.c, 0, a.dtype, a.t.device)
+        return c.dres[idx]
+
+    # ---- forward -----------------------------------------------------------------------------
+    def forward(self, c, sync_bn=None):
+        """c.acts[0] (and c.z) must be filled.  Returns dict of head outputs."""
+        for i, ly in enumerate(self.layers):
+            a_in = c.acts[ly.src]
+            ih, iw = c.dims[ly.src]
+            oh, ow = ly.out_hw(ih, iw)
+            mode = L.CONV_DGRAD if ly.transposed else L.CONV_FWD
+            kw = dict(mode=mode, kh=ly.k, kw=ly.k, stride=ly.stride, pad=ly.pad, cout=ly.cout, out_h=oh, out_w=ow)
+            bias = ly.conv.bias if ly.use_bias else None
+            if ly.head:
+                ops.conv(a_in, ly.w_f, bias, None, act=ly.act, out_nchw=c.heads[ly.name], **kw)
+                continue
+            out = c.acts[i + 1]
+            if ly.norm == L.NORM_NONE:
+                ops.conv(a_in, ly.w_f, bias, out, act=ly.act, out_reflect=ly.out_halo > 0, **kw)
+                continue
+            ops.conv(a_in, ly.w_f, ly.conv.bias if ly.fwd_bias else None, c.yraw[i], **kw)
+            nm = ly.norm_mod
+            res = c.acts[ly.residual] if ly.residual is not None else None
+            if ly.norm == L.NORM_COND_INSTANCE:
+                gam, bet = c.cin[i]
+                sc, sh = nm.scale_conv[0], nm.shift_conv[0]
+                ops.cin_affine_fwd(c.z, sc.weight, sc.bias, sh.weight, sh.bias, gam, bet)
+                ops.norm_fwd(c.yraw[i], out, c.nst[i], mode=ly.norm, act=ly.act, gamma=gam, beta=bet, residual=res,
+                             eps=nm.eps)
+            elif ly.norm == L.NORM_INSTANCE:
+                ops.norm_fwd(c.yraw[i], out, c.nst[i], mode=ly.norm, act=ly.act, gamma=nm.scale, beta=nm.shift,
+                             residual=res, eps=nm.eps)
+            else:  # batch norm (training mode; running stats live in one [2, c] buffer)
+                if sync_bn is None:
+                    ops.norm_fwd(c.yraw[i], out, c.nst[i], mode=ly.norm, act=ly.act, gamma=nm.weight, beta=nm.bias,
+                                 bn_running=running_pair(nm), eps=nm.eps, momentum=nm.momentum)
+                else:
+                    ops.norm_fwd(c.yraw[i], out, c.nst[i], mode=ly.norm, act=ly.act, gamma=nm.weight, beta=nm.bias,
+                                 bn_running=running_pair(nm), eps=nm.eps, momentum=nm.momentum, phase=1)
+                    sync_bn(c.nst[i].ws[:2 * out.c])
+                    ops.norm_fwd(c.yraw[i], out, c.nst[i], mode=ly.norm, act=ly.act, gamma=nm.weight, beta=nm.bias,
+                                 bn_running=running_pair(nm), eps=nm.eps, momentum=nm.momentum, phase=2,
+                                 world_size=sync_bn.world_size)
+                nm.num_batches_tracked += 1
+        return c.heads
+
+    # ---- backward ----------------------------------------------------------------------------
+    def backward(self, c, seeds, want_dx=False, want_dw=True, want_dz=False, sync_bn=None):
+        """seeds: {head layer name: True} -- the seed gradient planes c.dyraw[idx] of those heads have been
+        filled by the caller (loss kernels / pack_nchw).  Parameter gradients accumulate into the arena.
+        Returns the input-gradient plane (ring = input halo) if want_dx."""
+        A = self.arena
+        pending = {}      # act index -> (dy plane, dy2 plane)
+        if want_dz and c.dz is not None:
+            c.dz.zero_()
+        for i in range(len(self.layers) - 1, -1, -1):
+            ly = self.layers[i]
+            a_in = c.acts[ly.src]
+            dyr = c.dyraw[i]
+            if ly.head:
+                if ly.name not in seeds:
+                    continue
+                if want_dw and ly.use_bias:
+                    ops.channel_sum(dyr, ly.cout, A.g(ly.conv.bias))
+            else:
+                if (i + 1) not in pending:
+                    continue        # no gradient reaches this layer (e.g. logvar branch)
+                dy, dy2 = pending.pop(i + 1)
+                nm = ly.norm_mod
+                d_res = self._dres(c, ly.residual) if ly.residual is not None else None
+                y = c.acts[i + 1] if ly.act != L.ACT_NONE else None
+                if ly.norm == L.NORM_NONE:
+                    ops.norm_bwd(dy, dyr, c.nst[i], mode=L.NORM_NONE, act=ly.act, y=y, dy2=dy2,
+                                 d_beta=A.g(ly.conv.bias) if (want_dw and ly.use_bias) else None)
+                elif ly.norm == L.NORM_COND_INSTANCE:
+                    gam, bet = c.cin[i]
+                    ops.norm_bwd(dy, dyr, c.nst[i], mode=ly.norm, act=ly.act, y=y, x=c.yraw[i], gamma=gam, dy2=dy2,
+                                 d_res=d_res)
+                    if want_dw or want_dz:
+                        sc, sh = nm.scale_conv[0], nm.shift_conv[0]
+                        if want_dw:
+                            tg = (A.g(sc.weight), A.g(sc.bias), A.g(sh.weight), A.g(sh.bias))
+                        else:
+                            tg = self._scratch_cin(sc)
+                        ops.cin_affine_bwd(c.z, sc.weight, sh.weight, gam, bet, c.nst[i].sums, *tg,
+                                           c.dz if want_dz else None)
+                elif ly.norm == L.NORM_INSTANCE:
+                    ops.norm_bwd(dy, dyr, c.nst[i], mode=ly.norm, act=ly.act, y=y, x=c.yraw[i], gamma=nm.scale, dy2=dy2,
+                                 d_res=d_res, d_gamma=A.g(nm.scale) if want_dw else None,
+                                 d_beta=A.g(nm.shift) if want_dw else None)
+                else:
+                    kw = dict(mode=ly.norm, act=ly.act, y=y, x=c.yraw[i], gamma=nm.weight, dy2=dy2, d_res=d_res,
+                              d_gamma=A.g(nm.weight) if want_dw else None, d_beta=A.g(nm.bias) if want_dw else None)
+                    if sync_bn is None:
+                        ops.norm_bwd(dy, dyr, c.nst[i], **kw)
+                    else:
+                        ops.norm_bwd(dy, dyr, c.nst[i], phase=1, **kw)
+                        sync_bn(c.nst[i].ws[:2 * dyr.c])
+                        ops.norm_bwd(dy, dyr, c.nst[i], phase=2, world_size=sync_bn.world_size, **kw)
+                if ly.residual is not None:
+                    d0, d1 = pending.get(ly.residual, (None, None))
+                    pending[ly.residual] = (d_res, d1) if d0 is None else (d0, d_res)
+            # weight gradient
+            if want_dw:
+                dw = A.g(ly.conv.weight)
+                if ly.transposed:
+                    ops.conv_wgrad(a_in, dyr, dw, kh=ly.k, kw=ly.k, stride=ly.stride, pad=ly.pad, pa=ly.cin, qb=ly.cout)
+                else:
+                    ops.conv_wgrad(dyr, a_in, dw, kh=ly.k, kw=ly.k, stride=ly.stride, pad=ly.pad, pa=ly.cout, qb=ly.cin)
+            # data gradient
+            if ly.src > 0 or want_dx:
+                gin = self._gact(c, ly.src, i)
+                ih, iw = c.dims[ly.src]
+                if ly.transposed:
+                    ops.conv(dyr, ly.w_d, None, gin, mode=L.CONV_FWD, kh=ly.k, kw=ly.k, stride=ly.stride, pad=ly.pad,
+                             cout=ly.cin, out_h=ih, out_w=iw)
+                else:
+                    ops.conv(dyr, ly.w_d, None, gin, mode=L.CONV_DGRAD, kh=ly.k, kw=ly.k, stride=ly.stride, pad=ly.pad,
+                             ring=a_in.halo, cout=ly.cin, out_h=ih, out_w=iw)
+                d0, d1 = pending.get(ly.src, (None, None))
+                assert d0 is None or d1 is None, "more than two gradient contributions for one activation"
+                pending[ly.src] = (gin, d1) if d0 is None else (gin, d0)
+        return pending.get(0, (None, None))[0] if want_dx else None
+
+    def _scratch_cin(self, sc):
+        key = ("cin_scratch", sc.weight.shape)
+        if key not in self._ctx_cache:
+            dev = self.arena.device
+            self._ctx_cache[key] = (torch.zeros_like(sc.weight), torch.zeros_like(sc.bias),
+                                    torch.zeros_like(sc.weight), torch.zeros_like(sc.bias))
+        return self._ctx_cache[key]

@@ -46,6 +46,14 @@ class PlaneT:
     def to_nchw(self, c=None):
         return self.interior()[..., :c].permute(0, 3, 1, 2).float().contiguous()
 
+    def batch_slice(self, i0, i1):
+        """view of images [i0, i1) as a plane of batch i1-i0 (shares memory)"""
+        v = PlaneT.__new__(PlaneT)
+        v.n, v.h, v.w, v.c, v.halo, v.dtype = i1 - i0, self.h, self.w, self.c, self.halo, self.dtype
+        v.t = self.t[i0:i1]
+        v._s = L.Plane(v.t.data_ptr(), v.n, v.h, v.w, v.c, v.halo, _DT[self.dtype])
+        return v
+
     @staticmethod
     def from_nchw(x, halo=0, dtype=torch.bfloat16, c_store=None, reflect=True):
         """test helper: build a plane from an NCHW tensor through the library's own pack kernel."""
@@ -58,10 +66,10 @@ class PlaneT:
 NULL_PLANE = C.POINTER(L.Plane)()
 
 
-def pack_nchw(src, dst, c_off=0):
+def pack_nchw(src, dst, c_off=0, tanh_y=None):
     n, c, h, w = src.shape
     assert src.dtype == torch.float32 and src.is_contiguous()
-    L.check(L.lib().dtg_pack_nchw(_ptr(src), n, c, h, w, dst.s, c_off, _stream()), "pack_nchw")
+    L.check(L.lib().dtg_pack_nchw(_ptr(src), _ptr(tanh_y), n, c, h, w, dst.s, c_off, _stream()), "pack_nchw")
 
 
 def unpack_nchw(src, c, c_off=0, out=None):
@@ -213,7 +221,7 @@ def cin_affine_bwd(z, ws, wb, gamma, beta, sums, d_ws, d_bs, d_wb, d_bb, d_z):
             "cin_affine_bwd")
 
 
-def grad_gather(srcs, c_offs, c, out=None, tanh_y=None, out_nchw=None):
+def grad_gather(srcs, c_offs, c, out=None, tanh_y=None, out_nchw=None, add_nchw=None):
     arr = (C.POINTER(L.Plane) * len(srcs))(*[C.pointer(s._s) for s in srcs])
     offs = (C.c_int * len(srcs))(*c_offs)
     if out is None:
@@ -222,7 +230,7 @@ def grad_gather(srcs, c_offs, c, out=None, tanh_y=None, out_nchw=None):
         outp = C.byref(dummy)
     else:
         outp = out.s
-    L.check(L.lib().dtg_grad_gather(arr, offs, len(srcs), _ptr(tanh_y), c, outp, _ptr(out_nchw), _stream()), "grad_gather")
+    L.check(L.lib().dtg_grad_gather(arr, offs, len(srcs), _ptr(add_nchw), _ptr(tanh_y), c, outp, _ptr(out_nchw), _stream()), "grad_gather")
 
 
 def channel_sum(x, c, d_bias):

@@ -171,18 +171,22 @@ int dtg_cin_affine_bwd(const float* z, const float* ws, const float* wb, const f
  * Layout conversion at network entry/exit (the reference tensors are fp32 NCHW, dataloader.py:33):
  * dtg_pack_nchw writes channels [c_off, c_off+c) of `dst` from a dense NCHW fp32 tensor (this is
  * also torch.cat on channels, model.py:410,472) and mirrors them into dst.halo (ReflectionPad2d(3),
- * networks.py:159,211).  dtg_unpack_nchw is the inverse for the interior.
+ * networks.py:159,211).  If tanh_y != NULL (same shape as src) the values are multiplied by
+ * 1 - tanh_y^2 first (Tanh backward when src is a gradient w.r.t. a generator output).
+ * dtg_unpack_nchw is the inverse for the interior.
  * ------------------------------------------------------------------------------------------- */
-int dtg_pack_nchw(const float* src, int n, int c, int h, int w, const dtg_plane* dst, int c_off, void* stream);
+int dtg_pack_nchw(const float* src, const float* tanh_y, int n, int c, int h, int w, const dtg_plane* dst, int c_off,
+                  void* stream);
 int dtg_unpack_nchw(const dtg_plane* src, int c_off, int c, float* dst, void* stream);
 
 /* Sum of up to 3 gradient planes (each optionally with a halo to fold, channel offset c_off[i]),
  * optionally multiplied by tanh'(y) = 1 - y^2 (y dense NCHW fp32, the generator output), written to
  * `out` channels [0,c).  Implements autograd's fan-in accumulation for fake_A / fake_B
  *  fused with Tanh backward (networks.py:188,243).  Also emits the dense NCHW fp32
- * gradient if out_nchw != NULL. */
-int dtg_grad_gather(const dtg_plane* const* srcs, const int* c_off, int nsrc, const float* tanh_y, int c,
-                    const dtg_plane* out, float* out_nchw, void* stream);
+ * gradient (before the tanh factor) if out_nchw != NULL; add_nchw is an optional dense fp32
+ * [n][c][h][w] addend (e.g. dz of the CIN projections added to D_z_B's input gradient). */
+int dtg_grad_gather(const dtg_plane* const* srcs, const int* c_off, int nsrc, const float* add_nchw,
+                    const float* tanh_y, int c, const dtg_plane* out, float* out_nchw, void* stream);
 
 /* per-channel sum over (n,h,w) of a plane's interior: d_bias[c] += sum  (conv bias gradients) */
 int dtg_channel_sum(const dtg_plane* x, int c, float* d_bias, void* stream);

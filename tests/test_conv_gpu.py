@@ -17,7 +17,7 @@ def _q(t, dtype):
     """round to what the plane stores (bf16) / what tcgen05 kind::tf32 consumes (10-bit mantissa, truncation)."""
     if dtype == torch.bfloat16:
         return t.to(torch.bfloat16).float()
-    return (t.view(torch.int32) & ~0x1FFF).view(torch.float32)
+    return ((t.view(torch.int32) + 0x1000) & ~0x1FFF).view(torch.float32)   # round-to-nearest tf32
 
 
 def _tol(dtype):

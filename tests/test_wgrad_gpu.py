@@ -15,7 +15,7 @@ DEV = "cuda"
 def _q(t, dtype):
     if dtype == torch.bfloat16:
         return t.to(torch.bfloat16).float()
-    return (t.view(torch.int32) & ~0x1FFF).view(torch.float32)
+    return ((t.view(torch.int32) + 0x1000) & ~0x1FFF).view(torch.float32)   # round-to-nearest tf32
 
 
 CASES = [
