@@ -43,6 +43,7 @@ _lib = None
 _P = C.c_void_p
 _SIGS = {
     "dtg_version": (C.c_int, []),
+    "dtg_launch_count": (C.c_ulonglong, []),
     "dtg_last_error": (C.c_int, [C.c_char_p, C.c_size_t]),
     "dtg_pack_weights": (C.c_int, [_P, C.c_int, C.c_int, _P]),
     "dtg_conv": (C.c_int, [C.POINTER(ConvArgs), C.POINTER(Plane), _P, C.c_int, C.c_int, _P, C.POINTER(Plane), _P, _P]),
@@ -59,7 +60,7 @@ _SIGS = {
     "dtg_unpack_nchw": (C.c_int, [C.POINTER(Plane), C.c_int, C.c_int, _P, _P]),
     "dtg_grad_gather": (C.c_int, [C.POINTER(C.POINTER(Plane)), C.POINTER(C.c_int), C.c_int, _P, _P, C.c_int,
                                   C.POINTER(Plane), _P, _P]),
-    "dtg_channel_sum": (C.c_int, [C.POINTER(Plane), C.c_int, _P, _P]),
+    "dtg_channel_sum": (C.c_int, [C.POINTER(Plane), C.c_int, _P, _P, _P]),
     "dtg_loss_lsgan": (C.c_int, [_P, C.c_int, C.c_int, C.c_int, C.c_float, C.c_float, _P, C.c_int, C.c_int,
                                  C.POINTER(Plane), _P, _P]),
     "dtg_loss_l1": (C.c_int, [_P, _P, C.c_int, C.c_int, C.c_int, C.c_int, C.c_float, C.c_int, _P, C.c_int, C.c_int,

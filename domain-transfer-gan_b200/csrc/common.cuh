@@ -25,6 +25,14 @@ int cu_fail(CUresult e, const char* what);
     if (_e != cudaSuccess) return ::dtg::cuda_fail(_e, #expr); \
   } while (0)
 
+// every kernel launch site: bump the library-wide launch counter, then surface launch errors
+void count_launch();
+#define DTG_LAUNCHED()                         \
+  do {                                         \
+    ::dtg::count_launch();                     \
+    DTG_CHECK_CUDA(cudaGetLastError());        \
+  } while (0)
+
 #define DTG_REQUIRE(cond, ...)            \
   do {                                    \
     if (!(cond)) {                        \

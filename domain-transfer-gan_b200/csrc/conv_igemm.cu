@@ -321,7 +321,7 @@ static int launch_igemm(const IgemmParams& p, cudaStream_t stream) {
   const int total = p.tiles_w * p.tiles_h * p.tiles_n * p.num_phases;
   const int grid = std::max(1, std::min(total, num_sms));
   igemm_kernel<TF32><<<grid, kThreads, smem, stream>>>(p);
-  DTG_CHECK_CUDA(cudaGetLastError());
+  DTG_LAUNCHED();
   return DTG_OK;
 }
 

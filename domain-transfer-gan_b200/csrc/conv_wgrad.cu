@@ -335,10 +335,10 @@ extern "C" int dtg_conv_wgrad(const dtg_wgrad_args* a, const dtg_plane* pp, cons
     wgrad_kernel<true><<<grid, kWThreads, smem, stream>>>(p);
   else
     wgrad_kernel<false><<<grid, kWThreads, smem, stream>>>(p);
-  DTG_CHECK_CUDA(cudaGetLastError());
+  DTG_LAUNCHED();
   const int total = pl.ntaps * a->pa * a->qb;
   const int rgrid = std::max(1, std::min((total + 255) / 256, 148 * 8));
   wgrad_reduce_kernel<<<rgrid, 256, 0, stream>>>(p.ws, dw, pl.splits, pl.ntaps, p.mtot, pl.n_umma, a->pa, a->qb);
-  DTG_CHECK_CUDA(cudaGetLastError());
+  DTG_LAUNCHED();
   return DTG_OK;
 }

@@ -1,6 +1,8 @@
 // Layout kernels: weight packing for the implicit-GEMM operands, NCHW fp32 <-> NHWC plane
 // conversion at network entry/exit (with reflection halo), gradient fan-in gather (+tanh backward),
 // per-channel sums (bias gradients).  All HBM-bound, coalesced along the contiguous axis.
+#include <algorithm>
+
 #include "common.cuh"
 
 namespace dtg {
@@ -126,30 +128,60 @@ __global__ void grad_gather_kernel(GatherArgs g, const float* __restrict__ add_n
   }
 }
 
-// d_bias[c] += sum over pixels; one block per 32 channels x pixel-slab, warp shuffle + atomics-free
-// final pass through a second tiny kernel would be overkill: the tensors this runs on are small
-// (network heads), so a single block per channel group does a fixed-order tree reduction.
-__global__ void channel_sum_kernel(dtg_plane x, int c, float* __restrict__ d_bias) {
-  const int ch = blockIdx.x;
-  if (ch >= c) return;
+// d_bias[c] += sum over (n,h,w) of a plane, c <= 16 (network heads).  Two-stage inside one launch: per-block
+// partials, the last block to finish adds them up in a fixed order (deterministic, no float atomics).
+constexpr int kCsBlocks = 96;
+struct ChanSumWs {
+  unsigned int counter;
+  unsigned int pad[15];
+  float part[kCsBlocks][16];
+};
+
+__global__ void __launch_bounds__(256) channel_sum_kernel(dtg_plane x, int c, float* __restrict__ d_bias, ChanSumWs* ws) {
   const int Hb = x.h + 2 * x.halo, Wb = x.w + 2 * x.halo;
   const size_t total = static_cast<size_t>(x.n) * x.h * x.w;
-  float acc = 0.f;
-  for (size_t i = threadIdx.x; i < total; i += blockDim.x) {
+  float acc[16];
+#pragma unroll
+  for (int k = 0; k < 16; ++k) acc[k] = 0.f;
+  for (size_t i = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; i < total;
+       i += static_cast<size_t>(gridDim.x) * blockDim.x) {
     const int xx = i % x.w;
     const int yy = (i / x.w) % x.h;
     const int b = i / (static_cast<size_t>(x.w) * x.h);
     const size_t pix = (static_cast<size_t>(b) * Hb + yy + x.halo) * Wb + xx + x.halo;
-    acc += ld_elem(x.ptr, pix * x.c + ch, x.dtype);
+#pragma unroll
+    for (int k = 0; k < 16; ++k)
+      if (k < c) acc[k] += ld_elem(x.ptr, pix * x.c + k, x.dtype);
   }
-  __shared__ float red[32];
-  for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
-  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = acc;
-  __syncthreads();
-  if (threadIdx.x < 32) {
-    float v = threadIdx.x < (blockDim.x >> 5) ? red[threadIdx.x] : 0.f;
+  __shared__ float red[8][16];
+  __shared__ bool last;
+#pragma unroll
+  for (int k = 0; k < 16; ++k) {
+    float v = acc[k];
     for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
-    if (threadIdx.x == 0) d_bias[ch] += v;
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5][k] = v;
+  }
+  __syncthreads();
+  if (threadIdx.x < 16) {
+    float v = 0.f;
+    for (int w = 0; w < 8; ++w) v += red[w][threadIdx.x];
+    ws->part[blockIdx.x][threadIdx.x] = v;
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    __threadfence();
+    const unsigned int prev = atomicAdd(&ws->counter, 1u);
+    last = prev == gridDim.x - 1;
+    if (last) {
+      ws->counter = 0;
+      __threadfence();
+    }
+  }
+  __syncthreads();
+  if (last && threadIdx.x < c) {
+    float v = 0.f;
+    for (unsigned int b = 0; b < gridDim.x; ++b) v += ws->part[b][threadIdx.x];
+    d_bias[threadIdx.x] += v;
   }
 }
 
@@ -168,7 +200,7 @@ extern "C" int dtg_pack_weights(const dtg_pack_item* items_dev, int nitems, int 
   DTG_REQUIRE(items_dev && nitems > 0, "dtg_pack_weights: no items");
   dim3 grid(grid_for(static_cast<size_t>(max_elems), 256, 64), nitems);
   pack_weights_kernel<<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(items_dev);
-  DTG_CHECK_CUDA(cudaGetLastError());
+  DTG_LAUNCHED();
   return DTG_OK;
 }
 
@@ -178,7 +210,7 @@ extern "C" int dtg_pack_nchw(const float* src, const float* tanh_y, int n, int c
   DTG_REQUIRE(dst->n == n && dst->h == h && dst->w == w && c_off + c <= dst->c, "dtg_pack_nchw: shape mismatch");
   const size_t total = static_cast<size_t>(n) * h * w;
   pack_nchw_kernel<<<grid_for(total, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(src, tanh_y, n, c, h, w, *dst, c_off);
-  DTG_CHECK_CUDA(cudaGetLastError());
+  DTG_LAUNCHED();
   return DTG_OK;
 }
 
@@ -186,7 +218,7 @@ extern "C" int dtg_unpack_nchw(const dtg_plane* src, int c_off, int c, float* ds
   DTG_REQUIRE(src && src->ptr && dst && c_off + c <= src->c, "dtg_unpack_nchw: bad args");
   const size_t total = static_cast<size_t>(src->n) * src->h * src->w;
   unpack_nchw_kernel<<<grid_for(total, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(*src, c_off, c, dst);
-  DTG_CHECK_CUDA(cudaGetLastError());
+  DTG_LAUNCHED();
   return DTG_OK;
 }
 
@@ -206,13 +238,15 @@ extern "C" int dtg_grad_gather(const dtg_plane* const* srcs, const int* c_off, i
   DTG_REQUIRE(out->ptr == nullptr || c <= out->c, "dtg_grad_gather: out channels");
   const size_t total = static_cast<size_t>(out->n) * out->h * out->w;
   grad_gather_kernel<<<grid_for(total, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(g, add_nchw, tanh_y, c, *out, out_nchw);
-  DTG_CHECK_CUDA(cudaGetLastError());
+  DTG_LAUNCHED();
   return DTG_OK;
 }
 
-extern "C" int dtg_channel_sum(const dtg_plane* x, int c, float* d_bias, void* stream) {
-  DTG_REQUIRE(x && x->ptr && d_bias && c <= x->c, "dtg_channel_sum: bad args");
-  channel_sum_kernel<<<c, 256, 0, static_cast<cudaStream_t>(stream)>>>(*x, c, d_bias);
-  DTG_CHECK_CUDA(cudaGetLastError());
+extern "C" int dtg_channel_sum(const dtg_plane* x, int c, float* d_bias, void* workspace, void* stream) {
+  DTG_REQUIRE(x && x->ptr && d_bias && workspace && c <= x->c && c <= 16, "dtg_channel_sum: bad args (c <= 16)");
+  const size_t total = static_cast<size_t>(x->n) * x->h * x->w;
+  const int blocks = static_cast<int>(std::max<size_t>(1, std::min<size_t>((total + 1023) / 1024, kCsBlocks)));
+  channel_sum_kernel<<<blocks, 256, 0, static_cast<cudaStream_t>(stream)>>>(*x, c, d_bias, reinterpret_cast<ChanSumWs*>(workspace));
+  DTG_LAUNCHED();
   return DTG_OK;
 }

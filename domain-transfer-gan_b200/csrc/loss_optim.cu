@@ -224,7 +224,7 @@ extern "C" int dtg_loss_lsgan(const float* pred, int n, int h, int w, float targ
   }
   lsgan_kernel<<<red_blocks(static_cast<size_t>(n) * h * w), kRedThreads, 0, static_cast<cudaStream_t>(stream)>>>(
       pred, n, h, w, target, grad_scale, scalars, slot_loss, slot_mean, dp, reinterpret_cast<RedWs*>(workspace));
-  DTG_CHECK_CUDA(cudaGetLastError());
+  DTG_LAUNCHED();
   return DTG_OK;
 }
 
@@ -238,7 +238,7 @@ extern "C" int dtg_loss_l1(const float* a, const float* b, int n, int c, int h, 
   }
   l1_kernel<<<red_blocks(static_cast<size_t>(n) * c * h * w), kRedThreads, 0, static_cast<cudaStream_t>(stream)>>>(
       a, b, n, c, h, w, grad_scale, tanh_bwd, scalars, slot_loss, slot_aux, dp, reinterpret_cast<RedWs*>(workspace));
-  DTG_CHECK_CUDA(cudaGetLastError());
+  DTG_LAUNCHED();
   return DTG_OK;
 }
 
@@ -247,7 +247,7 @@ extern "C" int dtg_grad_sumsq(const float* g, size_t count, float grad_scale, fl
   DTG_REQUIRE((reinterpret_cast<uintptr_t>(g) & 15) == 0, "dtg_grad_sumsq: arena must be 16-byte aligned");
   sumsq_kernel<<<red_blocks(count / 4), kRedThreads, 0, static_cast<cudaStream_t>(stream)>>>(g, count, grad_scale, out_sumsq,
                                                                                               reinterpret_cast<RedWs*>(workspace));
-  DTG_CHECK_CUDA(cudaGetLastError());
+  DTG_LAUNCHED();
   return DTG_OK;
 }
 
@@ -256,13 +256,13 @@ extern "C" int dtg_adam_clip(float* p, float* g, float* m, float* v, size_t coun
   DTG_REQUIRE(p && g && m && v && hyper && sumsq && step_dev, "dtg_adam_clip: null argument");
   const int grid = static_cast<int>(std::max<size_t>(1, std::min<size_t>((count + 255) / 256, 148 * 8)));
   adam_clip_kernel<<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(p, g, m, v, count, hyper, sumsq, step_dev, grad_scale);
-  DTG_CHECK_CUDA(cudaGetLastError());
+  DTG_LAUNCHED();
   return DTG_OK;
 }
 
 extern "C" int dtg_step_increment(int32_t* step_dev, void* stream) {
   DTG_REQUIRE(step_dev, "dtg_step_increment: null");
   step_inc_kernel<<<1, 1, 0, static_cast<cudaStream_t>(stream)>>>(step_dev);
-  DTG_CHECK_CUDA(cudaGetLastError());
+  DTG_LAUNCHED();
   return DTG_OK;
 }

@@ -12,7 +12,7 @@
 namespace dtg {
 
 constexpr int kNormThreads = 256;
-constexpr int kMaxSplits = 16;
+constexpr int kMaxSplits = 32;
 
 template <typename T>
 struct Vec;
@@ -304,54 +304,64 @@ __global__ void __launch_bounds__(kNormThreads) norm_apply_kernel(dtg_plane x, d
   }
 }
 
-// backward finalize: sums[n][c] = (A, B); kcoef[n][c] = (k0, kA, kB, 0); d_gamma / d_beta accumulation
-__global__ void norm_bwd_finalize_kernel(const float* __restrict__ partial, const float* __restrict__ bnsum, int splits,
-                                         int n, int c, int hw, int mode, int world, const float* __restrict__ stats,
-                                         const float* __restrict__ gamma, float* __restrict__ sums,
-                                         float* __restrict__ d_gamma, float* __restrict__ d_beta,
-                                         float* __restrict__ kcoef) {
+// backward finalize, stage 1 (one thread per (n,c)): sums[n][c] = (A, B) summed over the pixel splits in a
+// fixed order; instance modes also emit kcoef[n][c] = (rstd*gamma, A/m, B/d, 0).
+__global__ void norm_bwd_sums_kernel(const float* __restrict__ partial, int splits, int n, int c, int hw, int mode,
+                                     const float* __restrict__ stats, const float* __restrict__ gamma,
+                                     float* __restrict__ sums, float* __restrict__ kcoef) {
+  const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= n * c) return;
+  const int ch = idx % c;
+  float A = 0.f, B = 0.f;
+  for (int s = 0; s < splits; ++s) {
+    const size_t o = (static_cast<size_t>(s) * n * c + idx) * 2;
+    A += partial[o];
+    B += partial[o + 1];
+  }
+  sums[idx * 2] = A;
+  sums[idx * 2 + 1] = B;
+  if (mode == DTG_NORM_INSTANCE || mode == DTG_NORM_COND_INSTANCE) {
+    const float m = static_cast<float>(hw);
+    const float d = mode == DTG_NORM_COND_INSTANCE ? m - 1.f : m;
+    const float ga = mode == DTG_NORM_COND_INSTANCE ? gamma[idx] : gamma[ch];
+    kcoef[idx * 4] = stats[idx * 2 + 1] * ga;
+    kcoef[idx * 4 + 1] = A / m;
+    kcoef[idx * 4 + 2] = B / d;
+  }
+}
+
+// stage 2 (one thread per channel): reduce sums over n -> parameter gradients (+=) and, for batch norm,
+// the per-channel sums handed to the cross-GPU all-reduce.
+__global__ void norm_bwd_channel_kernel(const float* __restrict__ sums, int n, int c, int mode, float* __restrict__ bnsum,
+                                        float* __restrict__ d_gamma, float* __restrict__ d_beta) {
   const int ch = blockIdx.x * blockDim.x + threadIdx.x;
   if (ch >= c) return;
-  float accA = 0.f, accB = 0.f;
+  float a = 0.f, b = 0.f;
   for (int i = 0; i < n; ++i) {
-    float A = 0.f, B = 0.f;
-    for (int s = 0; s < splits; ++s) {
-      const size_t o = ((static_cast<size_t>(s) * n + i) * c + ch) * 2;
-      A += partial[o];
-      B += partial[o + 1];
-    }
-    accA += A;
-    accB += B;
-    const size_t o = static_cast<size_t>(i) * c + ch;
-    if (sums) {
-      sums[o * 2] = A;
-      sums[o * 2 + 1] = B;
-    }
-    if (mode == DTG_NORM_INSTANCE || mode == DTG_NORM_COND_INSTANCE) {
-      const float m = static_cast<float>(hw);
-      const float d = mode == DTG_NORM_COND_INSTANCE ? m - 1.f : m;
-      const float ga = mode == DTG_NORM_COND_INSTANCE ? gamma[o] : gamma[ch];
-      kcoef[o * 4] = stats[o * 2 + 1] * ga;
-      kcoef[o * 4 + 1] = A / m;
-      kcoef[o * 4 + 2] = B / d;
-    }
+    a += sums[(static_cast<size_t>(i) * c + ch) * 2];
+    b += sums[(static_cast<size_t>(i) * c + ch) * 2 + 1];
   }
   if (mode == DTG_NORM_BATCH) {
-    // bnsum holds the (possibly all-reduced) per-channel sums
-    const float A = bnsum[ch * 2], B = bnsum[ch * 2 + 1];
-    const float m = static_cast<float>(hw) * n * world;
-    for (int i = 0; i < n; ++i) {
-      const size_t o = static_cast<size_t>(i) * c + ch;
-      kcoef[o * 4] = stats[o * 2 + 1] * gamma[ch];
-      kcoef[o * 4 + 1] = A / m;
-      kcoef[o * 4 + 2] = B / m;
-    }
-    // parameter gradients use the LOCAL sums (the caller all-reduces parameter gradients)
+    bnsum[ch * 2] = a;
+    bnsum[ch * 2 + 1] = b;
   }
-  if (mode != DTG_NORM_COND_INSTANCE) {
-    if (d_beta) d_beta[ch] += accA;
-    if (d_gamma && mode != DTG_NORM_NONE) d_gamma[ch] += accB;
+  if (mode != DTG_NORM_COND_INSTANCE) {   // parameter gradients use the LOCAL sums (the caller all-reduces them)
+    if (d_beta) d_beta[ch] += a;
+    if (d_gamma && mode != DTG_NORM_NONE) d_gamma[ch] += b;
   }
+}
+
+// stage 3, batch norm only (one thread per (n,c)): kcoef from the (all-reduced) per-channel sums
+__global__ void norm_bwd_bn_kcoef_kernel(const float* __restrict__ bnsum, int n, int c, int hw, int world,
+                                         const float* __restrict__ stats, const float* __restrict__ gamma,
+                                         float* __restrict__ kcoef) {
+  const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= n * c) return;
+  const int ch = idx % c;
+  const float m = static_cast<float>(hw) * n * world;
+  kcoef[idx * 4] = stats[idx * 2 + 1] * gamma[ch];
+  kcoef[idx * 4 + 1] = bnsum[ch * 2] / m;
+  kcoef[idx * 4 + 2] = bnsum[ch * 2 + 1] / m;
 }
 
 // backward apply: dx = k0*(g - kA - xhat*kB)  (NONE: dx = g); d_res = g
@@ -452,7 +462,7 @@ __global__ void cin_affine_bwd_kernel(const float* __restrict__ z, const float* 
 
 static int pick_splits(int n, int c, int cg, int hw) {
   const int ctas = n * (c / cg);
-  int s = (2 * 148 + ctas - 1) / ctas;
+  int s = (6 * 148 + ctas - 1) / ctas;
   s = std::min(s, kMaxSplits);
   s = std::min(s, std::max(1, hw / 64));
   return std::max(1, s);
@@ -460,7 +470,7 @@ static int pick_splits(int n, int c, int cg, int hw) {
 
 static int elemwise_grid(size_t total) {
   size_t g = (total + kNormThreads - 1) / kNormThreads;
-  return static_cast<int>(std::max<size_t>(1, std::min<size_t>(g, 148 * 8)));
+  return static_cast<int>(std::max<size_t>(1, std::min<size_t>(g, 148 * 32)));
 }
 
 static const dtg_plane kNullPlane = {nullptr, 0, 0, 0, 0, 0, 0};
@@ -472,7 +482,7 @@ using namespace dtg;
 extern "C" size_t dtg_norm_workspace_bytes(const dtg_plane* x) {
   if (!x) return 0;
   const size_t nc = static_cast<size_t>(x->n) * x->c;
-  return (2 * static_cast<size_t>(x->c) + kMaxSplits * nc * 2 + nc * 4) * sizeof(float);
+  return (2 * static_cast<size_t>(x->c) + kMaxSplits * nc * 2 + nc * 4 + nc * 2) * sizeof(float);
 }
 
 extern "C" int dtg_norm_fwd(const dtg_norm_args* a, const dtg_plane* x, const dtg_plane* residual, const float* gamma,
@@ -504,10 +514,10 @@ extern "C" int dtg_norm_fwd(const dtg_norm_args* a, const dtg_plane* x, const dt
         norm_stats_kernel<__nv_bfloat16><<<grid, kNormThreads, 0, stream>>>(*x, cg, splits, mode != DTG_NORM_BATCH, part);
       else
         norm_stats_kernel<float><<<grid, kNormThreads, 0, stream>>>(*x, cg, splits, mode != DTG_NORM_BATCH, part);
-      DTG_CHECK_CUDA(cudaGetLastError());
+      DTG_LAUNCHED();
       if (mode == DTG_NORM_BATCH) {
         bn_collapse_kernel<<<(x->c + 127) / 128, 128, 0, stream>>>(part, splits, x->n, x->c, bnsum);
-        DTG_CHECK_CUDA(cudaGetLastError());
+        DTG_LAUNCHED();
       }
       if (a->phase == 1) return DTG_OK;
     }
@@ -516,7 +526,7 @@ extern "C" int dtg_norm_fwd(const dtg_norm_args* a, const dtg_plane* x, const dt
     norm_fwd_finalize_kernel<<<(cnt + 127) / 128, 128, 0, stream>>>(part, bnsum, x->ptr, x->dtype, splits, x->n, x->c, hw,
                                                                    mode, a->eps, a->momentum, world, gamma, beta,
                                                                    bn_running, stats, coef);
-    DTG_CHECK_CUDA(cudaGetLastError());
+    DTG_LAUNCHED();
   } else if (a->phase == 1) {
     return DTG_OK;
   }
@@ -526,7 +536,7 @@ extern "C" int dtg_norm_fwd(const dtg_norm_args* a, const dtg_plane* x, const dt
     norm_apply_kernel<__nv_bfloat16><<<elemwise_grid(total), kNormThreads, 0, stream>>>(*x, res, coef, mode != DTG_NORM_NONE, a->act, *out);
   else
     norm_apply_kernel<float><<<elemwise_grid(total), kNormThreads, 0, stream>>>(*x, res, coef, mode != DTG_NORM_NONE, a->act, *out);
-  DTG_CHECK_CUDA(cudaGetLastError());
+  DTG_LAUNCHED();
   return DTG_OK;
 }
 
@@ -557,24 +567,27 @@ extern "C" int dtg_norm_bwd(const dtg_norm_args* a, const dtg_plane* dy, const d
   float* part = partial + 2 * c;
   float* kcoef = part + static_cast<size_t>(kMaxSplits) * n * c * 2;
   const bool need_reduce = mode != DTG_NORM_NONE || d_beta != nullptr || sums != nullptr;
+  float* sums_buf = sums ? sums : kcoef + static_cast<size_t>(n) * c * 4;   // scratch when the caller wants none
+  const int nc = n * c;
   if ((a->phase == 0 || a->phase == 1) && need_reduce) {
     dim3 grid(c / cg, n, splits);
     if (bf)
       norm_bwd_reduce_kernel<__nv_bfloat16><<<grid, kNormThreads, 0, stream>>>(*dy, p_dy2, p_y, p_x, stats, mode, a->act, cg, splits, part);
     else
       norm_bwd_reduce_kernel<float><<<grid, kNormThreads, 0, stream>>>(*dy, p_dy2, p_y, p_x, stats, mode, a->act, cg, splits, part);
-    DTG_CHECK_CUDA(cudaGetLastError());
-    if (mode == DTG_NORM_BATCH) {
-      bn_collapse_kernel<<<(c + 127) / 128, 128, 0, stream>>>(part, splits, n, c, bnsum);
-      DTG_CHECK_CUDA(cudaGetLastError());
+    DTG_LAUNCHED();
+    norm_bwd_sums_kernel<<<(nc + 127) / 128, 128, 0, stream>>>(part, splits, n, c, hw, mode, stats, gamma, sums_buf, kcoef);
+    DTG_LAUNCHED();
+    if (mode != DTG_NORM_COND_INSTANCE && (mode == DTG_NORM_BATCH || d_beta || d_gamma)) {
+      norm_bwd_channel_kernel<<<(c + 63) / 64, 64, 0, stream>>>(sums_buf, n, c, mode, bnsum, d_gamma, d_beta);
+      DTG_LAUNCHED();
     }
   }
   if (a->phase == 1) return DTG_OK;
-  if (need_reduce) {
+  if (mode == DTG_NORM_BATCH) {
     const int world = a->world_size > 0 ? a->world_size : 1;
-    norm_bwd_finalize_kernel<<<(c + 127) / 128, 128, 0, stream>>>(part, bnsum, splits, n, c, hw, mode, world, stats, gamma,
-                                                                 sums, d_gamma, d_beta, kcoef);
-    DTG_CHECK_CUDA(cudaGetLastError());
+    norm_bwd_bn_kcoef_kernel<<<(nc + 127) / 128, 128, 0, stream>>>(bnsum, n, c, hw, world, stats, gamma, kcoef);
+    DTG_LAUNCHED();
   }
   const dtg_plane p_res = (d_res && d_res->ptr) ? *d_res : kNullPlane;
   const size_t total = static_cast<size_t>(n) * hw * (c / V);
@@ -582,7 +595,7 @@ extern "C" int dtg_norm_bwd(const dtg_norm_args* a, const dtg_plane* dy, const d
     norm_bwd_apply_kernel<__nv_bfloat16><<<elemwise_grid(total), kNormThreads, 0, stream>>>(*dy, p_dy2, p_y, p_x, stats, kcoef, mode, a->act, *dx, p_res);
   else
     norm_bwd_apply_kernel<float><<<elemwise_grid(total), kNormThreads, 0, stream>>>(*dy, p_dy2, p_y, p_x, stats, kcoef, mode, a->act, *dx, p_res);
-  DTG_CHECK_CUDA(cudaGetLastError());
+  DTG_LAUNCHED();
   return DTG_OK;
 }
 
@@ -590,7 +603,7 @@ extern "C" int dtg_cin_affine_fwd(const float* z, const float* ws, const float* 
                                   int n, int c, int nz, float* gamma, float* beta, void* stream) {
   DTG_REQUIRE(z && ws && bs && wb && bb && gamma && beta, "dtg_cin_affine_fwd: null argument");
   cin_affine_fwd_kernel<<<(n * c + 127) / 128, 128, 0, static_cast<cudaStream_t>(stream)>>>(z, ws, bs, wb, bb, n, c, nz, gamma, beta);
-  DTG_CHECK_CUDA(cudaGetLastError());
+  DTG_LAUNCHED();
   return DTG_OK;
 }
 
@@ -601,6 +614,6 @@ extern "C" int dtg_cin_affine_bwd(const float* z, const float* ws, const float* 
   const int total = c * nz + n * nz;
   cin_affine_bwd_kernel<<<(total + 127) / 128, 128, 0, static_cast<cudaStream_t>(stream)>>>(z, ws, wb, gamma, beta, sums, n, c, nz, d_ws,
                                                                                               d_bs, d_wb, d_bb, d_z);
-  DTG_CHECK_CUDA(cudaGetLastError());
+  DTG_LAUNCHED();
   return DTG_OK;
 }

@@ -2,6 +2,7 @@
 // cudaGetDriverEntryPoint so the library has no link-time dependency on libcuda).
 #include <stdarg.h>
 
+#include <atomic>
 #include <mutex>
 
 #include "common.cuh"
@@ -9,6 +10,9 @@
 namespace dtg {
 
 static thread_local char g_err[512] = "";
+static std::atomic<unsigned long long> g_launches{0};
+
+void count_launch() { g_launches.fetch_add(1, std::memory_order_relaxed); }
 
 void set_error(const char* fmt, ...) {
   va_list ap;
@@ -77,6 +81,8 @@ int encode_tiled(CUtensorMap* map, int dtype, int rank, void* base, const uint64
 }  // namespace dtg
 
 extern "C" int dtg_version(void) { return DTG_VERSION; }
+
+extern "C" unsigned long long dtg_launch_count(void) { return dtg::g_launches.load(std::memory_order_relaxed); }
 
 extern "C" int dtg_last_error(char* buf, size_t cap) {
   size_t n = strlen(dtg::g_err);

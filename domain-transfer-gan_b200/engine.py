@@ -230,7 +230,8 @@ class NetExec:
             ih, iw = c.dims[ly.src]
             oh, ow = ly.out_hw(ih, iw)
             mode = L.CONV_DGRAD if ly.transposed else L.CONV_FWD
-            kw = dict(mode=mode, kh=ly.k, kw=ly.k, stride=ly.stride, pad=ly.pad, cout=ly.cout, out_h=oh, out_w=ow)
+            kw = dict(mode=mode, kh=ly.k, kw=ly.k, stride=ly.stride, pad=ly.pad, cout=ly.cout, out_h=oh, out_w=ow,
+                      cin=ly.cin)
             bias = ly.conv.bias if ly.use_bias else None
             if ly.head:
                 ops.conv(a_in, ly.w_f, bias, None, act=ly.act, out_nchw=c.heads[ly.name], **kw)
@@ -334,10 +335,10 @@ class NetExec:
                 ih, iw = c.dims[ly.src]
                 if ly.transposed:
                     ops.conv(dyr, ly.w_d, None, gin, mode=L.CONV_FWD, kh=ly.k, kw=ly.k, stride=ly.stride, pad=ly.pad,
-                             cout=ly.cin, out_h=ih, out_w=iw)
+                             cout=ly.cin, out_h=ih, out_w=iw, cin=ly.cout)
                 else:
                     ops.conv(dyr, ly.w_d, None, gin, mode=L.CONV_DGRAD, kh=ly.k, kw=ly.k, stride=ly.stride, pad=ly.pad,
-                             ring=a_in.halo, cout=ly.cin, out_h=ih, out_w=iw)
+                             ring=a_in.halo, cout=ly.cin, out_h=ih, out_w=iw, cin=ly.cout)
                 d0, d1 = pending.get(ly.src, (None, None))
                 assert d0 is None or d1 is None, "more than two gradient contributions for one activation"
                 pending[ly.src] = (gin, d1) if d0 is None else (gin, d0)

@@ -168,7 +168,7 @@ class AugmentedCycleGAN(object):
         sc, ws = self.scalars, self.red_ws
         dp = self.dp
         sync_bn = dp.sync_bn if dp is not None else None
-        gs = 1.0 / dp.world_size if dp is not None else 1.0
+        gs = 1.0 / dp.world_size if dp is not None else 1.0     # all-reduce SUM -> mean of shard gradients
         z_prior = prior_z_B.reshape(n, nz)
         i_mu = self._head_idx(E, "mu")
 
@@ -218,13 +218,17 @@ class AugmentedCycleGAN(object):
 
         self.optimizer_D_A.zero_grad()
         self.optimizer_D_B.zero_grad()
+        ar = dp.allreduce_arena if dp is not None else (lambda arena: None)   # async, overlaps later backward
         DA.backward(cdA, {"out": True})
+        ar(DA.arena)
         DB.backward(cdB, {"out": True})
+        ar(DB.arena)
         if o.z_gan:
             DZ.backward(cz1, {"out": True}, sync_bn=sync_bn)
             DZ.backward(cz2, {"out": True}, sync_bn=sync_bn)
+        ar(DZ.arena)
         if dp is not None:
-            dp.allreduce_grads([DA.arena, DB.arena, DZ.arena])
+            dp.wait()
         self.optimizer_D_A.step(gs)
         self.optimizer_D_B.step(gs)
 
@@ -272,13 +276,16 @@ class AugmentedCycleGAN(object):
         # d mu_z_realB = D_z dgrad + dz of F15's CIN projections -> seed of F3's mu head
         ops.grad_gather([g12], [0], nz, out=c3.dyraw[i_mu], add_nchw=c15.dz)
         g3 = E.backward(c3, {"mu": True}, want_dx=True, sync_bn=sync_bn)             # channels 0..2: d fake_A
+        ar(E.arena)
         cB = o.input_nc if o.enc_A_B else 0
         ops.grad_gather([g14, g13, g11], [cB, 0, 0], o.output_nc, out=c1.dyraw[iGAo], tanh_y=fake_B)
         GAB.backward(c1, {"out": True})
+        ar(GAB.arena)
         ops.grad_gather([g15, g10, g3], [0, 0, 0], o.input_nc, out=c2.dyraw[iGo], tanh_y=fake_A)
         GBA.backward(c2, {"out": True})
+        ar(GBA.arena)
         if dp is not None:
-            dp.allreduce_grads([GAB.arena, GBA.arena, E.arena])
+            dp.wait()
         self.optimizer_G_A.step(gs)
         self.optimizer_G_B.step(gs)
         return OrderedDict([('real_A', real_A), ('fake_B', fake_B), ('rec_A', rec_A),

@@ -135,15 +135,51 @@ def add_packed(tab, w, dtype, kind):
     raise ValueError(kind)
 
 
+class KernelProfile:
+    """Optional per-call CUDA-event timing of the tensor-core kernels (bench.py roofline accounting).
+    Records (kind, algorithmic FLOPs, start event, end event) per call on the launching stream."""
+
+    def __init__(self):
+        self.records = []
+
+    def begin(self):
+        e = torch.cuda.Event(enable_timing=True)
+        e.record(torch.cuda.current_stream())
+        return e
+
+    def end(self, kind, flops, e0):
+        e1 = torch.cuda.Event(enable_timing=True)
+        e1.record(torch.cuda.current_stream())
+        self.records.append((kind, flops, e0, e1))
+
+    def summary(self):
+        out = {}
+        for kind, flops, e0, e1 in self.records:
+            d = out.setdefault(kind, {"flops": 0.0, "ms": 0.0, "launches": 0})
+            d["flops"] += flops
+            d["ms"] += e0.elapsed_time(e1)
+            d["launches"] += 1
+        return out
+
+
+PROFILE = None    # set to a KernelProfile to time conv / wgrad calls
+
+
 def conv(x, wp, bias, out, *, mode=L.CONV_FWD, kh, kw, stride=1, pad=0, ring=0, act=L.ACT_NONE, cout,
-         out_h, out_w, out_reflect=False, out_nchw=None):
-    """x: PlaneT; wp: packed weight [taps, rows_p, cols_p]; out: PlaneT or None with out_nchw fp32 tensor."""
+         out_h, out_w, out_reflect=False, out_nchw=None, cin=None):
+    """x: PlaneT; wp: packed weight [taps, rows_p, cols_p]; out: PlaneT or None with out_nchw fp32 tensor.
+    cin: real input channels (FLOP accounting only)."""
     a = L.ConvArgs(mode, kh, kw, stride, pad, ring, act, cout, 1 if out_nchw is not None else 0,
                    1 if out_reflect else 0, out_h, out_w)
     assert wp.shape[0] == kh * kw
+    e0 = PROFILE.begin() if PROFILE is not None else None
     rc = L.lib().dtg_conv(C.byref(a), x.s, _ptr(wp), wp.shape[1], wp.shape[2], _ptr(bias),
                           out.s if out is not None else NULL_PLANE, _ptr(out_nchw), _stream())
     L.check(rc, "conv")
+    if e0 is not None:
+        # algorithmic MACs = (pixels of the low-resolution side) * cin * cout * taps, for fwd and dgrad alike
+        pix = x.n * (out_h * out_w if mode == L.CONV_FWD else x.h * x.w)
+        PROFILE.end("igemm_kernel", 2.0 * pix * (cin or wp.shape[2]) * cout * kh * kw, e0)
 
 
 _ws_cache = {}
@@ -168,7 +204,10 @@ def conv_wgrad(p, q, dw, *, kh, kw, stride=1, pad=0, pa, qb, ws=None):
     if ws is None:
         ws = workspace(need, dw.device, "wgrad")
     assert dw.dtype == torch.float32 and dw.is_contiguous() and dw.numel() == pa * qb * kh * kw
+    e0 = PROFILE.begin() if PROFILE is not None else None
     L.check(L.lib().dtg_conv_wgrad(C.byref(a), p.s, q.s, _ptr(dw), _ptr(ws), ws.numel(), _stream()), "conv_wgrad")
+    if e0 is not None:
+        PROFILE.end("wgrad_kernel", 2.0 * p.n * p.h * p.w * pa * qb * kh * kw, e0)
 
 
 def norm_workspace_floats(x):
@@ -233,8 +272,14 @@ def grad_gather(srcs, c_offs, c, out=None, tanh_y=None, out_nchw=None, add_nchw=
     L.check(L.lib().dtg_grad_gather(arr, offs, len(srcs), _ptr(add_nchw), _ptr(tanh_y), c, outp, _ptr(out_nchw), _stream()), "grad_gather")
 
 
+_cs_ws = {}
+
+
 def channel_sum(x, c, d_bias):
-    L.check(L.lib().dtg_channel_sum(x.s, c, _ptr(d_bias), _stream()), "channel_sum")
+    dev = str(d_bias.device)
+    if dev not in _cs_ws:
+        _cs_ws[dev] = torch.zeros(2048, dtype=torch.float32, device=d_bias.device)
+    L.check(L.lib().dtg_channel_sum(x.s, c, _ptr(d_bias), _ptr(_cs_ws[dev]), _stream()), "channel_sum")
 
 
 def loss_lsgan(pred, target, grad_scale, scalars, slot_loss, slot_mean, dpred, ws):

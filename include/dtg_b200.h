@@ -47,6 +47,8 @@ typedef struct dtg_plane {
 } dtg_plane;
 
 int dtg_version(void);
+/* number of kernels this library has enqueued so far in this process (monotonic; for bench accounting) */
+unsigned long long dtg_launch_count(void);
 /* copies the calling thread's last error message (NUL terminated) into buf; returns its length */
 int dtg_last_error(char* buf, size_t cap);
 
@@ -188,8 +190,9 @@ int dtg_unpack_nchw(const dtg_plane* src, int c_off, int c, float* dst, void* st
 int dtg_grad_gather(const dtg_plane* const* srcs, const int* c_off, int nsrc, const float* add_nchw,
                     const float* tanh_y, int c, const dtg_plane* out, float* out_nchw, void* stream);
 
-/* per-channel sum over (n,h,w) of a plane's interior: d_bias[c] += sum  (conv bias gradients) */
-int dtg_channel_sum(const dtg_plane* x, int c, float* d_bias, void* stream);
+/* per-channel sum over (n,h,w) of a plane's interior: d_bias[c] += sum, c <= 16 (bias gradients of the network
+ * heads).  workspace: >= 8 KB, zero-initialised once by the caller (self-resetting), deterministic two-stage. */
+int dtg_channel_sum(const dtg_plane* x, int c, float* d_bias, void* workspace, void* stream);
 
 /* ---------------------------------------------------------------------------------------------
  * Fused losses (model.py:56-72, 327-334, 432-439, 458-505): each call reduces one term into
