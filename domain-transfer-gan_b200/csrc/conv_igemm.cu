@@ -13,6 +13,7 @@
 // (TMEM -> registers -> bias/activation -> global).  Persistent CTAs, double-buffered accumulators.
 #include <algorithm>
 #include <mutex>
+#include <type_traits>
 
 #include "common.cuh"
 
@@ -23,6 +24,9 @@ constexpr int kRowBytes = 128;
 constexpr int kTileM = 128;
 constexpr int kATileBytes = kTileM * kRowBytes;  // 16 KB
 constexpr int kThreads = 192;
+constexpr int kEpiPitch = 144;                                   // 128-byte chunk row + 16 B pad (bank spread)
+constexpr int kEpiWarpBytes = 32 * kEpiPitch + 32 * 4 * 8;       // staging rows + destination-offset table
+constexpr int kBarrierBytes = 256;
 
 struct IgemmParams {
   CUtensorMap tmA[4];
@@ -65,6 +69,7 @@ __global__ void __launch_bounds__(kThreads, 1) igemm_kernel(const __grid_constan
   uint64_t* bar_tfull = bar_empty + S;
   uint64_t* bar_tempty = bar_tfull + 2;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bar_tempty + 2);
+  uint8_t* epi_smem = smem + S * stage_bytes + kBarrierBytes;
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -175,13 +180,25 @@ __global__ void __launch_bounds__(kThreads, 1) igemm_kernel(const __grid_constan
     }
   } else {
     // ===================== epilogue =====================
-    const int quad = warp & 3;  // TMEM lane quadrant this warp may access
+    // TMEM -> registers -> (bias, activation, convert) -> per-warp smem staging (128-byte channel chunks) ->
+    // global rows written as full 128-byte lines (8 lanes x 16 B per row, 4 rows per warp instruction).
+    using OutT = typename std::conditional<TF32, float, __nv_bfloat16>::type;
+    constexpr int ES = sizeof(OutT);
+    constexpr int CHUNK_CH = 128 / ES;   // channels per 128-byte chunk
+    constexpr int PIECE_CH = 16 / ES;    // channels per 16-byte piece
+    const int quad = warp & 3;           // TMEM lane quadrant this warp may access
     const int row = quad * 32 + lane;
     const int iw = row % p.bw;
     const int ih = (row / p.bw) % p.bh;
     const int in_ = row / (p.bw * p.bh);
-    const int es = p.out_dtype == DTG_BF16 ? 2 : 4;
     const int Hb = p.out_H + 2 * p.out_halo, Wb = p.out_W + 2 * p.out_halo;
+    uint8_t* stile = epi_smem + quad * kEpiWarpBytes;
+    uint32_t* soff = reinterpret_cast<uint32_t*>(stile + 32 * kEpiPitch);   // [32] row offsets in 16-byte units
+    const bool has_bias = p.bias != nullptr;
+    const bool plain = !has_bias && p.act == DTG_ACT_NONE;
+    const int ncols = min(p.n_umma, p.out_nchw ? p.n_umma : p.out_C);
+    const int piece = lane & 7, rsub = lane >> 3;
+    uint8_t* const outp = reinterpret_cast<uint8_t*>(p.out);
     int it = 0;
     for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
       const int ph = tile / tiles_per_phase;
@@ -194,68 +211,98 @@ __global__ void __launch_bounds__(kThreads, 1) igemm_kernel(const __grid_constan
       if (a0 >= p.ph_OH[ph] || b0 >= p.ph_OW[ph]) continue;
       const int buf = it & 1;
       const uint32_t use = static_cast<uint32_t>(it >> 1);
-      mbar_wait(&bar_tfull[buf], use & 1);
-      tc_fence_after();
       const int a = a0 + ih, b = b0 + iw, n = n0 + in_;
       const bool valid = (row < box_rows) && a < p.ph_OH[ph] && b < p.ph_OW[ph] && n < p.N;
       const int oh = p.ph_oh0[ph] + a * p.out_step;
       const int ow = p.ph_ow0[ph] + b * p.out_step;
-      int hts[3], wts[3];
-      int nh = 1, nw = 1;
-      hts[0] = oh;
-      wts[0] = ow;
-      if (p.out_reflect && !p.out_nchw) {
-        nh = reflect_targets(oh, p.out_H, p.out_halo, hts);
-        nw = reflect_targets(ow, p.out_W, p.out_halo, wts);
-      }
+      const size_t pix0 = (static_cast<size_t>(n) * Hb + (oh + p.out_halo)) * Wb + (ow + p.out_halo);
+      if (!p.out_nchw) soff[lane] = valid ? static_cast<uint32_t>((pix0 * p.out_C * ES) >> 4) : 0xFFFFFFFFu;
+      mbar_wait(&bar_tfull[buf], use & 1);
+      tc_fence_after();
       const uint32_t taddr = tmem_base + (static_cast<uint32_t>(quad * 32) << 16) + buf * p.n_umma;
-      for (int c0 = 0; c0 < p.n_umma; c0 += 16) {
-        uint32_t v[16];
-        tmem_ld16(taddr + c0, v);
-        tmem_ld_wait();
-        if (!valid) continue;
-        float f[16];
-#pragma unroll
-        for (int j = 0; j < 16; ++j) {
-          float x = __uint_as_float(v[j]);
-          const int c = c0 + j;
-          if (p.bias != nullptr && c < p.cvalid) x += __ldg(p.bias + c);
-          f[j] = apply_act(x, p.act);
-        }
-        if (p.out_nchw) {
+      if (p.out_nchw) {
+        // heads (<= 16 channels): lanes are consecutive pixels, so per-channel stores are already coalesced
+        for (int c0 = 0; c0 < p.n_umma; c0 += 16) {
+          uint32_t v[16];
+          tmem_ld16(taddr + c0, v);
+          tmem_ld_wait();
+          if (!valid) continue;
           float* o = reinterpret_cast<float*>(p.out);
 #pragma unroll
           for (int j = 0; j < 16; ++j) {
             const int c = c0 + j;
-            if (c < p.cvalid)
-              o[((static_cast<size_t>(n) * p.cvalid + c) * p.out_H + oh) * p.out_W + ow] = f[j];
-          }
-        } else {
-          if (c0 >= p.out_C) continue;
-          for (int ihh = 0; ihh < nh; ++ihh) {
-            for (int iww = 0; iww < nw; ++iww) {
-              const size_t pix = (static_cast<size_t>(n) * Hb + (hts[ihh] + p.out_halo)) * Wb + (wts[iww] + p.out_halo);
-              uint8_t* dst = reinterpret_cast<uint8_t*>(p.out) + (pix * p.out_C + c0) * es;
-              if (p.out_dtype == DTG_BF16) {
-                uint32_t pk[8];
-#pragma unroll
-                for (int j = 0; j < 8; ++j) {
-                  __nv_bfloat162 h2 = __floats2bfloat162_rn(f[2 * j], f[2 * j + 1]);
-                  pk[j] = *reinterpret_cast<uint32_t*>(&h2);
-                }
-                reinterpret_cast<uint4*>(dst)[0] = make_uint4(pk[0], pk[1], pk[2], pk[3]);
-                if (c0 + 8 < p.out_C) reinterpret_cast<uint4*>(dst)[1] = make_uint4(pk[4], pk[5], pk[6], pk[7]);
-              } else {
-#pragma unroll
-                for (int q = 0; q < 4; ++q) {
-                  if (c0 + 4 * q < p.out_C)
-                    reinterpret_cast<float4*>(dst)[q] = make_float4(round_tf32(f[4 * q]), round_tf32(f[4 * q + 1]),
-                                                                    round_tf32(f[4 * q + 2]), round_tf32(f[4 * q + 3]));
-                }
-              }
+            if (c < p.cvalid) {
+              float x = __uint_as_float(v[j]);
+              if (has_bias) x += __ldg(p.bias + c);
+              o[((static_cast<size_t>(n) * p.cvalid + c) * p.out_H + oh) * p.out_W + ow] = apply_act(x, p.act);
             }
           }
         }
+      } else {
+        for (int cbase = 0; cbase < ncols; cbase += CHUNK_CH) {
+          __syncwarp();
+          const int cend = min(cbase + CHUNK_CH, p.n_umma);
+          for (int c0 = cbase; c0 < cend; c0 += 16) {
+            uint32_t v[16];
+            tmem_ld16(taddr + c0, v);
+            tmem_ld_wait();
+            if (!plain) {
+#pragma unroll
+              for (int j = 0; j < 16; ++j) {
+                float x = __uint_as_float(v[j]);
+                if (has_bias && c0 + j < p.cvalid) x += __ldg(p.bias + c0 + j);
+                v[j] = __float_as_uint(apply_act(x, p.act));
+              }
+            }
+            uint8_t* dst = stile + lane * kEpiPitch + (c0 - cbase) * ES;
+            if constexpr (!TF32) {
+              uint32_t pk[8];
+#pragma unroll
+              for (int j = 0; j < 8; ++j) {
+                __nv_bfloat162 h2 = __floats2bfloat162_rn(__uint_as_float(v[2 * j]), __uint_as_float(v[2 * j + 1]));
+                pk[j] = *reinterpret_cast<uint32_t*>(&h2);
+              }
+              reinterpret_cast<uint4*>(dst)[0] = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+              reinterpret_cast<uint4*>(dst)[1] = make_uint4(pk[4], pk[5], pk[6], pk[7]);
+            } else {
+#pragma unroll
+              for (int q = 0; q < 4; ++q)
+                reinterpret_cast<float4*>(dst)[q] =
+                    make_float4(round_tf32(__uint_as_float(v[4 * q])), round_tf32(__uint_as_float(v[4 * q + 1])),
+                                round_tf32(__uint_as_float(v[4 * q + 2])), round_tf32(__uint_as_float(v[4 * q + 3])));
+            }
+          }
+          __syncwarp();
+          const int ch_of_piece = cbase + piece * PIECE_CH;
+          if (ch_of_piece < p.out_C) {
+            uint8_t* const obase = outp + static_cast<size_t>(ch_of_piece) * ES;
+#pragma unroll
+            for (int r4 = 0; r4 < 32; r4 += 4) {
+              const int rr = r4 + rsub;
+              const uint32_t off = soff[rr];
+              const uint4 val = *reinterpret_cast<const uint4*>(stile + rr * kEpiPitch + piece * 16);
+              if (off != 0xFFFFFFFFu) *reinterpret_cast<uint4*>(obase + (static_cast<size_t>(off) << 4)) = val;
+            }
+          }
+          if (p.out_reflect && valid) {
+            // mirrored copies into the reflect halo (boundary rows only): each lane copies its own row's chunk
+            int hts[3], wts[3];
+            const int nh = reflect_targets(oh, p.out_H, p.out_halo, hts);
+            const int nw = reflect_targets(ow, p.out_W, p.out_halo, wts);
+            if (nh * nw > 1) {
+              const int npieces = min(8, (p.out_C - cbase + PIECE_CH - 1) / PIECE_CH);
+              for (int i2 = 0; i2 < nh; ++i2)
+                for (int j2 = 0; j2 < nw; ++j2) {
+                  if (i2 == 0 && j2 == 0) continue;
+                  const size_t pix = (static_cast<size_t>(n) * Hb + (hts[i2] + p.out_halo)) * Wb + (wts[j2] + p.out_halo);
+                  uint8_t* o = outp + (pix * p.out_C + cbase) * ES;
+                  for (int q = 0; q < npieces; ++q)
+                    reinterpret_cast<uint4*>(o)[q] = *reinterpret_cast<const uint4*>(stile + lane * kEpiPitch + q * 16);
+                }
+            }
+          }
+        }
+        __syncwarp();
       }
       tc_fence_before();
       __syncwarp();
@@ -317,7 +364,7 @@ static int launch_igemm(const IgemmParams& p, cudaStream_t stream) {
     }
   }
   const int stage_bytes = kATileBytes + p.n_umma * kRowBytes;
-  const size_t smem = static_cast<size_t>(p.stages) * stage_bytes + 1024 + 256;
+  const size_t smem = static_cast<size_t>(p.stages) * stage_bytes + 1024 + kBarrierBytes + 4 * kEpiWarpBytes;
   const int total = p.tiles_w * p.tiles_h * p.tiles_n * p.num_phases;
   const int grid = std::max(1, std::min(total, num_sms));
   igemm_kernel<TF32><<<grid, kThreads, smem, stream>>>(p);
@@ -497,7 +544,7 @@ extern "C" int dtg_conv(const dtg_conv_args* a, const dtg_plane* in, const void*
   }
 
   const int stage_bytes = kATileBytes + p.n_umma * kRowBytes;
-  p.stages = std::max(2, std::min(8, (200 * 1024) / stage_bytes));
+  p.stages = std::max(2, std::min(8, (196 * 1024) / stage_bytes));
   int cols = 32;
   while (cols < 2 * p.n_umma) cols <<= 1;
   p.tmem_cols = cols;

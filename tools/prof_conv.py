@@ -1,0 +1,47 @@
+"""Micro-driver for ncu: one conv configuration through the C ABI, a few launches.
+usage: python tools/prof_conv.py <case> [reps]   case in {res, res_dgrad, c3a, c7in, c7out, db3, res_wgrad, c7in_wgrad}"""
+import sys, os
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import torch
+import dtg  # noqa
+from dtg_b200 import _lib as L, ops
+
+case = sys.argv[1] if len(sys.argv) > 1 else "res"
+reps = int(sys.argv[2]) if len(sys.argv) > 2 else 5
+N = 80
+dt = torch.bfloat16
+g = torch.Generator().manual_seed(0)
+CASES = {  # cin, cout, h, k, s, pad, halo, mode
+    "res": (128, 128, 32, 3, 1, 1, 1, "fwd"), "res_dgrad": (128, 128, 32, 3, 1, 1, 1, "dgrad"),
+    "c3a": (32, 64, 64, 3, 1, 1, 0, "fwd"), "c3b": (64, 32, 64, 3, 1, 1, 0, "fwd"),
+    "c7in": (3, 32, 64, 7, 1, 3, 3, "fwd"), "c7out": (32, 3, 64, 7, 1, 3, 0, "fwd"),
+    "db3": (256, 256, 15, 4, 1, 1, 0, "fwd"), "down": (64, 128, 64, 3, 2, 1, 0, "fwd"),
+    "res_wgrad": (128, 128, 32, 3, 1, 1, 1, "wgrad"), "c7in_wgrad": (3, 32, 64, 7, 1, 3, 3, "wgrad"),
+    "c3b_wgrad": (64, 32, 64, 3, 1, 1, 0, "wgrad"),
+}
+cin, cout, h, k, s, pad, halo, mode = CASES[case]
+oh = (h + 2 * pad - k) // s + 1
+x = ops.PlaneT(N, h, h, ops.cpad(cin, dt), halo, dt); x.t.normal_()
+w = (torch.randn(cout, cin, k, k, generator=g) * 0.05).cuda()
+ev = [torch.cuda.Event(enable_timing=True) for _ in range(reps + 1)]
+if mode == "fwd":
+    wp = ops.pack_conv_weight(w, dt, "fwd")
+    out = ops.PlaneT(N, oh, oh, ops.cpad(cout, dt), 0, dt)
+    f = lambda: ops.conv(x, wp, None, out, kh=k, kw=k, stride=s, pad=pad, cout=cout, out_h=oh, out_w=oh)
+elif mode == "dgrad":
+    wp = ops.pack_conv_weight(w, dt, "dgrad")
+    dy = ops.PlaneT(N, oh, oh, ops.cpad(cout, dt), 0, dt); dy.t.normal_()
+    dx = ops.PlaneT(N, h, h, ops.cpad(cin, dt), halo, dt)
+    f = lambda: ops.conv(dy, wp, None, dx, mode=L.CONV_DGRAD, kh=k, kw=k, stride=s, pad=pad, ring=halo, cout=cin, out_h=h, out_w=h)
+else:
+    dy = ops.PlaneT(N, oh, oh, ops.cpad(cout, dt), 0, dt); dy.t.normal_()
+    dw = torch.zeros(cout, cin, k, k, device="cuda")
+    f = lambda: ops.conv_wgrad(dy, x, dw, kh=k, kw=k, stride=s, pad=pad, pa=cout, qb=cin)
+f(); torch.cuda.synchronize()
+ev[0].record()
+for i in range(reps):
+    f(); ev[i + 1].record()
+torch.cuda.synchronize()
+ts = [ev[i].elapsed_time(ev[i + 1]) * 1e3 for i in range(reps)]
+fl = 2.0 * N * oh * oh * cin * cout * k * k
+print(case, "us per call:", ["%.1f" % t for t in ts], "TFLOP/s best %.1f" % (fl / min(ts) / 1e6))
