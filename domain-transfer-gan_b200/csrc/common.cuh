@@ -44,7 +44,7 @@ void count_launch();
 // Tensor-map encode through the driver entry point (no link-time libcuda dependency).
 int encode_tiled(CUtensorMap* map, int dtype, int rank, void* base, const uint64_t* dims,
                  const uint64_t* strides_bytes /* rank-1 entries */, const uint32_t* box,
-                 int swizzle /* 0 none, 1 = 128B (16-byte atoms), 2 = 128B with 32-byte atoms */);
+                 int swizzle /* 0 none, 1 = 128B (16-byte atoms), 2 = 128B with 32-byte atoms, 3 = 64B, 4 = 32B */);
 
 static inline int elem_size(int dtype) { return dtype == DTG_BF16 ? 2 : 4; }
 

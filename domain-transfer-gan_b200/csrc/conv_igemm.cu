@@ -16,45 +16,9 @@
 #include <type_traits>
 
 #include "common.cuh"
+#include "conv_epilogue.cuh"
 
 namespace dtg {
-
-constexpr int kMaxTaps = 64;
-constexpr int kRowBytes = 128;
-constexpr int kTileM = 128;
-constexpr int kATileBytes = kTileM * kRowBytes;  // 16 KB
-constexpr int kThreads = 192;
-constexpr int kEpiPitch = 144;                                   // 128-byte chunk row + 16 B pad (bank spread)
-constexpr int kEpiWarpBytes = 32 * kEpiPitch + 32 * 4 * 8;       // staging rows + destination-offset table
-constexpr int kBarrierBytes = 256;
-
-struct IgemmParams {
-  CUtensorMap tmA[4];
-  CUtensorMap tmB;
-  int bw, bh, bn;
-  int tiles_w, tiles_h, tiles_n;
-  int num_phases;
-  int ph_tap_begin[5];
-  int ph_oh0[4], ph_ow0[4];
-  int ph_OH[4], ph_OW[4];
-  int out_step;
-  int N;
-  short tap_dh[kMaxTaps], tap_dw[kMaxTaps];
-  unsigned char tap_map[kMaxTaps], tap_w[kMaxTaps];
-  int kchunks;
-  int n_umma;  // = packed weight rows per tap
-  int stages;
-  int tmem_cols;
-  // epilogue
-  void* out;
-  int out_nchw;  // 1: dense fp32 NCHW [N][cvalid][out_H][out_W]
-  int out_dtype;
-  int out_C, out_halo, out_H, out_W;
-  int cvalid;
-  int act;
-  int out_reflect;
-  const float* bias;
-};
 
 template <bool TF32>
 __global__ void __launch_bounds__(kThreads, 1) igemm_kernel(const __grid_constant__ IgemmParams p) {
@@ -105,7 +69,7 @@ __global__ void __launch_bounds__(kThreads, 1) igemm_kernel(const __grid_constan
 
   if (warp == 0) {
     // ===================== TMA producer =====================
-    if (lane == 0) {
+    {   // warp-uniform loop; only the TMA / mbarrier instructions are predicated on elect.sync
       int stage = 0;
       uint32_t phase = 0;
       for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
@@ -124,9 +88,12 @@ __global__ void __launch_bounds__(kThreads, 1) igemm_kernel(const __grid_constan
           for (int kc = 0; kc < p.kchunks; ++kc) {
             mbar_wait(&bar_empty[stage], phase ^ 1);
             uint8_t* sa = smem + stage * stage_bytes;
-            mbar_expect_tx(&bar_full[stage], tx_bytes);
-            tma_load_4d(sa, mapA, &bar_full[stage], kc * KC, cw, chh, n0);
-            tma_load_2d(sa + kATileBytes, &p.tmB, &bar_full[stage], kc * KC, wrow);
+            if (elect_one()) {
+              mbar_expect_tx(&bar_full[stage], tx_bytes);
+              tma_load_4d(sa, mapA, &bar_full[stage], kc * KC, cw, chh, n0);
+              tma_load_2d(sa + kATileBytes, &p.tmB, &bar_full[stage], kc * KC, wrow);
+            }
+            __syncwarp();
             if (++stage == S) {
               stage = 0;
               phase ^= 1;
@@ -157,16 +124,16 @@ __global__ void __launch_bounds__(kThreads, 1) igemm_kernel(const __grid_constan
       for (int k = 0; k < nk; ++k) {
         mbar_wait(&bar_full[stage], phase);
         tc_fence_after();
-        if (lane == 0) {
+        {
           const uint32_t sa = smem_u32(smem + stage * stage_bytes);
           const uint32_t sb = sa + kATileBytes;
+          const uint64_t ad0 = umma_desc_sw128(sa, 16, 1024);
+          const uint64_t bd0 = umma_desc_sw128(sb, 16, 1024);
+          if (elect_one()) {
 #pragma unroll
-          for (int j = 0; j < 4; ++j) {
-            const uint64_t ad = umma_desc_sw128(sa + j * 32, 16, 1024);
-            const uint64_t bd = umma_desc_sw128(sb + j * 32, 16, 1024);
-            tc_mma<TF32>(d_tmem, ad, bd, idesc, (k > 0 || j > 0) ? 1u : 0u);
+            for (int j = 0; j < 4; ++j) tc_mma<TF32>(d_tmem, ad0 + 2 * j, bd0 + 2 * j, idesc, (k > 0 || j > 0) ? 1u : 0u);
+            tc_commit(&bar_empty[stage]);
           }
-          tc_commit(&bar_empty[stage]);
         }
         __syncwarp();
         if (++stage == S) {
@@ -174,7 +141,7 @@ __global__ void __launch_bounds__(kThreads, 1) igemm_kernel(const __grid_constan
           phase ^= 1;
         }
       }
-      if (lane == 0) tc_commit(&bar_tfull[buf]);
+      if (elect_one()) tc_commit(&bar_tfull[buf]);
       __syncwarp();
       ++it;
     }
@@ -182,23 +149,12 @@ __global__ void __launch_bounds__(kThreads, 1) igemm_kernel(const __grid_constan
     // ===================== epilogue =====================
     // TMEM -> registers -> (bias, activation, convert) -> per-warp smem staging (128-byte channel chunks) ->
     // global rows written as full 128-byte lines (8 lanes x 16 B per row, 4 rows per warp instruction).
-    using OutT = typename std::conditional<TF32, float, __nv_bfloat16>::type;
-    constexpr int ES = sizeof(OutT);
-    constexpr int CHUNK_CH = 128 / ES;   // channels per 128-byte chunk
-    constexpr int PIECE_CH = 16 / ES;    // channels per 16-byte piece
     const int quad = warp & 3;           // TMEM lane quadrant this warp may access
     const int row = quad * 32 + lane;
     const int iw = row % p.bw;
     const int ih = (row / p.bw) % p.bh;
     const int in_ = row / (p.bw * p.bh);
-    const int Hb = p.out_H + 2 * p.out_halo, Wb = p.out_W + 2 * p.out_halo;
     uint8_t* stile = epi_smem + quad * kEpiWarpBytes;
-    uint32_t* soff = reinterpret_cast<uint32_t*>(stile + 32 * kEpiPitch);   // [32] row offsets in 16-byte units
-    const bool has_bias = p.bias != nullptr;
-    const bool plain = !has_bias && p.act == DTG_ACT_NONE;
-    const int ncols = min(p.n_umma, p.out_nchw ? p.n_umma : p.out_C);
-    const int piece = lane & 7, rsub = lane >> 3;
-    uint8_t* const outp = reinterpret_cast<uint8_t*>(p.out);
     int it = 0;
     for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
       const int ph = tile / tiles_per_phase;
@@ -215,95 +171,11 @@ __global__ void __launch_bounds__(kThreads, 1) igemm_kernel(const __grid_constan
       const bool valid = (row < box_rows) && a < p.ph_OH[ph] && b < p.ph_OW[ph] && n < p.N;
       const int oh = p.ph_oh0[ph] + a * p.out_step;
       const int ow = p.ph_ow0[ph] + b * p.out_step;
-      const size_t pix0 = (static_cast<size_t>(n) * Hb + (oh + p.out_halo)) * Wb + (ow + p.out_halo);
-      if (!p.out_nchw) soff[lane] = valid ? static_cast<uint32_t>((pix0 * p.out_C * ES) >> 4) : 0xFFFFFFFFu;
+      epilogue_prepare<TF32>(p.e, valid, n, oh, ow, stile, lane);
       mbar_wait(&bar_tfull[buf], use & 1);
       tc_fence_after();
       const uint32_t taddr = tmem_base + (static_cast<uint32_t>(quad * 32) << 16) + buf * p.n_umma;
-      if (p.out_nchw) {
-        // heads (<= 16 channels): lanes are consecutive pixels, so per-channel stores are already coalesced
-        for (int c0 = 0; c0 < p.n_umma; c0 += 16) {
-          uint32_t v[16];
-          tmem_ld16(taddr + c0, v);
-          tmem_ld_wait();
-          if (!valid) continue;
-          float* o = reinterpret_cast<float*>(p.out);
-#pragma unroll
-          for (int j = 0; j < 16; ++j) {
-            const int c = c0 + j;
-            if (c < p.cvalid) {
-              float x = __uint_as_float(v[j]);
-              if (has_bias) x += __ldg(p.bias + c);
-              o[((static_cast<size_t>(n) * p.cvalid + c) * p.out_H + oh) * p.out_W + ow] = apply_act(x, p.act);
-            }
-          }
-        }
-      } else {
-        for (int cbase = 0; cbase < ncols; cbase += CHUNK_CH) {
-          __syncwarp();
-          const int cend = min(cbase + CHUNK_CH, p.n_umma);
-          for (int c0 = cbase; c0 < cend; c0 += 16) {
-            uint32_t v[16];
-            tmem_ld16(taddr + c0, v);
-            tmem_ld_wait();
-            if (!plain) {
-#pragma unroll
-              for (int j = 0; j < 16; ++j) {
-                float x = __uint_as_float(v[j]);
-                if (has_bias && c0 + j < p.cvalid) x += __ldg(p.bias + c0 + j);
-                v[j] = __float_as_uint(apply_act(x, p.act));
-              }
-            }
-            uint8_t* dst = stile + lane * kEpiPitch + (c0 - cbase) * ES;
-            if constexpr (!TF32) {
-              uint32_t pk[8];
-#pragma unroll
-              for (int j = 0; j < 8; ++j) {
-                __nv_bfloat162 h2 = __floats2bfloat162_rn(__uint_as_float(v[2 * j]), __uint_as_float(v[2 * j + 1]));
-                pk[j] = *reinterpret_cast<uint32_t*>(&h2);
-              }
-              reinterpret_cast<uint4*>(dst)[0] = make_uint4(pk[0], pk[1], pk[2], pk[3]);
-              reinterpret_cast<uint4*>(dst)[1] = make_uint4(pk[4], pk[5], pk[6], pk[7]);
-            } else {
-#pragma unroll
-              for (int q = 0; q < 4; ++q)
-                reinterpret_cast<float4*>(dst)[q] =
-                    make_float4(round_tf32(__uint_as_float(v[4 * q])), round_tf32(__uint_as_float(v[4 * q + 1])),
-                                round_tf32(__uint_as_float(v[4 * q + 2])), round_tf32(__uint_as_float(v[4 * q + 3])));
-            }
-          }
-          __syncwarp();
-          const int ch_of_piece = cbase + piece * PIECE_CH;
-          if (ch_of_piece < p.out_C) {
-            uint8_t* const obase = outp + static_cast<size_t>(ch_of_piece) * ES;
-#pragma unroll
-            for (int r4 = 0; r4 < 32; r4 += 4) {
-              const int rr = r4 + rsub;
-              const uint32_t off = soff[rr];
-              const uint4 val = *reinterpret_cast<const uint4*>(stile + rr * kEpiPitch + piece * 16);
-              if (off != 0xFFFFFFFFu) *reinterpret_cast<uint4*>(obase + (static_cast<size_t>(off) << 4)) = val;
-            }
-          }
-          if (p.out_reflect && valid) {
-            // mirrored copies into the reflect halo (boundary rows only): each lane copies its own row's chunk
-            int hts[3], wts[3];
-            const int nh = reflect_targets(oh, p.out_H, p.out_halo, hts);
-            const int nw = reflect_targets(ow, p.out_W, p.out_halo, wts);
-            if (nh * nw > 1) {
-              const int npieces = min(8, (p.out_C - cbase + PIECE_CH - 1) / PIECE_CH);
-              for (int i2 = 0; i2 < nh; ++i2)
-                for (int j2 = 0; j2 < nw; ++j2) {
-                  if (i2 == 0 && j2 == 0) continue;
-                  const size_t pix = (static_cast<size_t>(n) * Hb + (hts[i2] + p.out_halo)) * Wb + (wts[j2] + p.out_halo);
-                  uint8_t* o = outp + (pix * p.out_C + cbase) * ES;
-                  for (int q = 0; q < npieces; ++q)
-                    reinterpret_cast<uint4*>(o)[q] = *reinterpret_cast<const uint4*>(stile + lane * kEpiPitch + q * 16);
-                }
-            }
-          }
-        }
-        __syncwarp();
-      }
+      epilogue_rows<TF32>(p.e, taddr, valid, n, oh, ow, stile, lane);
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(&bar_tempty[buf]);
@@ -387,7 +259,6 @@ extern "C" int dtg_conv(const dtg_conv_args* a, const dtg_plane* in, const void*
   const bool tf32 = in->dtype == DTG_F32;
   const int KC = kRowBytes / es;
   DTG_REQUIRE((in->c * es) % 16 == 0 && (w_cols * es) % 16 == 0, "dtg_conv: channel pitch must be a multiple of 16 bytes");
-  DTG_REQUIRE(w_cols <= in->c || true, "unused");
   const int s = a->stride, hl = in->halo;
   const int Hb = in->h + 2 * hl, Wb = in->w + 2 * hl;
 
@@ -395,11 +266,12 @@ extern "C" int dtg_conv(const dtg_conv_args* a, const dtg_plane* in, const void*
   memset(&p, 0, sizeof(p));
   p.N = in->n;
   p.n_umma = w_rows;
+  p.e.n_umma = w_rows;
   p.kchunks = (std::min(w_cols, in->c) + KC - 1) / KC;
-  p.act = a->act;
-  p.bias = bias;
-  p.cvalid = a->cout;
-  p.out_reflect = a->out_reflect;
+  p.e.act = a->act;
+  p.e.bias = bias;
+  p.e.cvalid = a->cout;
+  p.e.out_reflect = a->out_reflect;
   const int OHl = a->out_h, OWl = a->out_w;  // interior extents of the output
 
   int PW = 0, PH = 0;
@@ -491,6 +363,41 @@ extern "C" int dtg_conv(const dtg_conv_args* a, const dtg_plane* in, const void*
   p.tiles_h = (PH + p.bh - 1) / p.bh;
   p.tiles_n = (in->n + p.bn - 1) / p.bn;
 
+  // output
+  if (a->out_nchw_f32) {
+    DTG_REQUIRE(out_nchw != nullptr, "dtg_conv: out_nchw is null");
+    p.e.out = out_nchw;
+    p.e.out_nchw = 1;
+    p.e.out_H = OHl;
+    p.e.out_W = OWl;
+    p.e.out_halo = 0;
+    p.e.out_C = a->cout;
+    DTG_REQUIRE(a->ring == 0, "dtg_conv: ring with NCHW output");
+  } else {
+    DTG_REQUIRE(out != nullptr && out->ptr != nullptr, "dtg_conv: out plane is null");
+    DTG_REQUIRE(out->dtype == in->dtype, "dtg_conv: out dtype must equal in dtype");
+    DTG_REQUIRE(out->h == OHl && out->w == OWl && out->n == in->n, "dtg_conv: out plane extent mismatch");
+    DTG_REQUIRE(out->c % (16 / es) == 0 && out->c <= w_rows, "dtg_conv: out plane channels %d vs packed rows %d", out->c, w_rows);
+    DTG_REQUIRE(out->halo >= (a->mode == DTG_CONV_DGRAD ? a->ring : 0), "dtg_conv: out halo < ring");
+    p.e.out = out->ptr;
+    p.e.out_C = out->c;
+    p.e.out_halo = out->halo;
+    p.e.out_H = out->h;
+    p.e.out_W = out->w;
+  }
+
+  const int stage_bytes = kATileBytes + p.n_umma * kRowBytes;
+  p.stages = std::max(2, std::min(8, (196 * 1024) / stage_bytes));
+  int cols = 32;
+  while (cols < 2 * p.n_umma) cols <<= 1;
+  p.tmem_cols = cols;
+  if (a->out_reflect && !a->out_nchw_f32)
+    DTG_REQUIRE(p.e.out_H >= 2 * p.e.out_halo + 2 && p.e.out_W >= 2 * p.e.out_halo + 2, "dtg_conv: reflect halo %d too wide for %dx%d", p.e.out_halo, p.e.out_H, p.e.out_W);
+  {
+    const int rc = try_launch_pconv(p, in, w, w_rows, w_cols, a->kh * a->kw, static_cast<cudaStream_t>(stream));
+    if (rc <= 0) return rc;   // launched (0) or failed (<0); 1 = not eligible
+  }
+
   // activation tensor maps
   const bool fwd_s2 = (a->mode == DTG_CONV_FWD && s == 2);
   for (int m = 0; m < 4; ++m) {
@@ -518,36 +425,6 @@ extern "C" int dtg_conv(const dtg_conv_args* a, const dtg_plane* in, const void*
     if (rc != DTG_OK) return rc;
   }
 
-  // output
-  if (a->out_nchw_f32) {
-    DTG_REQUIRE(out_nchw != nullptr, "dtg_conv: out_nchw is null");
-    p.out = out_nchw;
-    p.out_nchw = 1;
-    p.out_dtype = DTG_F32;
-    p.out_H = OHl;
-    p.out_W = OWl;
-    p.out_halo = 0;
-    p.out_C = a->cout;
-    DTG_REQUIRE(a->ring == 0, "dtg_conv: ring with NCHW output");
-  } else {
-    DTG_REQUIRE(out != nullptr && out->ptr != nullptr, "dtg_conv: out plane is null");
-    DTG_REQUIRE(out->dtype == in->dtype, "dtg_conv: out dtype must equal in dtype");
-    DTG_REQUIRE(out->h == OHl && out->w == OWl && out->n == in->n, "dtg_conv: out plane extent mismatch");
-    DTG_REQUIRE(out->c % (16 / es) == 0 && out->c <= w_rows, "dtg_conv: out plane channels %d vs packed rows %d", out->c, w_rows);
-    DTG_REQUIRE(out->halo >= (a->mode == DTG_CONV_DGRAD ? a->ring : 0), "dtg_conv: out halo < ring");
-    p.out = out->ptr;
-    p.out_dtype = out->dtype;
-    p.out_C = out->c;
-    p.out_halo = out->halo;
-    p.out_H = out->h;
-    p.out_W = out->w;
-  }
-
-  const int stage_bytes = kATileBytes + p.n_umma * kRowBytes;
-  p.stages = std::max(2, std::min(8, (196 * 1024) / stage_bytes));
-  int cols = 32;
-  while (cols < 2 * p.n_umma) cols <<= 1;
-  p.tmem_cols = cols;
   return tf32 ? launch_igemm<true>(p, static_cast<cudaStream_t>(stream))
               : launch_igemm<false>(p, static_cast<cudaStream_t>(stream));
 }

@@ -82,7 +82,7 @@ __global__ void __launch_bounds__(kWThreads, 1) wgrad_kernel(const __grid_consta
   const uint32_t tx_bytes = (p.nblkA + ntl * p.nblkB) * kBlkBytes;
 
   if (warp == 0) {
-    if (lane == 0) {
+    {   // warp-uniform loop; only the TMA / mbarrier instructions are predicated on elect.sync
       int stage = 0;
       uint32_t phase = 0;
       for (int tile = t_begin; tile < t_end; ++tile) {
@@ -94,15 +94,18 @@ __global__ void __launch_bounds__(kWThreads, 1) wgrad_kernel(const __grid_consta
         const int a0 = th * p.bh, b0 = tw * p.bw, n0 = tn * p.bn;
         mbar_wait(&bar_empty[stage], phase ^ 1);
         uint8_t* s = smem + stage * stage_bytes;
-        mbar_expect_tx(&bar_full[stage], tx_bytes);
+        if (elect_one()) mbar_expect_tx(&bar_full[stage], tx_bytes);
+        __syncwarp();
         for (int blk = 0; blk < p.nblkA; ++blk)
-          tma_load_4d(s + blk * kBlkBytes, &p.tmP, &bar_full[stage], mblock * 128 + blk * CH, b0, a0, n0);
+          if (elect_one()) tma_load_4d(s + blk * kBlkBytes, &p.tmP, &bar_full[stage], mblock * 128 + blk * CH, b0, a0, n0);
         for (int tl = 0; tl < ntl; ++tl) {
           const int t = tap0 + tl;
           for (int blk = 0; blk < p.nblkB; ++blk)
-            tma_load_4d(s + a_bytes + (tl * p.nblkB + blk) * kBlkBytes, &p.tmQ[p.tap_map[t]], &bar_full[stage],
-                        blk * CH, b0 + p.tap_dw[t], a0 + p.tap_dh[t], n0);
+            if (elect_one())
+              tma_load_4d(s + a_bytes + (tl * p.nblkB + blk) * kBlkBytes, &p.tmQ[p.tap_map[t]], &bar_full[stage],
+                          blk * CH, b0 + p.tap_dw[t], a0 + p.tap_dh[t], n0);
         }
+        __syncwarp();
         if (++stage == S) {
           stage = 0;
           phase ^= 1;
@@ -116,18 +119,20 @@ __global__ void __launch_bounds__(kWThreads, 1) wgrad_kernel(const __grid_consta
     for (int tile = t_begin; tile < t_end; ++tile) {
       mbar_wait(&bar_full[stage], phase);
       tc_fence_after();
-      if (lane == 0) {
+      {
         const uint32_t sa = smem_u32(smem + stage * stage_bytes);
+        const uint64_t ad0 = umma_desc_sw128(sa, kBlkBytes, TF32 ? 512 : 1024, TF32 ? 1 : 2);
         for (int tl = 0; tl < ntl; ++tl) {
           const uint32_t sb = sa + a_bytes + tl * p.nblkB * kBlkBytes;
+          const uint64_t bd0 = umma_desc_sw128(sb, kBlkBytes, TF32 ? 512 : 1024, TF32 ? 1 : 2);
+          const uint32_t d = tmem_base + tl * p.n_umma;
+          if (elect_one()) {
 #pragma unroll
-          for (int j = 0; j < kKP / UK; ++j) {
-            const uint64_t ad = umma_desc_sw128(sa + j * UK * 128, kBlkBytes, TF32 ? 512 : 1024, TF32 ? 1 : 2);
-            const uint64_t bd = umma_desc_sw128(sb + j * UK * 128, kBlkBytes, TF32 ? 512 : 1024, TF32 ? 1 : 2);
-            tc_mma<TF32>(tmem_base + tl * p.n_umma, ad, bd, idesc, (tile > t_begin || j > 0) ? 1u : 0u);
+            for (int j = 0; j < kKP / UK; ++j)
+              tc_mma<TF32>(d, ad0 + j * (UK * 128 / 16), bd0 + j * (UK * 128 / 16), idesc, (tile > t_begin || j > 0) ? 1u : 0u);
           }
         }
-        tc_commit(&bar_empty[stage]);
+        if (elect_one()) tc_commit(&bar_empty[stage]);
       }
       __syncwarp();
       if (++stage == S) {
@@ -135,7 +140,7 @@ __global__ void __launch_bounds__(kWThreads, 1) wgrad_kernel(const __grid_consta
         phase ^= 1;
       }
     }
-    if (lane == 0) tc_commit(bar_done);
+    if (elect_one()) tc_commit(bar_done);
     __syncwarp();
   } else {
     const int quad = warp & 3;

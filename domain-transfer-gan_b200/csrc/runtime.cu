@@ -65,8 +65,11 @@ int encode_tiled(CUtensorMap* map, int dtype, int rank, void* base, const uint64
   }
   CUresult r = fn(map, dtype == DTG_BF16 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32,
                   static_cast<cuuint32_t>(rank), base, gd, gs, bx, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
-                  swizzle == 1 ? CU_TENSOR_MAP_SWIZZLE_128B
-                               : (swizzle == 2 ? CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B : CU_TENSOR_MAP_SWIZZLE_NONE),
+                  swizzle == 1   ? CU_TENSOR_MAP_SWIZZLE_128B
+                  : swizzle == 2 ? CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B
+                  : swizzle == 3 ? CU_TENSOR_MAP_SWIZZLE_64B
+                  : swizzle == 4 ? CU_TENSOR_MAP_SWIZZLE_32B
+                                 : CU_TENSOR_MAP_SWIZZLE_NONE,
                   CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) {
     set_error("cuTensorMapEncodeTiled failed (%d): rank %d dims [%llu,%llu,%llu,%llu] box [%u,%u,%u,%u] base %p",

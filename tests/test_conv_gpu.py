@@ -41,6 +41,9 @@ CASES = [
     (5, 128, 128, 8, 8, 3, 2, 1, 0),       # D_A / E tail (several images per tile)
     (130, 16, 64, 1, 1, 1, 1, 0, 0),       # Linear as 1x1 conv on [N,1,1,C]
     (4, 256, 256, 4, 4, 4, 1, 0, 0),       # encoder 4x4 valid conv -> 1x1
+    (2, 64, 32, 64, 64, 3, 1, 1, 0),       # patch-resident kernel, one full 128-byte chunk
+    (3, 16, 32, 13, 21, 3, 1, 1, 0),       # patch-resident kernel, ragged tile edges
+    (2, 32, 16, 40, 24, 5, 1, 2, 2),       # 5x5 reflect halo 2
 ]
 
 
@@ -97,6 +100,8 @@ DGRAD_CASES = [
     (2, 64, 128, 64, 3, 2, 1, 0),      # stride-2 dgrad: 4 parity phases
     (2, 64, 128, 32, 4, 2, 1, 0),
     (2, 3, 32, 64, 7, 1, 3, 3),
+    (2, 32, 3, 64, 7, 1, 3, 0),        # dgrad of the generator's 7x7 tail (3-channel dy)
+    (2, 64, 32, 64, 3, 1, 1, 0),
     (2, 128, 256, 16, 4, 1, 1, 0),
     (3, 256, 256, 4, 4, 1, 0, 0),
 ]

@@ -7,7 +7,7 @@ import dtg  # noqa
 from dtg_b200 import _lib as L, ops
 
 case = sys.argv[1] if len(sys.argv) > 1 else "res"
-reps = int(sys.argv[2]) if len(sys.argv) > 2 else 5
+reps = int(sys.argv[2]) if len(sys.argv) > 2 else 10
 N = 80
 dt = torch.bfloat16
 g = torch.Generator().manual_seed(0)
@@ -17,13 +17,13 @@ CASES = {  # cin, cout, h, k, s, pad, halo, mode
     "c7in": (3, 32, 64, 7, 1, 3, 3, "fwd"), "c7out": (32, 3, 64, 7, 1, 3, 0, "fwd"),
     "db3": (256, 256, 15, 4, 1, 1, 0, "fwd"), "down": (64, 128, 64, 3, 2, 1, 0, "fwd"),
     "res_wgrad": (128, 128, 32, 3, 1, 1, 1, "wgrad"), "c7in_wgrad": (3, 32, 64, 7, 1, 3, 3, "wgrad"),
-    "c3b_wgrad": (64, 32, 64, 3, 1, 1, 0, "wgrad"),
+    "c3b_wgrad": (64, 32, 64, 3, 1, 1, 0, "wgrad"), "c7out_dgrad": (32, 3, 64, 7, 1, 3, 0, "dgrad"),
+    "c7in_dgrad": (3, 32, 64, 7, 1, 3, 3, "dgrad"), "c7out_wgrad": (32, 3, 64, 7, 1, 3, 0, "wgrad"), "c3a_wgrad": (32, 64, 64, 3, 1, 1, 0, "wgrad"),
 }
 cin, cout, h, k, s, pad, halo, mode = CASES[case]
 oh = (h + 2 * pad - k) // s + 1
 x = ops.PlaneT(N, h, h, ops.cpad(cin, dt), halo, dt); x.t.normal_()
 w = (torch.randn(cout, cin, k, k, generator=g) * 0.05).cuda()
-ev = [torch.cuda.Event(enable_timing=True) for _ in range(reps + 1)]
 if mode == "fwd":
     wp = ops.pack_conv_weight(w, dt, "fwd")
     out = ops.PlaneT(N, oh, oh, ops.cpad(cout, dt), 0, dt)
@@ -37,11 +37,20 @@ else:
     dy = ops.PlaneT(N, oh, oh, ops.cpad(cout, dt), 0, dt); dy.t.normal_()
     dw = torch.zeros(cout, cin, k, k, device="cuda")
     f = lambda: ops.conv_wgrad(dy, x, dw, kh=k, kw=k, stride=s, pad=pad, pa=cout, qb=cin)
-f(); torch.cuda.synchronize()
-ev[0].record()
-for i in range(reps):
-    f(); ev[i + 1].record()
-torch.cuda.synchronize()
-ts = [ev[i].elapsed_time(ev[i + 1]) * 1e3 for i in range(reps)]
+f(); f(); torch.cuda.synchronize()
+# `reps` back-to-back launches captured in one CUDA graph: pure GPU time (no host launch gaps)
+side = torch.cuda.Stream()
+g = torch.cuda.CUDAGraph()
+with torch.cuda.graph(g, stream=side):
+    for i in range(reps):
+        f()
+g.replay()
+ts = []
+for _ in range(3):
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    torch.cuda.synchronize()
+    e0.record(); g.replay(); e1.record()
+    torch.cuda.synchronize()
+    ts.append(e0.elapsed_time(e1) * 1e3 / reps)
 fl = 2.0 * N * oh * oh * cin * cout * k * k
-print(case, "us per call:", ["%.1f" % t for t in ts], "TFLOP/s best %.1f" % (fl / min(ts) / 1e6))
+print(case, "us per call (graph of %d):" % reps, ["%.1f" % t for t in ts], "TFLOP/s best %.1f" % (fl / min(ts) / 1e6))

@@ -89,20 +89,28 @@ for key, f, aa, kk in calls:
     u["count"] += 1
 
 R = args.reps
+side = torch.cuda.Stream()
 for key, u in uniq.items():
     f, aa, kk = u["f"], u["a"], u["k"]
     lc = L.lib().dtg_launch_count()
     for _ in range(3):
         f(*aa, **kk)
     u["launches"] = (L.lib().dtg_launch_count() - lc) // 3
+    torch.cuda.synchronize()
+    # R back-to-back launches captured in one CUDA graph: pure GPU time, no host launch gaps
+    g = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(g, stream=side):
+        for _ in range(R):
+            f(*aa, **kk)
+    g.replay()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     torch.cuda.synchronize()
     e0.record()
-    for _ in range(R):
-        f(*aa, **kk)
+    g.replay()
     e1.record()
     torch.cuda.synchronize()
     u["us"] = e0.elapsed_time(e1) * 1e3 / R
+    del g
 m._restore(snap)
 
 
