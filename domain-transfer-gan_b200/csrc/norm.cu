@@ -8,88 +8,12 @@
 #include <algorithm>
 
 #include "common.cuh"
+#include "norm_common.cuh"
 
 namespace dtg {
 
 constexpr int kNormThreads = 256;
 constexpr int kMaxSplits = 32;
-
-template <typename T>
-struct Vec;
-template <>
-struct Vec<__nv_bfloat16> {
-  static constexpr int N = 8;
-  __device__ static __forceinline__ void load(const void* p, float (&f)[8]) {
-    const uint4 u = *reinterpret_cast<const uint4*>(p);
-    const uint32_t w[4] = {u.x, u.y, u.z, u.w};
-#pragma unroll
-    for (int i = 0; i < 4; ++i) {
-      f[2 * i] = __uint_as_float(w[i] << 16);
-      f[2 * i + 1] = __uint_as_float(w[i] & 0xFFFF0000u);
-    }
-  }
-  __device__ static __forceinline__ void store(void* p, const float (&f)[8]) {
-    uint32_t w[4];
-#pragma unroll
-    for (int i = 0; i < 4; ++i) {
-      __nv_bfloat162 h = __floats2bfloat162_rn(f[2 * i], f[2 * i + 1]);
-      w[i] = *reinterpret_cast<uint32_t*>(&h);
-    }
-    *reinterpret_cast<uint4*>(p) = make_uint4(w[0], w[1], w[2], w[3]);
-  }
-};
-template <>
-struct Vec<float> {
-  static constexpr int N = 4;
-  __device__ static __forceinline__ void load(const void* p, float (&f)[4]) {
-    const float4 u = *reinterpret_cast<const float4*>(p);
-    f[0] = u.x; f[1] = u.y; f[2] = u.z; f[3] = u.w;
-  }
-  __device__ static __forceinline__ void store(void* p, const float (&f)[4]) {
-    *reinterpret_cast<float4*>(p) = make_float4(round_tf32(f[0]), round_tf32(f[1]), round_tf32(f[2]), round_tf32(f[3]));
-  }
-};
-
-__device__ __forceinline__ size_t plane_pix(const dtg_plane& p, int n, int y, int x) {
-  return (static_cast<size_t>(n) * (p.h + 2 * p.halo) + y + p.halo) * (p.w + 2 * p.halo) + x + p.halo;
-}
-
-__device__ __forceinline__ float act_grad(float y, int act) {
-  if (act == DTG_ACT_RELU) return y > 0.f ? 1.f : 0.f;
-  if (act == DTG_ACT_LRELU) return y > 0.f ? 1.f : 0.2f;
-  return 1.f;
-}
-
-// g = (fold(dy) + dy2) * act'(y) for one pixel / channel vector
-template <typename T>
-__device__ __forceinline__ void load_g(const dtg_plane& dy, const dtg_plane& dy2, const dtg_plane& yp, int act, int n,
-                                       int y, int x, int c, float (&g)[Vec<T>::N]) {
-  constexpr int V = Vec<T>::N;
-  const int es = sizeof(T);
-  int hts[3], wts[3];
-  const int nh = reflect_targets(y, dy.h, dy.halo, hts), nw = reflect_targets(x, dy.w, dy.halo, wts);
-#pragma unroll
-  for (int i = 0; i < V; ++i) g[i] = 0.f;
-  for (int a = 0; a < nh; ++a)
-    for (int q = 0; q < nw; ++q) {
-      float t[V];
-      Vec<T>::load(reinterpret_cast<const uint8_t*>(dy.ptr) + (plane_pix(dy, n, hts[a], wts[q]) * dy.c + c) * es, t);
-#pragma unroll
-      for (int i = 0; i < V; ++i) g[i] += t[i];
-    }
-  if (dy2.ptr) {
-    float t[V];
-    Vec<T>::load(reinterpret_cast<const uint8_t*>(dy2.ptr) + (plane_pix(dy2, n, y, x) * dy2.c + c) * es, t);
-#pragma unroll
-    for (int i = 0; i < V; ++i) g[i] += t[i];
-  }
-  if (act != DTG_ACT_NONE) {
-    float t[V];
-    Vec<T>::load(reinterpret_cast<const uint8_t*>(yp.ptr) + (plane_pix(yp, n, y, x) * yp.c + c) * es, t);
-#pragma unroll
-    for (int i = 0; i < V; ++i) g[i] *= act_grad(t[i], act);
-  }
-}
 
 // Block-level fixed-order reduction of per-thread (s1[V], s2[V]) over the pixel lanes.
 // Thread t owns vector column v = t % nv; result for (v, i) written by thread (v*V + i) < nv*V.
@@ -330,16 +254,31 @@ __global__ void norm_bwd_sums_kernel(const float* __restrict__ partial, int spli
   }
 }
 
-// stage 2 (one thread per channel): reduce sums over n -> parameter gradients (+=) and, for batch norm,
-// the per-channel sums handed to the cross-GPU all-reduce.
-__global__ void norm_bwd_channel_kernel(const float* __restrict__ sums, int n, int c, int mode, float* __restrict__ bnsum,
-                                        float* __restrict__ d_gamma, float* __restrict__ d_beta) {
-  const int ch = blockIdx.x * blockDim.x + threadIdx.x;
-  if (ch >= c) return;
+// stage 2: reduce sums over n -> parameter gradients (+=) and, for batch norm, the per-channel sums handed to the
+// cross-GPU all-reduce.  Block = 32 channels x 8 sample lanes (fixed-order two-level sum: deterministic).
+__global__ void __launch_bounds__(256) norm_bwd_channel_kernel(const float* __restrict__ sums, int n, int c, int mode,
+                                                                 float* __restrict__ bnsum, float* __restrict__ d_gamma,
+                                                                 float* __restrict__ d_beta) {
+  __shared__ float2 sh[8][32];
+  const int cl = threadIdx.x & 31, nl = threadIdx.x >> 5;
+  const int ch = blockIdx.x * 32 + cl;
   float a = 0.f, b = 0.f;
-  for (int i = 0; i < n; ++i) {
-    a += sums[(static_cast<size_t>(i) * c + ch) * 2];
-    b += sums[(static_cast<size_t>(i) * c + ch) * 2 + 1];
+  if (ch < c) {
+#pragma unroll 4
+    for (int i = nl; i < n; i += 8) {
+      const float2 v = *reinterpret_cast<const float2*>(sums + (static_cast<size_t>(i) * c + ch) * 2);
+      a += v.x;
+      b += v.y;
+    }
+  }
+  sh[nl][cl] = make_float2(a, b);
+  __syncthreads();
+  if (nl != 0 || ch >= c) return;
+  a = b = 0.f;
+#pragma unroll
+  for (int l = 0; l < 8; ++l) {
+    a += sh[l][cl].x;
+    b += sh[l][cl].y;
   }
   if (mode == DTG_NORM_BATCH) {
     bnsum[ch * 2] = a;
@@ -503,6 +442,10 @@ extern "C" int dtg_norm_fwd(const dtg_norm_args* a, const dtg_plane* x, const dt
   if (mode != DTG_NORM_NONE) {
     DTG_REQUIRE(gamma && beta && stats && coef && partial, "dtg_norm_fwd: missing buffers");
     DTG_REQUIRE(mode != DTG_NORM_COND_INSTANCE || hw > 1, "dtg_norm_fwd: conditional instance norm needs H*W > 1");
+    {
+      const int rc = try_norm_fwd_fused(a, x, residual, gamma, beta, stats, out, stream);
+      if (rc <= 0) return rc;    // launched (0) or failed (<0); 1 = not handled by the cluster kernel
+    }
     int cg = 8 * V;
     while (x->c % cg != 0) cg >>= 1;
     const int splits = pick_splits(x->n, x->c, cg, hw);
@@ -569,6 +512,17 @@ extern "C" int dtg_norm_bwd(const dtg_norm_args* a, const dtg_plane* dy, const d
   const bool need_reduce = mode != DTG_NORM_NONE || d_beta != nullptr || sums != nullptr;
   float* sums_buf = sums ? sums : kcoef + static_cast<size_t>(n) * c * 4;   // scratch when the caller wants none
   const int nc = n * c;
+  if (mode == DTG_NORM_INSTANCE || mode == DTG_NORM_COND_INSTANCE) {
+    const int rc = try_norm_bwd_fused(a, dy, dy2, y, &p_x, stats, gamma, sums_buf, dx, d_res, stream);
+    if (rc < 0) return rc;
+    if (rc == 0) {
+      if (mode == DTG_NORM_INSTANCE && (d_beta || d_gamma)) {
+        norm_bwd_channel_kernel<<<(c + 31) / 32, 256, 0, stream>>>(sums_buf, n, c, mode, bnsum, d_gamma, d_beta);
+        DTG_LAUNCHED();
+      }
+      return DTG_OK;
+    }
+  }
   if ((a->phase == 0 || a->phase == 1) && need_reduce) {
     dim3 grid(c / cg, n, splits);
     if (bf)
@@ -579,7 +533,7 @@ extern "C" int dtg_norm_bwd(const dtg_norm_args* a, const dtg_plane* dy, const d
     norm_bwd_sums_kernel<<<(nc + 127) / 128, 128, 0, stream>>>(part, splits, n, c, hw, mode, stats, gamma, sums_buf, kcoef);
     DTG_LAUNCHED();
     if (mode != DTG_NORM_COND_INSTANCE && (mode == DTG_NORM_BATCH || d_beta || d_gamma)) {
-      norm_bwd_channel_kernel<<<(c + 63) / 64, 64, 0, stream>>>(sums_buf, n, c, mode, bnsum, d_gamma, d_beta);
+      norm_bwd_channel_kernel<<<(c + 31) / 32, 256, 0, stream>>>(sums_buf, n, c, mode, bnsum, d_gamma, d_beta);
       DTG_LAUNCHED();
     }
   }
