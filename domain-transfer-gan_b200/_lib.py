@@ -19,12 +19,13 @@ class Plane(C.Structure):
 class ConvArgs(C.Structure):
     _fields_ = [("mode", C.c_int32), ("kh", C.c_int32), ("kw", C.c_int32), ("stride", C.c_int32),
                 ("pad", C.c_int32), ("ring", C.c_int32), ("act", C.c_int32), ("cout", C.c_int32),
-                ("out_nchw_f32", C.c_int32), ("out_reflect", C.c_int32), ("out_h", C.c_int32), ("out_w", C.c_int32)]
+                ("out_nchw_f32", C.c_int32), ("out_reflect", C.c_int32), ("out_h", C.c_int32), ("out_w", C.c_int32),
+                ("fold_w", C.c_int32)]
 
 
 class WgradArgs(C.Structure):
     _fields_ = [("kh", C.c_int32), ("kw", C.c_int32), ("stride", C.c_int32), ("pad", C.c_int32),
-                ("pa", C.c_int32), ("qb", C.c_int32)]
+                ("pa", C.c_int32), ("qb", C.c_int32), ("fold", C.c_int32)]
 
 
 class NormArgs(C.Structure):
@@ -35,7 +36,8 @@ class NormArgs(C.Structure):
 class PackItem(C.Structure):
     _fields_ = [("src", C.c_void_p), ("dst", C.c_void_p), ("rows", C.c_int32), ("rows_p", C.c_int32),
                 ("cols", C.c_int32), ("cols_p", C.c_int32), ("taps", C.c_int32), ("srs", C.c_int32),
-                ("scs", C.c_int32), ("dtype", C.c_int32)]
+                ("scs", C.c_int32), ("dtype", C.c_int32), ("fold_kw", C.c_int32), ("fold_flip", C.c_int32),
+                ("fold_fc", C.c_int32), ("reserved", C.c_int32)]
 
 
 _lib = None
@@ -56,7 +58,7 @@ _SIGS = {
                                C.POINTER(Plane), _P, _P, _P, _P, _P, _P, C.POINTER(Plane), C.POINTER(Plane), _P]),
     "dtg_cin_affine_fwd": (C.c_int, [_P, _P, _P, _P, _P, C.c_int, C.c_int, C.c_int, _P, _P, _P]),
     "dtg_cin_affine_bwd": (C.c_int, [_P, _P, _P, _P, _P, _P, C.c_int, C.c_int, C.c_int, _P, _P, _P, _P, _P, _P]),
-    "dtg_pack_nchw": (C.c_int, [_P, _P, C.c_int, C.c_int, C.c_int, C.c_int, C.POINTER(Plane), C.c_int, _P]),
+    "dtg_pack_nchw": (C.c_int, [_P, _P, C.c_int, C.c_int, C.c_int, C.c_int, C.POINTER(Plane), C.c_int, C.c_int, _P]),
     "dtg_unpack_nchw": (C.c_int, [C.POINTER(Plane), C.c_int, C.c_int, _P, _P]),
     "dtg_grad_gather": (C.c_int, [C.POINTER(C.POINTER(Plane)), C.POINTER(C.c_int), C.c_int, _P, _P, C.c_int,
                                   C.POINTER(Plane), _P, _P]),

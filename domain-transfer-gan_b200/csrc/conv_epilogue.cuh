@@ -59,7 +59,7 @@ struct IgemmParams {
 // Patch-resident variant (conv_patch.cu): returns DTG_OK after launching, or 1 if the geometry is not eligible
 // (the caller then falls back to the per-tap igemm kernel).
 int try_launch_pconv(const IgemmParams& p, const dtg_plane* in, const void* w, int w_rows, int w_cols, int taps_total,
-                     cudaStream_t stream);
+                     int fold_w, cudaStream_t stream);
 
 // ---- TMA-store epilogue ------------------------------------------------------------------------------------
 __device__ __forceinline__ void tma_store_4d(const CUtensorMap* m, const void* smem_src, int c0, int c1, int c2, int c3) {

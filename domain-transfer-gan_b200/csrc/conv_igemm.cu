@@ -267,7 +267,7 @@ extern "C" int dtg_conv(const dtg_conv_args* a, const dtg_plane* in, const void*
   p.N = in->n;
   p.n_umma = w_rows;
   p.e.n_umma = w_rows;
-  p.kchunks = (std::min(w_cols, in->c) + KC - 1) / KC;
+  p.kchunks = a->fold_w ? 1 : (std::min(w_cols, in->c) + KC - 1) / KC;
   p.e.act = a->act;
   p.e.bias = bias;
   p.e.cvalid = a->cout;
@@ -276,7 +276,31 @@ extern "C" int dtg_conv(const dtg_conv_args* a, const dtg_plane* in, const void*
 
   int PW = 0, PH = 0;
   int ntaps = 0;
-  if (a->mode == DTG_CONV_FWD) {
+  if (a->fold_w) {
+    // kw-folded small-channel input: GEMM-K = (kw slot, channel) through an overlapping-row TMA view, taps = KH
+    DTG_REQUIRE(s == 1 && a->ring == 0, "dtg_conv fold_w: stride 1, ring 0 only");
+    DTG_REQUIRE(in->c * es == 16, "dtg_conv fold_w: input plane must hold 16 bytes per pixel (c = %d)", in->c);
+    DTG_REQUIRE(a->kw <= 8 && w_cols * es == kRowBytes, "dtg_conv fold_w: kw %d > 8 slots or weights not kw-folded (cols %d)", a->kw, w_cols);
+    DTG_REQUIRE(hl >= a->pad && hl >= a->kw - 1 - a->pad, "dtg_conv fold_w: needs a materialised halo (%d) >= pad", hl);
+    DTG_REQUIRE(in->h + 2 * a->pad - a->kh + 1 == OHl && in->w + 2 * a->pad - a->kw + 1 == OWl, "dtg_conv fold_w: output extent mismatch");
+    p.num_phases = 1;
+    p.out_step = 1;
+    p.ph_OH[0] = OHl;
+    p.ph_OW[0] = OWl;
+    p.ph_tap_begin[0] = 0;
+    const bool fwd = a->mode == DTG_CONV_FWD;
+    for (int kh = 0; kh < a->kh; ++kh) {
+      // FWD: rows y + kh - pad, window x - pad .. ; DGRAD: rows y + pad - kh, window x + pad - (KW-1) .. (weights flipped)
+      p.tap_dh[ntaps] = static_cast<short>(fwd ? kh - a->pad + hl : a->pad - kh + hl);
+      p.tap_dw[ntaps] = static_cast<short>(fwd ? hl - a->pad : hl + a->pad - (a->kw - 1));
+      p.tap_map[ntaps] = 0;
+      p.tap_w[ntaps] = static_cast<unsigned char>(kh);
+      ++ntaps;
+    }
+    p.ph_tap_begin[1] = ntaps;
+    PW = OWl;
+    PH = OHl;
+  } else if (a->mode == DTG_CONV_FWD) {
     DTG_REQUIRE((in->h + 2 * a->pad - a->kh) / s + 1 == OHl && (in->w + 2 * a->pad - a->kw) / s + 1 == OWl,
                 "dtg_conv fwd: output extent %dx%d inconsistent with input %dx%d k%d s%d p%d", OHl, OWl, in->h, in->w, a->kh, s, a->pad);
     DTG_REQUIRE(hl == 0 || hl >= a->pad, "dtg_conv fwd: materialised halo %d < pad %d", hl, a->pad);
@@ -394,8 +418,10 @@ extern "C" int dtg_conv(const dtg_conv_args* a, const dtg_plane* in, const void*
   if (a->out_reflect && !a->out_nchw_f32)
     DTG_REQUIRE(p.e.out_H >= 2 * p.e.out_halo + 2 && p.e.out_W >= 2 * p.e.out_halo + 2, "dtg_conv: reflect halo %d too wide for %dx%d", p.e.out_halo, p.e.out_H, p.e.out_W);
   {
-    const int rc = try_launch_pconv(p, in, w, w_rows, w_cols, a->kh * a->kw, static_cast<cudaStream_t>(stream));
+    const int rc = try_launch_pconv(p, in, w, w_rows, w_cols, a->fold_w ? a->kh : a->kh * a->kw, a->fold_w,
+                                    static_cast<cudaStream_t>(stream));
     if (rc <= 0) return rc;   // launched (0) or failed (<0); 1 = not eligible
+    DTG_REQUIRE(!a->fold_w, "dtg_conv fold_w: geometry not supported by the patch kernel");
   }
 
   // activation tensor maps

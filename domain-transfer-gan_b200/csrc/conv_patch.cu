@@ -243,7 +243,7 @@ static int pow2ceil_i(int v) {
 }
 
 int try_launch_pconv(const IgemmParams& g, const dtg_plane* in, const void* w, int w_rows, int w_cols, int taps_total,
-                     cudaStream_t stream) {
+                     int fold_w, cudaStream_t stream) {
   static const bool disabled = getenv("DTG_NO_PCONV") != nullptr;
   if (disabled || g.num_phases != 1 || g.out_step != 1) return 1;
   const int ntaps = g.ph_tap_begin[1];
@@ -251,7 +251,7 @@ int try_launch_pconv(const IgemmParams& g, const dtg_plane* in, const void* w, i
     if (g.tap_map[t] != 0) return 1;       // stride-2 parity maps: per-tap kernel
   const int es = elem_size(in->dtype);
   const bool tf32 = in->dtype == DTG_F32;
-  const int kbytes = std::min(w_cols, in->c) * es;
+  const int kbytes = fold_w ? w_cols * es : std::min(w_cols, in->c) * es;
   const int kchunks = (kbytes + kRowBytes - 1) / kRowBytes;
   const int rb = kchunks > 1 ? 128 : std::max(32, pow2ceil_i(kbytes));
   const int b_tap_bytes = g.n_umma * rb;
@@ -340,7 +340,8 @@ int try_launch_pconv(const IgemmParams& g, const dtg_plane* in, const void* w, i
   const int hl = in->halo;
   const int Hb = in->h + 2 * hl, Wb = in->w + 2 * hl;
   {
-    uint64_t dims[4] = {static_cast<uint64_t>(in->c), static_cast<uint64_t>(Wb), static_cast<uint64_t>(Hb),
+    // fold_w: overlapping rows -- pixel p's row is the 128 bytes of pixels p..p+7 (dim-1 stride = 16 B < row size)
+    uint64_t dims[4] = {static_cast<uint64_t>(fold_w ? rb / es : in->c), static_cast<uint64_t>(Wb), static_cast<uint64_t>(Hb),
                         static_cast<uint64_t>(in->n)};
     uint64_t strides[3] = {static_cast<uint64_t>(in->c) * es, static_cast<uint64_t>(Wb) * in->c * es,
                            static_cast<uint64_t>(Hb) * Wb * in->c * es};

@@ -176,16 +176,30 @@ __global__ void __launch_bounds__(kWThreads, 1) wgrad_kernel(const __grid_consta
 }
 
 // dw[(a*qb + b)*ntaps + t] += sum_s ws[((s*ntaps + t)*mtot + a)*n_umma + b]
+// fold = 1: accumulator column b' = j*fc + b holds filter column kw = j          (t = kh, KW real columns)
+// fold = 2: accumulator row    a' = j*fc + a holds filter column kw = KW - 1 - j
 __global__ void wgrad_reduce_kernel(const float* __restrict__ ws, float* __restrict__ dw, int splits, int ntaps,
-                                    int mtot, int n_umma, int pa, int qb) {
-  const int total = ntaps * pa * qb;
+                                    int mtot, int n_umma, int pa, int qb, int fold, int KW, int fc) {
+  const int total = ntaps * pa * qb * (fold ? KW : 1);
   for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
-    const int b = i % qb;
-    const int a = (i / qb) % pa;
-    const int t = i / (qb * pa);
+    int r = i;
+    int j = 0;
+    if (fold) {
+      j = r % KW;
+      r /= KW;
+    }
+    const int b = r % qb;
+    const int a = (r / qb) % pa;
+    const int t = r / (qb * pa);
+    const int row = fold == 2 ? j * fc + a : a;
+    const int col = fold == 1 ? j * fc + b : b;
     float acc = 0.f;
-    for (int s = 0; s < splits; ++s) acc += ws[((static_cast<size_t>(s) * ntaps + t) * mtot + a) * n_umma + b];
-    dw[(static_cast<size_t>(a) * qb + b) * ntaps + t] += acc;
+    for (int s = 0; s < splits; ++s) acc += ws[((static_cast<size_t>(s) * ntaps + t) * mtot + row) * n_umma + col];
+    const int kw = fold == 2 ? KW - 1 - j : j;
+    if (fold)
+      dw[((static_cast<size_t>(a) * qb + b) * ntaps + t) * KW + kw] += acc;
+    else
+      dw[(static_cast<size_t>(a) * qb + b) * ntaps + t] += acc;
   }
 }
 
@@ -207,13 +221,27 @@ static int make_plan(const dtg_wgrad_args* a, const dtg_plane* pp, const dtg_pla
   DTG_REQUIRE(pp->dtype == q->dtype, "wgrad: dtype mismatch");
   DTG_REQUIRE(a->kh * a->kw <= kWMaxTaps, "wgrad: too many taps");
   DTG_REQUIRE(a->stride == 1 || a->stride == 2, "wgrad: stride");
-  DTG_REQUIRE(pp->halo == 0, "wgrad: p plane must have halo 0");
+  const int fold = a->fold;
+  DTG_REQUIRE(fold >= 0 && fold <= 2, "wgrad: bad fold mode");
+  DTG_REQUIRE(fold == 2 || pp->halo == 0, "wgrad: p plane must have halo 0");
+  if (fold) {
+    const int es_ = tf32 ? 4 : 2;
+    DTG_REQUIRE(a->stride == 1 && a->kw <= 8, "wgrad fold: stride 1 and kw <= 8 only");
+    if (fold == 1)
+      DTG_REQUIRE(q->c * es_ == 16 && q->halo >= a->pad && q->halo >= a->kw - 1 - a->pad,
+                  "wgrad fold 1: q must be a 16-byte-per-pixel plane with a materialised halo >= pad");
+    else
+      DTG_REQUIRE(pp->c * es_ == 16 && pp->halo >= a->kw - 1 - a->pad && pp->halo >= a->pad && q->halo == 0,
+                  "wgrad fold 2: p must be a 16-byte-per-pixel plane with a zero halo >= pad, q without halo");
+  }
   DTG_REQUIRE(pp->n == q->n, "wgrad: batch mismatch");
   DTG_REQUIRE((q->h + 2 * a->pad - a->kh) / a->stride + 1 == pp->h && (q->w + 2 * a->pad - a->kw) / a->stride + 1 == pp->w,
               "wgrad: p extent %dx%d inconsistent with q %dx%d k%d s%d p%d", pp->h, pp->w, q->h, q->w, a->kh, a->stride, a->pad);
   DTG_REQUIRE(q->halo == 0 || q->halo >= a->pad, "wgrad: q halo %d < pad %d", q->halo, a->pad);
   DTG_REQUIRE(a->pa <= pp->c && a->qb <= q->c, "wgrad: valid channels exceed plane channels");
-  pl->ntaps = a->kh * a->kw;
+  pl->ntaps = fold ? a->kh : a->kh * a->kw;
+  const int pa_eff = fold == 2 ? CH : a->pa;     // folded operand: 8 kw slots x 16 bytes = one 128-byte channel block
+  const int qb_eff = fold == 1 ? CH : a->qb;
   pl->bw = std::min(pow2ceil(pp->w), kKP);
   pl->bh = std::min(pow2ceil(pp->h), kKP / pl->bw);
   pl->bn = kKP / (pl->bw * pl->bh);
@@ -221,9 +249,9 @@ static int make_plan(const dtg_wgrad_args* a, const dtg_plane* pp, const dtg_pla
   pl->tiles_h = (pp->h + pl->bh - 1) / pl->bh;
   pl->tiles_n = (pp->n + pl->bn - 1) / pl->bn;
   pl->T = pl->tiles_w * pl->tiles_h * pl->tiles_n;
-  pl->mblocks = (a->pa + 127) / 128;
+  pl->mblocks = (pa_eff + 127) / 128;
   pl->nblkA = 128 / CH;
-  pl->n_umma = (a->qb + CH - 1) / CH * CH;
+  pl->n_umma = (qb_eff + CH - 1) / CH * CH;
   DTG_REQUIRE(pl->n_umma <= 256, "wgrad: q channels %d > 256", a->qb);
   pl->nblkB = pl->n_umma / CH;
   const int tmem_max = 512 / pl->n_umma;
@@ -281,7 +309,14 @@ extern "C" int dtg_conv_wgrad(const dtg_wgrad_args* a, const dtg_plane* pp, cons
   p.ws = reinterpret_cast<float*>(workspace);
 
   const int s = a->stride, hl = q->halo;
-  for (int kh = 0; kh < a->kh; ++kh)
+  const int fold = a->fold;
+  if (fold)
+    for (int kh = 0; kh < a->kh; ++kh) {
+      p.tap_dh[kh] = static_cast<short>(kh - a->pad + hl);
+      p.tap_dw[kh] = static_cast<short>(fold == 1 ? hl - a->pad : 0);
+      p.tap_map[kh] = 0;
+    }
+  for (int kh = 0; kh < a->kh && !fold; ++kh)
     for (int kw = 0; kw < a->kw; ++kw) {
       const int t = kh * a->kw + kw;
       const int eh = kh - a->pad + hl, ew = kw - a->pad + hl;
@@ -297,7 +332,18 @@ extern "C" int dtg_conv_wgrad(const dtg_wgrad_args* a, const dtg_plane* pp, cons
     }
   uint32_t box[4] = {static_cast<uint32_t>(CH), static_cast<uint32_t>(pl.bw), static_cast<uint32_t>(pl.bh),
                      static_cast<uint32_t>(pl.bn)};
-  {
+  if (fold == 2) {
+    // p folded: window of pixel x = padded pixels x + halo - (KW-1-pad) .. +7 (overlapping rows, zero halo)
+    const int hp = pp->halo, Hp = pp->h + 2 * hp, Wp = pp->w + 2 * hp;
+    const int sft = hp - (a->kw - 1 - a->pad);
+    uint8_t* base = reinterpret_cast<uint8_t*>(pp->ptr) + (static_cast<size_t>(hp) * Wp + sft) * pp->c * es;
+    uint64_t dims[4] = {static_cast<uint64_t>(CH), static_cast<uint64_t>(pp->w), static_cast<uint64_t>(pp->h),
+                        static_cast<uint64_t>(pp->n)};
+    uint64_t strides[3] = {static_cast<uint64_t>(pp->c) * es, static_cast<uint64_t>(Wp) * pp->c * es,
+                           static_cast<uint64_t>(Hp) * Wp * pp->c * es};
+    rc = encode_tiled(&p.tmP, pp->dtype, 4, base, dims, strides, box, tf32 ? 2 : 1);
+    if (rc != DTG_OK) return rc;
+  } else {
     uint64_t dims[4] = {static_cast<uint64_t>(pp->c), static_cast<uint64_t>(pp->w), static_cast<uint64_t>(pp->h),
                         static_cast<uint64_t>(pp->n)};
     uint64_t strides[3] = {static_cast<uint64_t>(pp->c) * es, static_cast<uint64_t>(pp->w) * pp->c * es,
@@ -308,7 +354,7 @@ extern "C" int dtg_conv_wgrad(const dtg_wgrad_args* a, const dtg_plane* pp, cons
   const int Hb = q->h + 2 * hl, Wb = q->w + 2 * hl;
   for (int m = 0; m < 4; ++m) {
     const int ph = s == 2 ? (m >> 1) : 0, pw = s == 2 ? (m & 1) : 0;
-    uint64_t dims[4] = {static_cast<uint64_t>(q->c), static_cast<uint64_t>(std::max(1, (Wb - pw + s - 1) / s)),
+    uint64_t dims[4] = {static_cast<uint64_t>(fold == 1 ? CH : q->c), static_cast<uint64_t>(std::max(1, (Wb - pw + s - 1) / s)),
                         static_cast<uint64_t>(std::max(1, (Hb - ph + s - 1) / s)), static_cast<uint64_t>(q->n)};
     uint64_t strides[3] = {static_cast<uint64_t>(s) * q->c * es, static_cast<uint64_t>(s) * Wb * q->c * es,
                            static_cast<uint64_t>(Hb) * Wb * q->c * es};
@@ -341,9 +387,10 @@ extern "C" int dtg_conv_wgrad(const dtg_wgrad_args* a, const dtg_plane* pp, cons
   else
     wgrad_kernel<false><<<grid, kWThreads, smem, stream>>>(p);
   DTG_LAUNCHED();
-  const int total = pl.ntaps * a->pa * a->qb;
+  const int total = pl.ntaps * a->pa * a->qb * (fold ? a->kw : 1);
   const int rgrid = std::max(1, std::min((total + 255) / 256, 148 * 8));
-  wgrad_reduce_kernel<<<rgrid, 256, 0, stream>>>(p.ws, dw, pl.splits, pl.ntaps, p.mtot, pl.n_umma, a->pa, a->qb);
+  wgrad_reduce_kernel<<<rgrid, 256, 0, stream>>>(p.ws, dw, pl.splits, pl.ntaps, p.mtot, pl.n_umma, a->pa, a->qb, fold, a->kw,
+                                                 16 / es);
   DTG_LAUNCHED();
   return DTG_OK;
 }

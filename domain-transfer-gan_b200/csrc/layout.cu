@@ -34,14 +34,22 @@ __global__ void pack_weights_kernel(const dtg_pack_item* items) {
     const int r = (i / it.cols_p) % it.rows_p;
     const int t = i / (it.cols_p * it.rows_p);
     float v = 0.f;
-    if (r < it.rows && c < it.cols) v = it.src[(static_cast<size_t>(r) * it.srs + static_cast<size_t>(c) * it.scs) * it.taps + t];
+    if (it.fold_kw > 0) {
+      const int j = c / it.fold_fc, b = c % it.fold_fc;
+      if (r < it.rows && j < it.fold_kw && b < it.cols) {
+        const int kw = it.fold_flip ? it.fold_kw - 1 - j : j;
+        v = it.src[((static_cast<size_t>(r) * it.srs + static_cast<size_t>(b) * it.scs) * it.taps + t) * it.fold_kw + kw];
+      }
+    } else if (r < it.rows && c < it.cols) {
+      v = it.src[(static_cast<size_t>(r) * it.srs + static_cast<size_t>(c) * it.scs) * it.taps + t];
+    }
     st_elem(it.dst, i, it.dtype, v);
   }
 }
 
 // NCHW fp32 -> plane channels [c_off, c_off+c), mirrored into the halo.  One thread per (n,h,w).
 __global__ void pack_nchw_kernel(const float* __restrict__ src, const float* __restrict__ tanh_y, int n, int c, int h, int w,
-                                 dtg_plane dst, int c_off) {
+                                 dtg_plane dst, int c_off, int reflect) {
   const size_t total = static_cast<size_t>(n) * h * w;
   const int Hb = dst.h + 2 * dst.halo, Wb = dst.w + 2 * dst.halo;
   for (size_t i = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; i < total;
@@ -50,7 +58,7 @@ __global__ void pack_nchw_kernel(const float* __restrict__ src, const float* __r
     const int y = (i / w) % h;
     const int b = i / (static_cast<size_t>(w) * h);
     int hts[3], wts[3];
-    const int nh = reflect_targets(y, h, dst.halo, hts), nw = reflect_targets(x, w, dst.halo, wts);
+    const int nh = reflect_targets(y, h, reflect ? dst.halo : 0, hts), nw = reflect_targets(x, w, reflect ? dst.halo : 0, wts);
     for (int ch = 0; ch < c; ++ch) {
       const size_t si = ((static_cast<size_t>(b) * c + ch) * h + y) * w + x;
       float v = src[si];
@@ -205,11 +213,11 @@ extern "C" int dtg_pack_weights(const dtg_pack_item* items_dev, int nitems, int 
 }
 
 extern "C" int dtg_pack_nchw(const float* src, const float* tanh_y, int n, int c, int h, int w, const dtg_plane* dst, int c_off,
-                             void* stream) {
+                             int reflect, void* stream) {
   DTG_REQUIRE(src && dst && dst->ptr, "dtg_pack_nchw: null");
   DTG_REQUIRE(dst->n == n && dst->h == h && dst->w == w && c_off + c <= dst->c, "dtg_pack_nchw: shape mismatch");
   const size_t total = static_cast<size_t>(n) * h * w;
-  pack_nchw_kernel<<<grid_for(total, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(src, tanh_y, n, c, h, w, *dst, c_off);
+  pack_nchw_kernel<<<grid_for(total, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(src, tanh_y, n, c, h, w, *dst, c_off, reflect);
   DTG_LAUNCHED();
   return DTG_OK;
 }

@@ -119,6 +119,10 @@ class Layer:
         self.use_bias = use_bias and norm == L.NORM_NONE and conv.bias is not None
         self.fwd_bias = self.use_bias or (norm == L.NORM_BATCH and conv.bias is not None)
         self.w_f = self.w_d = None
+        # kw-folded execution of the small-channel 7x7 layers (decided in NetExec.prepare for the plane dtype):
+        # fold_in : the INPUT is a 16-byte-per-pixel plane  -> forward conv and wgrad read it kw-folded
+        # fold_out: the OUTPUT gradient is (head with <= fc channels) -> dgrad and wgrad read dy kw-folded
+        self.fold_in = self.fold_out = False
 
     def out_hw(self, h, w):
         if self.transposed:       # k3 s2 p1 op1 -> exactly 2x
@@ -157,10 +161,21 @@ class NetExec:
         if self.pack is None or rebuilt or dtype != self.dtype:
             self.dtype = dtype
             self.pack = ops.PackTable(self.arena.device)
+            fc = ops.fold_channels(dtype)
             for ly in self.layers:
                 w = ly.conv.weight
                 w4 = w if w.dim() == 4 else w.view(w.shape[0], w.shape[1], 1, 1)
-                if ly.transposed:
+                foldable = (not ly.transposed) and ly.stride == 1 and 3 < ly.k <= 8 and 2 * ly.pad == ly.k - 1
+                ly.fold_in = foldable and ly.src == 0 and ly.cin <= fc and self.in_channels <= fc and self.in_halo >= ly.pad
+                src_halo = self.in_halo if ly.src == 0 else self.layers[ly.src - 1].out_halo
+                ly.fold_out = foldable and ly.head and ly.cout <= fc and not ly.fold_in and src_halo == 0
+                if ly.fold_in:
+                    ly.w_f = ops.add_packed(self.pack, w4, dtype, "fwd_fold")
+                    ly.w_d = ops.add_packed(self.pack, w4, dtype, "dgrad")
+                elif ly.fold_out:
+                    ly.w_f = ops.add_packed(self.pack, w4, dtype, "fwd")
+                    ly.w_d = ops.add_packed(self.pack, w4, dtype, "dgrad_fold")
+                elif ly.transposed:
                     ly.w_f = ops.add_packed(self.pack, w4, dtype, "tfwd")
                     ly.w_d = ops.add_packed(self.pack, w4, dtype, "tdgrad")
                 else:
@@ -181,7 +196,7 @@ class NetExec:
         dt, dev = self.dtype, self.arena.device
         c = Ctx()
         c.n = n
-        c.acts[0] = ops.PlaneT(n, h, w, ops.cpad(self.in_channels, dt), self.in_halo, dt, dev)
+        c.acts[0] = ops.PlaneT(n, h, w, ops.cpad_small(self.in_channels, dt), self.in_halo, dt, dev)
         dims = {0: (h, w)}
         for i, ly in enumerate(self.layers):
             ih, iw = dims[ly.src]
@@ -189,7 +204,10 @@ class NetExec:
             cs = ops.cpad(ly.cout, dt)
             if ly.head:
                 c.heads[ly.name] = torch.zeros(n, ly.cout, oh, ow, dtype=torch.float32, device=dev)
-                c.dyraw[i] = ops.PlaneT(n, oh, ow, cs, 0, dt, dev)      # seed gradient plane
+                if ly.fold_out:     # seed gradient plane read kw-folded: 16-byte pixels, zero halo = the conv's padding
+                    c.dyraw[i] = ops.PlaneT(n, oh, ow, ops.fold_channels(dt), ly.pad, dt, dev)
+                else:
+                    c.dyraw[i] = ops.PlaneT(n, oh, ow, cs, 0, dt, dev)      # seed gradient plane
                 continue
             dims[i + 1] = (oh, ow)
             c.acts[i + 1] = ops.PlaneT(n, oh, ow, cs, ly.out_halo, dt, dev)
@@ -231,7 +249,7 @@ class NetExec:
             oh, ow = ly.out_hw(ih, iw)
             mode = L.CONV_DGRAD if ly.transposed else L.CONV_FWD
             kw = dict(mode=mode, kh=ly.k, kw=ly.k, stride=ly.stride, pad=ly.pad, cout=ly.cout, out_h=oh, out_w=ow,
-                      cin=ly.cin)
+                      cin=ly.cin, fold_w=ly.fold_in)
             bias = ly.conv.bias if ly.use_bias else None
             if ly.head:
                 ops.conv(a_in, ly.w_f, bias, None, act=ly.act, out_nchw=c.heads[ly.name], **kw)
@@ -328,7 +346,8 @@ class NetExec:
                 if ly.transposed:
                     ops.conv_wgrad(a_in, dyr, dw, kh=ly.k, kw=ly.k, stride=ly.stride, pad=ly.pad, pa=ly.cin, qb=ly.cout)
                 else:
-                    ops.conv_wgrad(dyr, a_in, dw, kh=ly.k, kw=ly.k, stride=ly.stride, pad=ly.pad, pa=ly.cout, qb=ly.cin)
+                    ops.conv_wgrad(dyr, a_in, dw, kh=ly.k, kw=ly.k, stride=ly.stride, pad=ly.pad, pa=ly.cout, qb=ly.cin,
+                                   fold=1 if ly.fold_in else (2 if ly.fold_out else 0))
             # data gradient
             if ly.src > 0 or want_dx:
                 gin = self._gact(c, ly.src, i)
@@ -338,7 +357,8 @@ class NetExec:
                              cout=ly.cin, out_h=ih, out_w=iw, cin=ly.cout)
                 else:
                     ops.conv(dyr, ly.w_d, None, gin, mode=L.CONV_DGRAD, kh=ly.k, kw=ly.k, stride=ly.stride, pad=ly.pad,
-                             ring=a_in.halo, cout=ly.cin, out_h=ih, out_w=iw, cin=ly.cout)
+                             ring=a_in.halo, cout=ly.cin, out_h=ih, out_w=iw, cin=ly.cout,
+                             fold_w=ly.fold_out)
                 d0, d1 = pending.get(ly.src, (None, None))
                 assert d0 is None or d1 is None, "more than two gradient contributions for one activation"
                 pending[ly.src] = (gin, d1) if d0 is None else (gin, d0)

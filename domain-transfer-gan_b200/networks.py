@@ -93,7 +93,7 @@ class _NetFn(torch.autograd.Function):
                 continue
             idx = [i for i, ly in enumerate(ex.layers) if ly.name == hn][0]
             ly = ex.layers[idx]
-            ops.pack_nchw(dy.contiguous().float(), c.dyraw[idx], 0, tanh_y=y if ly.act == L.ACT_TANH else None)
+            ops.pack_nchw(dy.contiguous().float(), c.dyraw[idx], 0, tanh_y=y if ly.act == L.ACT_TANH else None, reflect=False)
             seeds[hn] = True
         gin = ex.backward(c, seeds, want_dx=True, want_dw=True, want_dz=ctx.zshape is not None)
         grads, off = [], 0

@@ -25,14 +25,29 @@ def cpad(c, dtype):
     return max(16, (c + 15) // 16 * 16)
 
 
+def fold_channels(dtype):
+    """channels of a 16-byte-per-pixel plane (the unit of the kw-folded 7x7 kernels): 8 bf16 / 4 fp32"""
+    return 8 if dtype == torch.bfloat16 else 4
+
+
+def cpad_small(c, dtype):
+    """stored channels of network inputs / head gradients: a 16-byte pixel when the tensor fits (so that the 7x7
+    head / tail can read it kw-folded), else cpad"""
+    fc = fold_channels(dtype)
+    return fc if c <= fc else cpad(c, dtype)
+
+
 class PlaneT:
     """NHWC activation / gradient buffer with optional halo ring: tensor [n, h+2*halo, w+2*halo, c]."""
 
-    __slots__ = ("t", "n", "h", "w", "c", "halo", "dtype", "_s")
+    __slots__ = ("t", "n", "h", "w", "c", "halo", "dtype", "_s", "_buf")
 
     def __init__(self, n, h, w, c, halo=0, dtype=torch.bfloat16, device="cuda"):
         self.n, self.h, self.w, self.c, self.halo, self.dtype = n, h, w, c, halo, dtype
-        self.t = torch.zeros(n, h + 2 * halo, w + 2 * halo, c, dtype=dtype, device=device)
+        # 256 bytes of zero slack behind the plane: kw-folded TMA views read one 128-byte row past the last pixel
+        numel = n * (h + 2 * halo) * (w + 2 * halo) * c
+        self._buf = torch.zeros(numel + 256 // torch.empty((), dtype=dtype).element_size(), dtype=dtype, device=device)
+        self.t = self._buf[:numel].view(n, h + 2 * halo, w + 2 * halo, c)
         self._s = L.Plane(self.t.data_ptr(), n, h, w, c, halo, _DT[dtype])
 
     @property
@@ -51,6 +66,7 @@ class PlaneT:
         v = PlaneT.__new__(PlaneT)
         v.n, v.h, v.w, v.c, v.halo, v.dtype = i1 - i0, self.h, self.w, self.c, self.halo, self.dtype
         v.t = self.t[i0:i1]
+        v._buf = self._buf
         v._s = L.Plane(v.t.data_ptr(), v.n, v.h, v.w, v.c, v.halo, _DT[self.dtype])
         return v
 
@@ -59,17 +75,19 @@ class PlaneT:
         """test helper: build a plane from an NCHW tensor through the library's own pack kernel."""
         n, c, h, w = x.shape
         p = PlaneT(n, h, w, c_store or cpad(c, dtype), halo, dtype, x.device)
-        pack_nchw(x.float().contiguous(), p, 0)
+        pack_nchw(x.float().contiguous(), p, 0, reflect=reflect)
         return p
 
 
 NULL_PLANE = C.POINTER(L.Plane)()
 
 
-def pack_nchw(src, dst, c_off=0, tanh_y=None):
+def pack_nchw(src, dst, c_off=0, tanh_y=None, reflect=True):
+    """reflect=False leaves dst's halo untouched (zero padding: planes are zero-initialised)"""
     n, c, h, w = src.shape
     assert src.dtype == torch.float32 and src.is_contiguous()
-    L.check(L.lib().dtg_pack_nchw(_ptr(src), _ptr(tanh_y), n, c, h, w, dst.s, c_off, _stream()), "pack_nchw")
+    L.check(L.lib().dtg_pack_nchw(_ptr(src), _ptr(tanh_y), n, c, h, w, dst.s, c_off, 1 if reflect else 0, _stream()),
+            "pack_nchw")
 
 
 def unpack_nchw(src, c, c_off=0, out=None):
@@ -89,15 +107,18 @@ class PackTable:
         self.max_elems = 0
         self.device = device
 
-    def add(self, src, rows, cols, taps, srs, scs, dtype):
+    def add(self, src, rows, cols, taps, srs, scs, dtype, fold_kw=0, fold_flip=False):
         """src: fp32 tensor (PyTorch layout, contiguous).  Returns the packed destination tensor
-        [taps, rows_p, cols_p] with dst[t][r][c] = src.flat[(r*srs + c*scs)*taps + t]."""
+        [taps, rows_p, cols_p] with dst[t][r][c] = src.flat[(r*srs + c*scs)*taps + t].
+        fold_kw = KW > 0: kw-folded packing (taps = KH): dst[kh][r][j*fc + b] = src.flat[((r*srs + b*scs)*KH + kh)*KW + kw(j)],
+        128 bytes per row (8 filter-column slots of fc channels)."""
         rows_p = max(16, (rows + 15) // 16 * 16)
         q = 8 if dtype == torch.bfloat16 else 4
-        cols_p = (cols + q - 1) // q * q
+        cols_p = 8 * q if fold_kw else (cols + q - 1) // q * q
+        assert not fold_kw or (cols <= q and fold_kw <= 8)
         dst = torch.zeros(taps, rows_p, cols_p, dtype=dtype, device=self.device)
         self.items.append(L.PackItem(src.data_ptr(), dst.data_ptr(), rows, rows_p, cols, cols_p, taps, srs, scs,
-                                     _DT[dtype]))
+                                     _DT[dtype], fold_kw, 1 if fold_flip else 0, q, 0))
         self.keep.append((src, dst))
         self.max_elems = max(self.max_elems, dst.numel())
         self.dev = None
@@ -116,7 +137,9 @@ class PackTable:
 def pack_conv_weight(w, dtype, kind):
     """Convenience (tests / small modules): pack one weight immediately.
     kind: 'fwd'   conv weight [co,ci,kh,kw]  -> rows co, cols ci        (Conv2d forward)
+          'fwd_fold'   same, kw-folded for a <= 16-byte-per-pixel input (dtg_conv fold_w)
           'dgrad' conv weight [co,ci,kh,kw]  -> rows ci, cols co        (Conv2d data gradient)
+          'dgrad_fold' same, kw-folded + flipped for a small-channel dy (dtg_conv fold_w, DGRAD)
           'tfwd'  convT weight [ci,co,kh,kw] -> rows co, cols ci        (ConvTranspose2d forward)
           'tdgrad' convT weight [ci,co,kh,kw]-> rows ci, cols co        (ConvTranspose2d data gradient)"""
     tab = PackTable(w.device)
@@ -132,6 +155,10 @@ def add_packed(tab, w, dtype, kind):
         return tab.add(w, d0, d1, taps, d1, 1, dtype)
     if kind in ("dgrad", "tfwd"):      # rows = dim1, cols = dim0
         return tab.add(w, d1, d0, taps, 1, d1, dtype)
+    if kind == "fwd_fold":
+        return tab.add(w, d0, d1, kh, d1, 1, dtype, fold_kw=kw)
+    if kind == "dgrad_fold":
+        return tab.add(w, d1, d0, kh, 1, d1, dtype, fold_kw=kw, fold_flip=True)
     raise ValueError(kind)
 
 
@@ -166,12 +193,12 @@ PROFILE = None    # set to a KernelProfile to time conv / wgrad calls
 
 
 def conv(x, wp, bias, out, *, mode=L.CONV_FWD, kh, kw, stride=1, pad=0, ring=0, act=L.ACT_NONE, cout,
-         out_h, out_w, out_reflect=False, out_nchw=None, cin=None):
+         out_h, out_w, out_reflect=False, out_nchw=None, cin=None, fold_w=False):
     """x: PlaneT; wp: packed weight [taps, rows_p, cols_p]; out: PlaneT or None with out_nchw fp32 tensor.
     cin: real input channels (FLOP accounting only)."""
     a = L.ConvArgs(mode, kh, kw, stride, pad, ring, act, cout, 1 if out_nchw is not None else 0,
-                   1 if out_reflect else 0, out_h, out_w)
-    assert wp.shape[0] == kh * kw
+                   1 if out_reflect else 0, out_h, out_w, 1 if fold_w else 0)
+    assert wp.shape[0] == (kh if fold_w else kh * kw)
     e0 = PROFILE.begin() if PROFILE is not None else None
     rc = L.lib().dtg_conv(C.byref(a), x.s, _ptr(wp), wp.shape[1], wp.shape[2], _ptr(bias),
                           out.s if out is not None else NULL_PLANE, _ptr(out_nchw), _stream())
@@ -195,9 +222,10 @@ def workspace(nbytes, device="cuda", tag="default"):
     return t
 
 
-def conv_wgrad(p, q, dw, *, kh, kw, stride=1, pad=0, pa, qb, ws=None):
-    """dw[a][b][kh][kw] += sum_pix p[pix][a] * q[pix*stride + tap - pad][b]; dw fp32 contiguous."""
-    a = L.WgradArgs(kh, kw, stride, pad, pa, qb)
+def conv_wgrad(p, q, dw, *, kh, kw, stride=1, pad=0, pa, qb, ws=None, fold=0):
+    """dw[a][b][kh][kw] += sum_pix p[pix][a] * q[pix*stride + tap - pad][b]; dw fp32 contiguous.
+    fold: 1 = q is a 16-byte-per-pixel plane read kw-folded, 2 = p is (dtg_wgrad_args.fold)."""
+    a = L.WgradArgs(kh, kw, stride, pad, pa, qb, fold)
     need = L.lib().dtg_conv_wgrad_workspace_bytes(C.byref(a), p.s, q.s)
     if need == 0:
         raise RuntimeError("dtg_b200 conv_wgrad: invalid geometry: " + L.last_error())

@@ -57,11 +57,15 @@ int dtg_last_error(char* buf, size_t cap);
  * nn.Linear weights (networks.py:159-188,211-243,322-337,366-381,405-419,446-471).
  * dst[t][r][c] (rows padded to rows_p with zeros, cols to cols_p) = src[(r*srs + c*scs)*taps + t]
  * for r < rows, c < cols.  One item per launch-y; items live in DEVICE memory.
+ * kw-folded form (fold_kw = KW > 0; small-channel 7x7 layers, see dtg_conv fold_w): `taps` = KH and a
+ * destination column c = j*fold_fc + b holds filter column j (KW-1-j if fold_flip) of inner channel b:
+ * dst[kh][r][j*fold_fc + b] = src[((r*srs + b*scs)*KH + kh)*KW + kw(j)] for j < KW, b < cols, else 0.
  * ------------------------------------------------------------------------------------------- */
 typedef struct dtg_pack_item {
   const float* src;
   void* dst;
   int32_t rows, rows_p, cols, cols_p, taps, srs, scs, dtype;
+  int32_t fold_kw, fold_flip, fold_fc, reserved;
 } dtg_pack_item;
 int dtg_pack_weights(const dtg_pack_item* items_dev, int nitems, int max_elems, void* stream);
 
@@ -82,6 +86,12 @@ int dtg_pack_weights(const dtg_pack_item* items_dev, int nitems, int max_elems, 
  * Output: a plane (dtype of `in`), optionally mirrored into its halo (out_reflect, reflection
  * padding for the next conv), or a dense fp32 NCHW tensor [n][cout][oh][ow] (out_nchw_f32 = 1,
  * cout <= 16).
+ * fold_w = 1 (stride 1, ring 0): `in` is a 16-byte-per-pixel plane (8 bf16 / 4 fp32 channels) with a
+ * MATERIALISED halo >= pad; the kernel reads it through an overlapping-row TMA view (row of pixel p =
+ * the 128 bytes of pixels p..p+7), i.e. the KW filter columns become GEMM-K: taps = KH only and
+ * `w` is the kw-folded packing [kh][w_rows][128 bytes] (dtg_pack_item fold_kw; fold_flip for DGRAD).
+ * This is the generators' 7x7 head (networks.py:159-160,211-212) and the data gradient of their 7x7
+ * tail (networks.py:187,242) without a materialised im2col.
  * ------------------------------------------------------------------------------------------- */
 typedef struct dtg_conv_args {
   int32_t mode; /* DTG_CONV_FWD / DTG_CONV_DGRAD */
@@ -92,6 +102,7 @@ typedef struct dtg_conv_args {
   int32_t out_nchw_f32; /* 1: `out_nchw` is used instead of `out` */
   int32_t out_reflect;  /* 1: mirror results into out.halo */
   int32_t out_h, out_w; /* interior output extents (validated against the geometry) */
+  int32_t fold_w;       /* 1: kw-folded small-channel input (see above) */
 } dtg_conv_args;
 int dtg_conv(const dtg_conv_args* a, const dtg_plane* in, const void* w, int w_rows, int w_cols,
              const float* bias, const dtg_plane* out, float* out_nchw, void* stream);
@@ -108,6 +119,11 @@ int dtg_conv(const dtg_conv_args* a, const dtg_plane* in, const void* w, int w_r
 typedef struct dtg_wgrad_args {
   int32_t kh, kw, stride, pad;
   int32_t pa, qb; /* valid channel counts */
+  /* 0: plain.  1: q is a 16-byte-per-pixel plane (materialised halo >= pad) read kw-folded: GEMM-N =
+   * (kw, b), taps = KH.  2: p is a 16-byte-per-pixel plane with a ZERO halo >= KW-1-pad read kw-folded:
+   * GEMM-M = (kw', a), taps = KH; q must be zero-padded (no materialised halo).  Stride 1 only.  Used for
+   * the weight gradients of the generators' 7x7 head (1) and tail (2). */
+  int32_t fold;
 } dtg_wgrad_args;
 size_t dtg_conv_wgrad_workspace_bytes(const dtg_wgrad_args* a, const dtg_plane* p, const dtg_plane* q);
 int dtg_conv_wgrad(const dtg_wgrad_args* a, const dtg_plane* p, const dtg_plane* q, float* dw,
@@ -178,7 +194,7 @@ int dtg_cin_affine_bwd(const float* z, const float* ws, const float* wb, const f
  * dtg_unpack_nchw is the inverse for the interior.
  * ------------------------------------------------------------------------------------------- */
 int dtg_pack_nchw(const float* src, const float* tanh_y, int n, int c, int h, int w, const dtg_plane* dst, int c_off,
-                  void* stream);
+                  int reflect /* 1: mirror into dst.halo; 0: leave the halo untouched (zero padding) */, void* stream);
 int dtg_unpack_nchw(const dtg_plane* src, int c_off, int c, float* dst, void* stream);
 
 /* Sum of up to 3 gradient planes (each optionally with a halo to fold, channel offset c_off[i]),

@@ -141,3 +141,32 @@ def test_conv_transpose_forward():
     ops.conv(xp, wp, b, out, mode=L.CONV_DGRAD, kh=3, kw=3, stride=2, pad=1, cout=64, out_h=64, out_w=64)
     ref = F.conv_transpose2d(x.double(), wt.double(), b.double(), stride=2, padding=1, output_padding=1).float()
     assert _relerr(out.to_nchw(64), ref) < 1.2e-2
+
+
+@pytest.mark.parametrize("dtype", [torch.bfloat16, torch.float32])
+@pytest.mark.parametrize("k,h,w", [(7, 64, 64), (5, 24, 40)])
+def test_conv_fold_fwd_and_dgrad(k, h, w, dtype):
+    """kw-folded small-channel 7x7 (5x5) layers: forward on a 16-byte-per-pixel reflect-padded input, and the data
+    gradient of a 3-channel tail from a 16-byte-per-pixel dy with a zero halo (overlapping-row TMA views)."""
+    n, pad = 2, (k - 1) // 2
+    g = torch.Generator().manual_seed(21 + k)
+    fc = ops.fold_channels(dtype)
+    # forward 3 -> 32
+    x = _q(torch.randn(n, 3, h, w, generator=g), dtype).to(DEV)
+    wt = _q(torch.randn(32, 3, k, k, generator=g) * 0.1, dtype).to(DEV)
+    xp = ops.PlaneT.from_nchw(x, halo=pad, dtype=dtype, c_store=fc)
+    out = ops.PlaneT(n, h, w, 32, 0, dtype)
+    ops.conv(xp, ops.pack_conv_weight(wt, dtype, "fwd_fold"), None, out, kh=k, kw=k, pad=pad, cout=32, out_h=h, out_w=w,
+             fold_w=True)
+    ref = F.conv2d(F.pad(x, (pad,) * 4, mode="reflect").double(), wt.double()).float()
+    assert _relerr(out.to_nchw(32), ref) < _tol(dtype)
+    # dgrad of a 32 -> 3 conv: dy has 3 channels
+    dy = _q(torch.randn(n, 3, h, w, generator=g), dtype).to(DEV)
+    wt2 = _q(torch.randn(3, 32, k, k, generator=g) * 0.1, dtype).to(DEV)
+    dyp = ops.PlaneT.from_nchw(dy, halo=pad, dtype=dtype, c_store=fc, reflect=False)
+    dx = ops.PlaneT(n, h, w, 32, 0, dtype)
+    ops.conv(dyp, ops.pack_conv_weight(wt2, dtype, "dgrad_fold"), None, dx, mode=L.CONV_DGRAD, kh=k, kw=k, pad=pad, cout=32,
+             out_h=h, out_w=w, fold_w=True)
+    xin = torch.zeros(n, 32, h, w, device=DEV, dtype=torch.float64, requires_grad=True)
+    F.conv2d(xin, wt2.double(), padding=pad).backward(dy.double())
+    assert _relerr(dx.to_nchw(32), xin.grad.float()) < _tol(dtype)

@@ -69,3 +69,39 @@ def test_conv_transpose_wgrad():
     F.conv_transpose2d(x.double(), wt, stride=2, padding=1, output_padding=1).backward(dy.double())
     ref = wt.grad.float()
     assert float((dw - ref).abs().max() / ref.abs().max()) < 2e-3
+
+
+@pytest.mark.parametrize("dtype", [torch.bfloat16, torch.float32])
+@pytest.mark.parametrize("k,h,w", [(7, 64, 64), (5, 24, 40)])
+def test_conv_wgrad_fold_q(k, h, w, dtype):
+    """fold=1: the small-channel INPUT (16-byte pixels, materialised reflect halo) is read kw-folded (7x7 head)."""
+    n, cin, cout, pad = 2, 3, 32, (k - 1) // 2
+    g = torch.Generator().manual_seed(7 + k)
+    x = _q(torch.randn(n, cin, h, w, generator=g), dtype).to(DEV)
+    dy = _q(torch.randn(n, cout, h, w, generator=g), dtype).to(DEV)
+    xq = ops.PlaneT.from_nchw(x, halo=pad, dtype=dtype, c_store=ops.fold_channels(dtype))
+    dyp = ops.PlaneT.from_nchw(dy, dtype=dtype)
+    dw = torch.full((cout, cin, k, k), 0.25, device=DEV)
+    ops.conv_wgrad(dyp, xq, dw, kh=k, kw=k, stride=1, pad=pad, pa=cout, qb=cin, fold=1)
+    wt = torch.zeros(cout, cin, k, k, device=DEV, dtype=torch.float64, requires_grad=True)
+    F.conv2d(F.pad(x, (pad,) * 4, mode="reflect").double(), wt).backward(dy.double())
+    ref = wt.grad.float() + 0.25
+    assert float((dw - ref).abs().max() / ref.abs().max()) < 2e-3
+
+
+@pytest.mark.parametrize("dtype", [torch.bfloat16, torch.float32])
+@pytest.mark.parametrize("k,h,w", [(7, 64, 64), (5, 24, 40)])
+def test_conv_wgrad_fold_p(k, h, w, dtype):
+    """fold=2: the small-channel OUTPUT GRADIENT (16-byte pixels, zero halo) is read kw-folded (7x7 tail)."""
+    n, cin, cout, pad = 2, 32, 3, (k - 1) // 2
+    g = torch.Generator().manual_seed(11 + k)
+    x = _q(torch.randn(n, cin, h, w, generator=g), dtype).to(DEV)
+    dy = _q(torch.randn(n, cout, h, w, generator=g), dtype).to(DEV)
+    xq = ops.PlaneT.from_nchw(x, dtype=dtype)
+    dyp = ops.PlaneT.from_nchw(dy, halo=pad, dtype=dtype, c_store=ops.fold_channels(dtype), reflect=False)
+    dw = torch.zeros(cout, cin, k, k, device=DEV)
+    ops.conv_wgrad(dyp, xq, dw, kh=k, kw=k, stride=1, pad=pad, pa=cout, qb=cin, fold=2)
+    wt = torch.zeros(cout, cin, k, k, device=DEV, dtype=torch.float64, requires_grad=True)
+    F.conv2d(x.double(), wt, padding=pad).backward(dy.double())
+    ref = wt.grad.float()
+    assert float((dw - ref).abs().max() / ref.abs().max()) < 2e-3
