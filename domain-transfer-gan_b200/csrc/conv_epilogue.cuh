@@ -242,7 +242,7 @@ __device__ __forceinline__ void epilogue_rows(const EpiParams& p, uint32_t taddr
     return;
   }
   const uint32_t* soff = reinterpret_cast<const uint32_t*>(stile + 32 * kEpiPitch);
-  const bool plain = !has_bias && p.act == DTG_ACT_NONE;
+  const float slope = p.act == DTG_ACT_RELU ? 0.f : (p.act == DTG_ACT_LRELU ? 0.2f : 1.f);
   const int ncols = min(p.n_umma, p.out_C);
   const int piece = lane & 7, rsub = lane >> 3;
   uint8_t* const outp = reinterpret_cast<uint8_t*>(p.out);
@@ -254,12 +254,16 @@ __device__ __forceinline__ void epilogue_rows(const EpiParams& p, uint32_t taddr
       uint32_t v[16];
       tmem_ld16(taddr + c0, v);
       tmem_ld_wait();
-      if (!plain) {
+      if (has_bias) {
+#pragma unroll
+        for (int j = 0; j < 16; ++j)
+          if (c0 + j < p.cvalid) v[j] = __float_as_uint(__uint_as_float(v[j]) + __ldg(p.bias + c0 + j));
+      }
+      if (slope != 1.f) {     // max(x, slope*x): ReLU (0) / LeakyReLU (0.2), branch-free (tanh: NCHW heads only)
 #pragma unroll
         for (int j = 0; j < 16; ++j) {
-          float x = __uint_as_float(v[j]);
-          if (has_bias && c0 + j < p.cvalid) x += __ldg(p.bias + c0 + j);
-          v[j] = __float_as_uint(apply_act(x, p.act));
+          const float x = __uint_as_float(v[j]);
+          v[j] = __float_as_uint(fmaxf(x, slope * x));
         }
       }
       uint8_t* dst = stile + lane * kEpiPitch + (c0 - cbase) * ES;

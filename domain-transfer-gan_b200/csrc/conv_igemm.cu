@@ -415,6 +415,7 @@ extern "C" int dtg_conv(const dtg_conv_args* a, const dtg_plane* in, const void*
   int cols = 32;
   while (cols < 2 * p.n_umma) cols <<= 1;
   p.tmem_cols = cols;
+  DTG_REQUIRE(a->act != DTG_ACT_TANH || a->out_nchw_f32, "dtg_conv: tanh is only fused into dense NCHW head outputs");
   if (a->out_reflect && !a->out_nchw_f32)
     DTG_REQUIRE(p.e.out_H >= 2 * p.e.out_halo + 2 && p.e.out_W >= 2 * p.e.out_halo + 2, "dtg_conv: reflect halo %d too wide for %dx%d", p.e.out_halo, p.e.out_H, p.e.out_W);
   {

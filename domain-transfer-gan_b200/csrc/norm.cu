@@ -358,44 +358,68 @@ __global__ void cin_affine_fwd_kernel(const float* __restrict__ z, const float* 
   beta[idx] = b > 0.f ? b : 0.f;
 }
 
-// one thread per (c, k) for weights (+ bias when k == 0); then one thread per (n, k) for dz
-__global__ void cin_affine_bwd_kernel(const float* __restrict__ z, const float* __restrict__ ws, const float* __restrict__ wb,
-                                      const float* __restrict__ gamma, const float* __restrict__ beta,
-                                      const float* __restrict__ sums, int n, int c, int nz, float* __restrict__ d_ws,
-                                      float* __restrict__ d_bs, float* __restrict__ d_wb, float* __restrict__ d_bb,
-                                      float* __restrict__ d_z) {
-  const int idx = blockIdx.x * blockDim.x + threadIdx.x;
-  const int nw = c * nz;
-  if (idx < nw) {
-    const int ch = idx / nz, k = idx % nz;
-    float aw = 0.f, ab = 0.f, sw = 0.f, sb = 0.f;
-    for (int i = 0; i < n; ++i) {
-      const size_t o = static_cast<size_t>(i) * c + ch;
-      const float ds = gamma[o] > 0.f ? sums[o * 2 + 1] : 0.f;  // d_scale = sum g*xhat
-      const float db = beta[o] > 0.f ? sums[o * 2] : 0.f;       // d_shift = sum g
-      const float zz = z[i * nz + k];
-      aw += ds * zz;
-      ab += db * zz;
-      sw += ds;
-      sb += db;
+// Blocks [0, c): one channel each -- 16 latent columns x 8 sample lanes reduce over n (fixed-order two-level sum).
+// Blocks [c, c+n): one sample each -- 16 latent columns x 8 channel lanes reduce over c for dz.  nz <= 16.
+__global__ void __launch_bounds__(128) cin_affine_bwd_kernel(const float* __restrict__ z, const float* __restrict__ ws,
+                                                               const float* __restrict__ wb, const float* __restrict__ gamma,
+                                                               const float* __restrict__ beta, const float* __restrict__ sums,
+                                                               int n, int c, int nz, float* __restrict__ d_ws,
+                                                               float* __restrict__ d_bs, float* __restrict__ d_wb,
+                                                               float* __restrict__ d_bb, float* __restrict__ d_z) {
+  __shared__ float4 sh[8][16];
+  const int l = threadIdx.x >> 4;
+  for (int k0 = 0; k0 < nz; k0 += 16) {     // latent columns in groups of 16
+    const int k = k0 + (threadIdx.x & 15), kl = threadIdx.x & 15;
+    if (blockIdx.x < c) {
+      const int ch = blockIdx.x;
+      float aw = 0.f, ab = 0.f, sw = 0.f, sb = 0.f;
+      for (int i = l; i < n; i += 8) {
+        const size_t o = static_cast<size_t>(i) * c + ch;
+        const float2 su = *reinterpret_cast<const float2*>(sums + o * 2);
+        const float ds = gamma[o] > 0.f ? su.y : 0.f;   // d_scale = sum g*xhat
+        const float db = beta[o] > 0.f ? su.x : 0.f;    // d_shift = sum g
+        const float zz = k < nz ? z[i * nz + k] : 0.f;
+        aw += ds * zz;
+        ab += db * zz;
+        sw += ds;
+        sb += db;
+      }
+      sh[l][kl] = make_float4(aw, ab, sw, sb);
+      __syncthreads();
+      if (l == 0 && k < nz) {
+        float4 t = sh[0][kl];
+        for (int j = 1; j < 8; ++j) {
+          t.x += sh[j][kl].x;
+          t.y += sh[j][kl].y;
+          t.z += sh[j][kl].z;
+          t.w += sh[j][kl].w;
+        }
+        d_ws[ch * nz + k] += t.x;
+        d_wb[ch * nz + k] += t.y;
+        if (k == 0) {
+          d_bs[ch] += t.z;
+          d_bb[ch] += t.w;
+        }
+      }
+    } else if (d_z != nullptr) {
+      const int i = blockIdx.x - c;
+      float acc = 0.f;
+      for (int ch = l; ch < c; ch += 8) {
+        const size_t o = static_cast<size_t>(i) * c + ch;
+        const float2 su = *reinterpret_cast<const float2*>(sums + o * 2);
+        const float ds = gamma[o] > 0.f ? su.y : 0.f;
+        const float db = beta[o] > 0.f ? su.x : 0.f;
+        if (k < nz) acc += ds * ws[ch * nz + k] + db * wb[ch * nz + k];
+      }
+      sh[l][kl].x = acc;
+      __syncthreads();
+      if (l == 0 && k < nz) {
+        float t = sh[0][kl].x;
+        for (int j = 1; j < 8; ++j) t += sh[j][kl].x;
+        d_z[i * nz + k] += t;
+      }
     }
-    d_ws[idx] += aw;
-    d_wb[idx] += ab;
-    if (k == 0) {
-      d_bs[ch] += sw;
-      d_bb[ch] += sb;
-    }
-  } else if (idx < nw + n * nz && d_z != nullptr) {
-    const int j = idx - nw;
-    const int i = j / nz, k = j % nz;
-    float acc = 0.f;
-    for (int ch = 0; ch < c; ++ch) {
-      const size_t o = static_cast<size_t>(i) * c + ch;
-      const float ds = gamma[o] > 0.f ? sums[o * 2 + 1] : 0.f;
-      const float db = beta[o] > 0.f ? sums[o * 2] : 0.f;
-      acc += ds * ws[ch * nz + k] + db * wb[ch * nz + k];
-    }
-    d_z[j] += acc;
+    __syncthreads();
   }
 }
 
@@ -565,9 +589,8 @@ extern "C" int dtg_cin_affine_bwd(const float* z, const float* ws, const float* 
                                   const float* sums, int n, int c, int nz, float* d_ws, float* d_bs, float* d_wb,
                                   float* d_bb, float* d_z, void* stream) {
   DTG_REQUIRE(z && ws && wb && gamma && beta && sums && d_ws && d_bs && d_wb && d_bb, "dtg_cin_affine_bwd: null argument");
-  const int total = c * nz + n * nz;
-  cin_affine_bwd_kernel<<<(total + 127) / 128, 128, 0, static_cast<cudaStream_t>(stream)>>>(z, ws, wb, gamma, beta, sums, n, c, nz, d_ws,
-                                                                                              d_bs, d_wb, d_bb, d_z);
+  cin_affine_bwd_kernel<<<c + (d_z ? n : 0), 128, 0, static_cast<cudaStream_t>(stream)>>>(z, ws, wb, gamma, beta, sums, n, c, nz, d_ws,
+                                                                                           d_bs, d_wb, d_bb, d_z);
   DTG_LAUNCHED();
   return DTG_OK;
 }
