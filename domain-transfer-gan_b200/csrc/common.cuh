@@ -33,6 +33,30 @@ void count_launch();
     DTG_CHECK_CUDA(cudaGetLastError());        \
   } while (0)
 
+// Kernel launch with programmatic dependent launch (PDL): the next kernel in the stream may begin launching and run
+// its prologue while this one drains; every kernel calls pdl_enter() (trigger + wait) before touching global memory,
+// so data dependencies (RAW and WAR) are still honoured.  DTG_NO_PDL=1 disables the attribute.
+bool pdl_enabled();
+#ifdef __CUDACC__
+template <typename... KArgs, typename... Args>
+inline cudaError_t launch_k(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t stream, Args&&... args) {
+  cudaLaunchConfig_t cfg;
+  memset(&cfg, 0, sizeof(cfg));
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = stream;
+  cudaLaunchAttribute at[1];
+  at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  at[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = at;
+  cfg.numAttrs = pdl_enabled() ? 1 : 0;
+  const cudaError_t e = cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
+  if (e == cudaSuccess) count_launch();
+  return e;
+}
+#endif
+
 #define DTG_REQUIRE(cond, ...)            \
   do {                                    \
     if (!(cond)) {                        \
@@ -52,6 +76,15 @@ static inline int elem_size(int dtype) { return dtype == DTG_BF16 ? 2 : 4; }
 // device helpers
 // ------------------------------------------------------------------------------------------
 #ifdef __CUDACC__
+
+// PDL: let the dependent grid start launching, then wait until every prerequisite grid has completed and its memory
+// is visible.  Must precede the first global-memory access of a kernel.
+__device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_enter() {
+  pdl_trigger();
+  pdl_wait();
+}
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) {
   return static_cast<uint32_t>(__cvta_generic_to_shared(p));

@@ -24,6 +24,7 @@ template <bool TF32>
 __global__ void __launch_bounds__(kThreads, 1) igemm_kernel(const __grid_constant__ IgemmParams p) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  pdl_trigger();      // the next kernel may start its prologue; it still waits for this grid before touching memory
   constexpr int KC = TF32 ? 32 : 64;  // elements per 128-byte row
   const int b_bytes = p.n_umma * kRowBytes;
   const int stage_bytes = kATileBytes + b_bytes;
@@ -61,6 +62,7 @@ __global__ void __launch_bounds__(kThreads, 1) igemm_kernel(const __grid_constan
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  pdl_wait();         // barriers / TMEM / descriptor prefetch above overlap the previous kernel's tail
 
   const int tiles_per_phase = p.tiles_w * p.tiles_h * p.tiles_n;
   const int total_tiles = tiles_per_phase * p.num_phases;
@@ -239,8 +241,7 @@ static int launch_igemm(const IgemmParams& p, cudaStream_t stream) {
   const size_t smem = static_cast<size_t>(p.stages) * stage_bytes + 1024 + kBarrierBytes + 4 * kEpiWarpBytes;
   const int total = p.tiles_w * p.tiles_h * p.tiles_n * p.num_phases;
   const int grid = std::max(1, std::min(total, num_sms));
-  igemm_kernel<TF32><<<grid, kThreads, smem, stream>>>(p);
-  DTG_LAUNCHED();
+  DTG_CHECK_CUDA(launch_k(igemm_kernel<TF32>, grid, kThreads, smem, stream, p));
   return DTG_OK;
 }
 

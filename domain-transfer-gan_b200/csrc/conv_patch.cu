@@ -50,6 +50,7 @@ template <bool TF32>
 __global__ void __launch_bounds__(kThreads, 1) pconv_kernel(const __grid_constant__ PconvParams p) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  pdl_trigger();      // the next kernel may start its prologue; it still waits for this grid before touching memory
   const int S = p.a_stages;
   uint8_t* sA = smem;
   uint8_t* sB = smem + S * p.a_stage_bytes;
@@ -90,6 +91,7 @@ __global__ void __launch_bounds__(kThreads, 1) pconv_kernel(const __grid_constan
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  pdl_wait();         // barriers / TMEM / descriptor prefetch above overlap the previous kernel's tail
 
   const int tiles_per_img = p.tiles_w * p.tiles_h;
   const int total_tiles = tiles_per_img * p.N;
@@ -379,10 +381,9 @@ int try_launch_pconv(const IgemmParams& g, const dtg_plane* in, const void* w, i
   const int total = p.tiles_w * p.tiles_h * p.N;
   const int grid = std::max(1, std::min(total, num_sms));
   if (tf32)
-    pconv_kernel<true><<<grid, kThreads, smem, stream>>>(p);
+    DTG_CHECK_CUDA(launch_k(pconv_kernel<true>, grid, kThreads, smem, stream, p));
   else
-    pconv_kernel<false><<<grid, kThreads, smem, stream>>>(p);
-  DTG_LAUNCHED();
+    DTG_CHECK_CUDA(launch_k(pconv_kernel<false>, grid, kThreads, smem, stream, p));
   return DTG_OK;
 }
 

@@ -10,6 +10,7 @@
 // workspace with plain coalesced stores; wgrad_reduce_kernel sums the splits in a fixed order and
 // accumulates into the fp32 PyTorch-layout gradient (deterministic, no atomics).
 #include <algorithm>
+#include <cstdlib>
 #include <mutex>
 
 #include "common.cuh"
@@ -34,6 +35,15 @@ struct WgradParams {
   int n_umma;
   int mtot;  // mblocks * 128
   int stages, tmem_cols;
+  // patch mode (stride 1): the q operand of a tap group (whole filter rows) is ONE haloed patch per channel block
+  // per stage; every tap is a row-shifted window of it (UMMA descriptors with shifted start addresses)
+  int patch;
+  int pw, ph;                 // patch extents (pixels)
+  int q_org_w, q_org_h;       // patch origin = tile origin + org (+ group * rows_per_group in h)
+  int rows_per_group;
+  int q_blk_bytes;            // pw * ph * 128
+  int stage_bytes;
+  unsigned short b_off[kWMaxTaps];   // [local tap][k-step] window start inside the patch, 16-byte units
   float* ws;
 };
 
@@ -41,13 +51,14 @@ template <bool TF32>
 __global__ void __launch_bounds__(kWThreads, 1) wgrad_kernel(const __grid_constant__ WgradParams p) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  pdl_trigger();      // the next kernel may start its prologue; it still waits for this grid before touching memory
   constexpr int CH = TF32 ? 32 : 64;   // channels per 128-byte row
   constexpr int UK = TF32 ? 8 : 16;    // pixels consumed per MMA
   const int split = blockIdx.x, group = blockIdx.y, mblock = blockIdx.z;
   const int tap0 = group * p.tpg;
   const int ntl = min(p.tpg, p.ntaps - tap0);
   const int a_bytes = p.nblkA * kBlkBytes;
-  const int stage_bytes = a_bytes + p.tpg * p.nblkB * kBlkBytes;
+  const int stage_bytes = p.stage_bytes;
   const int S = p.stages;
   uint64_t* bar_full = reinterpret_cast<uint64_t*>(smem + S * stage_bytes);
   uint64_t* bar_empty = bar_full + S;
@@ -75,11 +86,13 @@ __global__ void __launch_bounds__(kWThreads, 1) wgrad_kernel(const __grid_consta
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  pdl_wait();         // barriers / TMEM / descriptor prefetch above overlap the previous kernel's tail
 
   const int T = p.tiles_w * p.tiles_h * p.tiles_n;
   const int t_begin = split * p.tiles_per_split;
   const int t_end = min(T, t_begin + p.tiles_per_split);
-  const uint32_t tx_bytes = (p.nblkA + ntl * p.nblkB) * kBlkBytes;
+  const uint32_t tx_bytes = p.patch ? static_cast<uint32_t>(p.nblkA * kBlkBytes + p.nblkB * p.q_blk_bytes)
+                                    : static_cast<uint32_t>((p.nblkA + ntl * p.nblkB) * kBlkBytes);
 
   if (warp == 0) {
     {   // warp-uniform loop; only the TMA / mbarrier instructions are predicated on elect.sync
@@ -98,12 +111,19 @@ __global__ void __launch_bounds__(kWThreads, 1) wgrad_kernel(const __grid_consta
         __syncwarp();
         for (int blk = 0; blk < p.nblkA; ++blk)
           if (elect_one()) tma_load_4d(s + blk * kBlkBytes, &p.tmP, &bar_full[stage], mblock * 128 + blk * CH, b0, a0, n0);
-        for (int tl = 0; tl < ntl; ++tl) {
-          const int t = tap0 + tl;
+        if (p.patch) {
           for (int blk = 0; blk < p.nblkB; ++blk)
             if (elect_one())
-              tma_load_4d(s + a_bytes + (tl * p.nblkB + blk) * kBlkBytes, &p.tmQ[p.tap_map[t]], &bar_full[stage],
-                          blk * CH, b0 + p.tap_dw[t], a0 + p.tap_dh[t], n0);
+              tma_load_4d(s + a_bytes + blk * p.q_blk_bytes, &p.tmQ[0], &bar_full[stage], blk * CH, b0 + p.q_org_w,
+                          a0 + p.q_org_h + group * p.rows_per_group, n0);
+        } else {
+          for (int tl = 0; tl < ntl; ++tl) {
+            const int t = tap0 + tl;
+            for (int blk = 0; blk < p.nblkB; ++blk)
+              if (elect_one())
+                tma_load_4d(s + a_bytes + (tl * p.nblkB + blk) * kBlkBytes, &p.tmQ[p.tap_map[t]], &bar_full[stage],
+                            blk * CH, b0 + p.tap_dw[t], a0 + p.tap_dh[t], n0);
+          }
         }
         __syncwarp();
         if (++stage == S) {
@@ -122,14 +142,27 @@ __global__ void __launch_bounds__(kWThreads, 1) wgrad_kernel(const __grid_consta
       {
         const uint32_t sa = smem_u32(smem + stage * stage_bytes);
         const uint64_t ad0 = umma_desc_sw128(sa, kBlkBytes, TF32 ? 512 : 1024, TF32 ? 1 : 2);
-        for (int tl = 0; tl < ntl; ++tl) {
-          const uint32_t sb = sa + a_bytes + tl * p.nblkB * kBlkBytes;
-          const uint64_t bd0 = umma_desc_sw128(sb, kBlkBytes, TF32 ? 512 : 1024, TF32 ? 1 : 2);
-          const uint32_t d = tmem_base + tl * p.n_umma;
+        if (p.patch) {
+          const uint64_t bq0 = umma_desc_sw128(sa + a_bytes, p.q_blk_bytes, TF32 ? 512 : 1024, TF32 ? 1 : 2);
           if (elect_one()) {
+            const uint32_t acc = tile > t_begin ? 1u : 0u;
+            for (int tl = 0; tl < ntl; ++tl) {
+              const uint32_t d = tmem_base + tl * p.n_umma;
 #pragma unroll
-            for (int j = 0; j < kKP / UK; ++j)
-              tc_mma<TF32>(d, ad0 + j * (UK * 128 / 16), bd0 + j * (UK * 128 / 16), idesc, (tile > t_begin || j > 0) ? 1u : 0u);
+              for (int j = 0; j < kKP / UK; ++j)
+                tc_mma<TF32>(d, ad0 + j * (UK * 128 / 16), bq0 + p.b_off[tl * (kKP / UK) + j], idesc, j > 0 ? 1u : acc);
+            }
+          }
+        } else {
+          for (int tl = 0; tl < ntl; ++tl) {
+            const uint32_t sb = sa + a_bytes + tl * p.nblkB * kBlkBytes;
+            const uint64_t bd0 = umma_desc_sw128(sb, kBlkBytes, TF32 ? 512 : 1024, TF32 ? 1 : 2);
+            const uint32_t d = tmem_base + tl * p.n_umma;
+            if (elect_one()) {
+#pragma unroll
+              for (int j = 0; j < kKP / UK; ++j)
+                tc_mma<TF32>(d, ad0 + j * (UK * 128 / 16), bd0 + j * (UK * 128 / 16), idesc, (tile > t_begin || j > 0) ? 1u : 0u);
+            }
           }
         }
         if (elect_one()) tc_commit(&bar_empty[stage]);
@@ -178,34 +211,74 @@ __global__ void __launch_bounds__(kWThreads, 1) wgrad_kernel(const __grid_consta
 // dw[(a*qb + b)*ntaps + t] += sum_s ws[((s*ntaps + t)*mtot + a)*n_umma + b]
 // fold = 1: accumulator column b' = j*fc + b holds filter column kw = j          (t = kh, KW real columns)
 // fold = 2: accumulator row    a' = j*fc + a holds filter column kw = KW - 1 - j
-__global__ void wgrad_reduce_kernel(const float* __restrict__ ws, float* __restrict__ dw, int splits, int ntaps,
-                                    int mtot, int n_umma, int pa, int qb, int fold, int KW, int fc) {
-  const int total = ntaps * pa * qb * (fold ? KW : 1);
-  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
-    int r = i;
-    int j = 0;
-    if (fold) {
-      j = r % KW;
-      r /= KW;
+__global__ void __launch_bounds__(256) wgrad_reduce_kernel(const float* __restrict__ ws, float* __restrict__ dw, int splits,
+                                                           int ntaps, int mtot, int n_umma, int pa, int qb, int fold, int KW,
+                                                           int fc) {
+  pdl_enter();
+  // block = 32 float4 columns x 8 split lanes: lane l sums splits l, l+8, ... (independent loads), then the 8 lane
+  // partials are added in a fixed order (deterministic); one thread per float4 writes.
+  __shared__ float4 sh[8][32];
+  const int ncol4 = n_umma / 4;
+  const int rows = fold == 2 ? KW * fc : pa;          // accumulator rows that hold data
+  const int total = ntaps * rows * ncol4;
+  const size_t sstride = static_cast<size_t>(ntaps) * mtot * n_umma;
+  const int cl = threadIdx.x & 31, sl = threadIdx.x >> 5;
+  for (int i0 = blockIdx.x * 32; i0 < total; i0 += gridDim.x * 32) {
+    const int i = i0 + cl;
+    const bool ok = i < total;
+    const int c4 = ok ? i % ncol4 : 0;
+    const int row = ok ? (i / ncol4) % rows : 0;
+    const int t = ok ? i / (ncol4 * rows) : 0;
+    const float* src = ws + (static_cast<size_t>(t) * mtot + row) * n_umma + c4 * 4;
+    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (ok) {
+#pragma unroll 4
+      for (int s = sl; s < splits; s += 8) {
+        const float4 v = *reinterpret_cast<const float4*>(src + s * sstride);
+        acc.x += v.x;
+        acc.y += v.y;
+        acc.z += v.z;
+        acc.w += v.w;
+      }
     }
-    const int b = r % qb;
-    const int a = (r / qb) % pa;
-    const int t = r / (qb * pa);
-    const int row = fold == 2 ? j * fc + a : a;
-    const int col = fold == 1 ? j * fc + b : b;
-    float acc = 0.f;
-    for (int s = 0; s < splits; ++s) acc += ws[((static_cast<size_t>(s) * ntaps + t) * mtot + row) * n_umma + col];
-    const int kw = fold == 2 ? KW - 1 - j : j;
-    if (fold)
-      dw[((static_cast<size_t>(a) * qb + b) * ntaps + t) * KW + kw] += acc;
-    else
-      dw[(static_cast<size_t>(a) * qb + b) * ntaps + t] += acc;
+    __syncthreads();
+    sh[sl][cl] = acc;
+    __syncthreads();
+    if (sl != 0 || !ok) continue;
+#pragma unroll
+    for (int l = 1; l < 8; ++l) {
+      acc.x += sh[l][cl].x;
+      acc.y += sh[l][cl].y;
+      acc.z += sh[l][cl].z;
+      acc.w += sh[l][cl].w;
+    }
+    const float av[4] = {acc.x, acc.y, acc.z, acc.w};
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+      const int col = c4 * 4 + e;
+      int a = row, b = col, j = 0;
+      if (fold == 1) {
+        j = col / fc;
+        b = col % fc;
+      } else if (fold == 2) {
+        j = row / fc;
+        a = row % fc;
+      }
+      if (a >= pa || b >= qb || j >= KW) continue;
+      if (fold) {
+        const int kw = fold == 2 ? KW - 1 - j : j;
+        dw[((static_cast<size_t>(a) * qb + b) * ntaps + t) * KW + kw] += av[e];
+      } else {
+        dw[(static_cast<size_t>(a) * qb + b) * ntaps + t] += av[e];
+      }
+    }
   }
 }
 
 struct WgradPlan {
   int bw, bh, bn, tiles_w, tiles_h, tiles_n, T;
   int ntaps, tpg, ngroups, mblocks, nblkA, nblkB, n_umma, stages, tmem_cols, splits, tiles_per_split;
+  int patch, pw, ph, rows_per_group, stage_bytes;
   size_t ws_bytes;
 };
 
@@ -260,7 +333,35 @@ static int make_plan(const dtg_wgrad_args* a, const dtg_plane* pp, const dtg_pla
   pl->ngroups = (pl->ntaps + tpg_max - 1) / tpg_max;
   pl->tpg = (pl->ntaps + pl->ngroups - 1) / pl->ngroups;
   pl->ngroups = (pl->ntaps + pl->tpg - 1) / pl->tpg;
-  const int stage_bytes = (pl->nblkA + pl->tpg * pl->nblkB) * kBlkBytes;
+  int stage_bytes = (pl->nblkA + pl->tpg * pl->nblkB) * kBlkBytes;
+  // patch mode: groups are whole filter rows (kh_eff x kw_eff taps, folded layers have kw_eff = 1)
+  pl->patch = 0;
+  {
+    static const bool no_patch = getenv("DTG_NO_WGRAD_PATCH") != nullptr;
+    const int kh_eff = a->kh, kw_eff = fold ? 1 : a->kw;
+    const int UKp = tf32 ? 8 : 16;
+    if (!no_patch && a->stride == 1 && pl->bn == 1 && pl->bw >= UKp && kw_eff * pl->n_umma <= 512) {
+      int r = 0;
+      for (int cand = kh_eff; cand >= 1; --cand) {
+        if (kh_eff % cand != 0 || cand * kw_eff * pl->n_umma > 512 || cand * kw_eff * (kKP / UKp) > kWMaxTaps) continue;
+        const int sb = pl->nblkA * kBlkBytes + pl->nblkB * (pl->bw + kw_eff - 1) * (pl->bh + cand - 1) * 128;
+        if (2 * ((sb + 1023) & ~1023) > 200 * 1024) continue;
+        r = cand;
+        break;
+      }
+      if (r > 0) {
+        pl->patch = 1;
+        pl->rows_per_group = r;
+        pl->pw = pl->bw + kw_eff - 1;
+        pl->ph = pl->bh + r - 1;
+        pl->tpg = r * kw_eff;
+        pl->ngroups = kh_eff / r;
+        stage_bytes = pl->nblkA * kBlkBytes + pl->nblkB * pl->pw * pl->ph * 128;
+      }
+    }
+  }
+  stage_bytes = (stage_bytes + 1023) & ~1023;
+  pl->stage_bytes = stage_bytes;
   pl->stages = std::max(2, std::min(6, (200 * 1024) / stage_bytes));
   int cols = 32;
   while (cols < pl->tpg * pl->n_umma) cols <<= 1;
@@ -306,6 +407,9 @@ extern "C" int dtg_conv_wgrad(const dtg_wgrad_args* a, const dtg_plane* pp, cons
   p.nblkA = pl.nblkA; p.nblkB = pl.nblkB; p.n_umma = pl.n_umma;
   p.mtot = pl.mblocks * 128;
   p.stages = pl.stages; p.tmem_cols = pl.tmem_cols;
+  p.patch = pl.patch; p.pw = pl.pw; p.ph = pl.ph; p.rows_per_group = pl.rows_per_group;
+  p.q_blk_bytes = pl.pw * pl.ph * 128;
+  p.stage_bytes = pl.stage_bytes;
   p.ws = reinterpret_cast<float*>(workspace);
 
   const int s = a->stride, hl = q->halo;
@@ -330,8 +434,25 @@ extern "C" int dtg_conv_wgrad(const dtg_wgrad_args* a, const dtg_plane* pp, cons
         p.tap_map[t] = static_cast<unsigned char>((eh & 1) * 2 + (ew & 1));
       }
     }
+  if (pl.patch) {
+    // tap (kh, kw) of group g = kh / r reads q at tile pixel + (tap_dh, tap_dw); patch origin = offsets of the group's
+    // first tap; local tap order is kh-major, matching the global tap index t = kh * kw_eff + kw
+    const int kw_eff = fold ? 1 : a->kw;
+    const int UKp = tf32 ? 8 : 16, nk = kKP / UKp, segs = pl.bw / UKp;
+    p.q_org_h = p.tap_dh[0];
+    p.q_org_w = p.tap_dw[0];
+    for (int tl = 0; tl < pl.tpg; ++tl) {
+      const int dkh = tl / kw_eff, dkw = tl % kw_eff;
+      for (int j = 0; j < nk; ++j) {
+        const int row = j / segs, seg = j % segs;
+        p.b_off[tl * nk + j] = static_cast<unsigned short>((((dkh + row) * pl.pw + dkw + seg * UKp) * 128) >> 4);
+      }
+    }
+  }
   uint32_t box[4] = {static_cast<uint32_t>(CH), static_cast<uint32_t>(pl.bw), static_cast<uint32_t>(pl.bh),
                      static_cast<uint32_t>(pl.bn)};
+  uint32_t qbox[4] = {static_cast<uint32_t>(CH), static_cast<uint32_t>(pl.patch ? pl.pw : pl.bw),
+                      static_cast<uint32_t>(pl.patch ? pl.ph : pl.bh), static_cast<uint32_t>(pl.bn)};
   if (fold == 2) {
     // p folded: window of pixel x = padded pixels x + halo - (KW-1-pad) .. +7 (overlapping rows, zero halo)
     const int hp = pp->halo, Hp = pp->h + 2 * hp, Wp = pp->w + 2 * hp;
@@ -359,7 +480,7 @@ extern "C" int dtg_conv_wgrad(const dtg_wgrad_args* a, const dtg_plane* pp, cons
     uint64_t strides[3] = {static_cast<uint64_t>(s) * q->c * es, static_cast<uint64_t>(s) * Wb * q->c * es,
                            static_cast<uint64_t>(Hb) * Wb * q->c * es};
     uint8_t* base = reinterpret_cast<uint8_t*>(q->ptr) + (static_cast<size_t>(ph) * Wb + pw) * q->c * es;
-    rc = encode_tiled(&p.tmQ[m], q->dtype, 4, base, dims, strides, box, tf32 ? 2 : 1);
+    rc = encode_tiled(&p.tmQ[m], q->dtype, 4, base, dims, strides, qbox, tf32 ? 2 : 1);
     if (rc != DTG_OK) return rc;
     if (s == 1) {
       for (int k = 1; k < 4; ++k) p.tmQ[k] = p.tmQ[0];
@@ -379,18 +500,15 @@ extern "C" int dtg_conv_wgrad(const dtg_wgrad_args* a, const dtg_plane* pp, cons
       attr_set[tf32 ? 1 : 0] = true;
     }
   }
-  const int stage_bytes = (pl.nblkA + pl.tpg * pl.nblkB) * kBlkBytes;
-  const size_t smem = static_cast<size_t>(pl.stages) * stage_bytes + 1024 + 256;
+  const size_t smem = static_cast<size_t>(pl.stages) * pl.stage_bytes + 1024 + 256;
   dim3 grid(pl.splits, pl.ngroups, pl.mblocks);
   if (tf32)
-    wgrad_kernel<true><<<grid, kWThreads, smem, stream>>>(p);
+    DTG_CHECK_CUDA(launch_k(wgrad_kernel<true>, grid, kWThreads, smem, stream, p));
   else
-    wgrad_kernel<false><<<grid, kWThreads, smem, stream>>>(p);
-  DTG_LAUNCHED();
-  const int total = pl.ntaps * a->pa * a->qb * (fold ? a->kw : 1);
-  const int rgrid = std::max(1, std::min((total + 255) / 256, 148 * 8));
-  wgrad_reduce_kernel<<<rgrid, 256, 0, stream>>>(p.ws, dw, pl.splits, pl.ntaps, p.mtot, pl.n_umma, a->pa, a->qb, fold, a->kw,
-                                                 16 / es);
-  DTG_LAUNCHED();
+    DTG_CHECK_CUDA(launch_k(wgrad_kernel<false>, grid, kWThreads, smem, stream, p));
+  const int total = pl.ntaps * (fold == 2 ? a->kw * (16 / es) : a->pa) * (pl.n_umma / 4);
+  const int rgrid = std::max(1, std::min((total + 31) / 32, 148 * 16));
+  DTG_CHECK_CUDA(launch_k(wgrad_reduce_kernel, rgrid, 256, 0, stream, p.ws, dw, pl.splits, pl.ntaps, p.mtot, pl.n_umma, a->pa, a->qb, fold, a->kw,
+                                                 16 / es));
   return DTG_OK;
 }

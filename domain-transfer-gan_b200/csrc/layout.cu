@@ -27,6 +27,7 @@ __device__ __forceinline__ void st_elem(void* base, size_t idx, int dtype, float
 
 // one block-row (blockIdx.y) per item; threads stride over the padded destination
 __global__ void pack_weights_kernel(const dtg_pack_item* items) {
+  pdl_enter();
   const dtg_pack_item it = items[blockIdx.y];
   const int total = it.taps * it.rows_p * it.cols_p;
   for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
@@ -50,6 +51,7 @@ __global__ void pack_weights_kernel(const dtg_pack_item* items) {
 // NCHW fp32 -> plane channels [c_off, c_off+c), mirrored into the halo.  One thread per (n,h,w).
 __global__ void pack_nchw_kernel(const float* __restrict__ src, const float* __restrict__ tanh_y, int n, int c, int h, int w,
                                  dtg_plane dst, int c_off, int reflect) {
+  pdl_enter();
   const size_t total = static_cast<size_t>(n) * h * w;
   const int Hb = dst.h + 2 * dst.halo, Wb = dst.w + 2 * dst.halo;
   for (size_t i = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; i < total;
@@ -76,6 +78,7 @@ __global__ void pack_nchw_kernel(const float* __restrict__ src, const float* __r
 }
 
 __global__ void unpack_nchw_kernel(dtg_plane src, int c_off, int c, float* __restrict__ dst) {
+  pdl_enter();
   const size_t total = static_cast<size_t>(src.n) * src.h * src.w;
   const int Hb = src.h + 2 * src.halo, Wb = src.w + 2 * src.halo;
   for (size_t i = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; i < total;
@@ -111,6 +114,7 @@ struct GatherArgs {
 
 __global__ void grad_gather_kernel(GatherArgs g, const float* __restrict__ add_nchw, const float* __restrict__ tanh_y, int c,
                                    dtg_plane out, float* __restrict__ out_nchw) {
+  pdl_enter();
   const int h = out.h, w = out.w;
   const size_t total = static_cast<size_t>(out.n) * h * w;
   for (size_t i = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; i < total;
@@ -146,6 +150,7 @@ struct ChanSumWs {
 };
 
 __global__ void __launch_bounds__(256) channel_sum_kernel(dtg_plane x, int c, float* __restrict__ d_bias, ChanSumWs* ws) {
+  pdl_enter();
   const int Hb = x.h + 2 * x.halo, Wb = x.w + 2 * x.halo;
   const size_t total = static_cast<size_t>(x.n) * x.h * x.w;
   float acc[16];
@@ -207,8 +212,7 @@ using namespace dtg;
 extern "C" int dtg_pack_weights(const dtg_pack_item* items_dev, int nitems, int max_elems, void* stream) {
   DTG_REQUIRE(items_dev && nitems > 0, "dtg_pack_weights: no items");
   dim3 grid(grid_for(static_cast<size_t>(max_elems), 256, 64), nitems);
-  pack_weights_kernel<<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(items_dev);
-  DTG_LAUNCHED();
+  DTG_CHECK_CUDA(launch_k(pack_weights_kernel, grid, 256, 0, static_cast<cudaStream_t>(stream), items_dev));
   return DTG_OK;
 }
 
@@ -217,16 +221,14 @@ extern "C" int dtg_pack_nchw(const float* src, const float* tanh_y, int n, int c
   DTG_REQUIRE(src && dst && dst->ptr, "dtg_pack_nchw: null");
   DTG_REQUIRE(dst->n == n && dst->h == h && dst->w == w && c_off + c <= dst->c, "dtg_pack_nchw: shape mismatch");
   const size_t total = static_cast<size_t>(n) * h * w;
-  pack_nchw_kernel<<<grid_for(total, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(src, tanh_y, n, c, h, w, *dst, c_off, reflect);
-  DTG_LAUNCHED();
+  DTG_CHECK_CUDA(launch_k(pack_nchw_kernel, grid_for(total, 256), 256, 0, static_cast<cudaStream_t>(stream), src, tanh_y, n, c, h, w, *dst, c_off, reflect));
   return DTG_OK;
 }
 
 extern "C" int dtg_unpack_nchw(const dtg_plane* src, int c_off, int c, float* dst, void* stream) {
   DTG_REQUIRE(src && src->ptr && dst && c_off + c <= src->c, "dtg_unpack_nchw: bad args");
   const size_t total = static_cast<size_t>(src->n) * src->h * src->w;
-  unpack_nchw_kernel<<<grid_for(total, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(*src, c_off, c, dst);
-  DTG_LAUNCHED();
+  DTG_CHECK_CUDA(launch_k(unpack_nchw_kernel, grid_for(total, 256), 256, 0, static_cast<cudaStream_t>(stream), *src, c_off, c, dst));
   return DTG_OK;
 }
 
@@ -245,8 +247,7 @@ extern "C" int dtg_grad_gather(const dtg_plane* const* srcs, const int* c_off, i
   }
   DTG_REQUIRE(out->ptr == nullptr || c <= out->c, "dtg_grad_gather: out channels");
   const size_t total = static_cast<size_t>(out->n) * out->h * out->w;
-  grad_gather_kernel<<<grid_for(total, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(g, add_nchw, tanh_y, c, *out, out_nchw);
-  DTG_LAUNCHED();
+  DTG_CHECK_CUDA(launch_k(grad_gather_kernel, grid_for(total, 256), 256, 0, static_cast<cudaStream_t>(stream), g, add_nchw, tanh_y, c, *out, out_nchw));
   return DTG_OK;
 }
 
@@ -254,7 +255,6 @@ extern "C" int dtg_channel_sum(const dtg_plane* x, int c, float* d_bias, void* w
   DTG_REQUIRE(x && x->ptr && d_bias && workspace && c <= x->c && c <= 16, "dtg_channel_sum: bad args (c <= 16)");
   const size_t total = static_cast<size_t>(x->n) * x->h * x->w;
   const int blocks = static_cast<int>(std::max<size_t>(1, std::min<size_t>((total + 1023) / 1024, kCsBlocks)));
-  channel_sum_kernel<<<blocks, 256, 0, static_cast<cudaStream_t>(stream)>>>(*x, c, d_bias, reinterpret_cast<ChanSumWs*>(workspace));
-  DTG_LAUNCHED();
+  DTG_CHECK_CUDA(launch_k(channel_sum_kernel, blocks, 256, 0, static_cast<cudaStream_t>(stream), *x, c, d_bias, reinterpret_cast<ChanSumWs*>(workspace)));
   return DTG_OK;
 }

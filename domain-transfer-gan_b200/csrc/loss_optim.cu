@@ -65,6 +65,7 @@ __device__ __forceinline__ void st_plane(const dtg_plane& p, size_t idx, float v
 __global__ void __launch_bounds__(kRedThreads) lsgan_kernel(const float* __restrict__ pred, int n, int h, int w, float target,
                                                             float gscale, float* __restrict__ scalars, int slot_loss,
                                                             int slot_mean, dtg_plane dp, RedWs* ws) {
+  pdl_enter();
   __shared__ float sm[(kRedThreads / 32) * 2];
   const int count = n * h * w;
   float v[2] = {0.f, 0.f};
@@ -96,6 +97,7 @@ __global__ void __launch_bounds__(kRedThreads) l1_kernel(const float* __restrict
                                                          int h, int w, float gscale, int tanh_bwd,
                                                          float* __restrict__ scalars, int slot_loss, int slot_aux,
                                                          dtg_plane da, RedWs* ws) {
+  pdl_enter();
   __shared__ float sm[(kRedThreads / 32) * 2];
   __shared__ float smm[(kRedThreads / 32) * 2];
   const int count = n * c * h * w;
@@ -156,6 +158,7 @@ __global__ void __launch_bounds__(kRedThreads) l1_kernel(const float* __restrict
 
 __global__ void __launch_bounds__(kRedThreads) sumsq_kernel(const float* __restrict__ g, size_t count, float gscale,
                                                             float* __restrict__ out, RedWs* ws) {
+  pdl_enter();
   __shared__ float sm[kRedThreads / 32];
   float v[1] = {0.f};
   const size_t n4 = count / 4;
@@ -178,6 +181,7 @@ __global__ void __launch_bounds__(256) adam_clip_kernel(float* __restrict__ p, f
                                                         float* __restrict__ v, size_t count, const float* __restrict__ hyper,
                                                         const float* __restrict__ sumsq, const int32_t* __restrict__ step_dev,
                                                         float gscale) {
+  pdl_enter();
   __shared__ float s_coef, s_step_size, s_inv_sqrt_bc2;
   if (threadIdx.x == 0) {
     const float lr = hyper[0], b1 = hyper[1], b2 = hyper[2], max_norm = hyper[4];
@@ -204,7 +208,8 @@ __global__ void __launch_bounds__(256) adam_clip_kernel(float* __restrict__ p, f
   }
 }
 
-__global__ void step_inc_kernel(int32_t* s) { *s += 1; }
+__global__ void step_inc_kernel(int32_t* s) {
+  pdl_enter(); *s += 1; }
 
 }  // namespace dtg
 
@@ -222,9 +227,7 @@ extern "C" int dtg_loss_lsgan(const float* pred, int n, int h, int w, float targ
     DTG_REQUIRE(dpred->n == n && dpred->h == h && dpred->w == w, "dtg_loss_lsgan: dpred plane mismatch");
     dp = *dpred;
   }
-  lsgan_kernel<<<red_blocks(static_cast<size_t>(n) * h * w), kRedThreads, 0, static_cast<cudaStream_t>(stream)>>>(
-      pred, n, h, w, target, grad_scale, scalars, slot_loss, slot_mean, dp, reinterpret_cast<RedWs*>(workspace));
-  DTG_LAUNCHED();
+  DTG_CHECK_CUDA(launch_k(lsgan_kernel, red_blocks(static_cast<size_t>(n) * h * w), kRedThreads, 0, static_cast<cudaStream_t>(stream), pred, n, h, w, target, grad_scale, scalars, slot_loss, slot_mean, dp, reinterpret_cast<RedWs*>(workspace)));
   return DTG_OK;
 }
 
@@ -236,18 +239,15 @@ extern "C" int dtg_loss_l1(const float* a, const float* b, int n, int c, int h, 
     DTG_REQUIRE(da->n == n && da->h == h && da->w == w && da->c >= c, "dtg_loss_l1: da plane mismatch");
     dp = *da;
   }
-  l1_kernel<<<red_blocks(static_cast<size_t>(n) * c * h * w), kRedThreads, 0, static_cast<cudaStream_t>(stream)>>>(
-      a, b, n, c, h, w, grad_scale, tanh_bwd, scalars, slot_loss, slot_aux, dp, reinterpret_cast<RedWs*>(workspace));
-  DTG_LAUNCHED();
+  DTG_CHECK_CUDA(launch_k(l1_kernel, red_blocks(static_cast<size_t>(n) * c * h * w), kRedThreads, 0, static_cast<cudaStream_t>(stream), a, b, n, c, h, w, grad_scale, tanh_bwd, scalars, slot_loss, slot_aux, dp, reinterpret_cast<RedWs*>(workspace)));
   return DTG_OK;
 }
 
 extern "C" int dtg_grad_sumsq(const float* g, size_t count, float grad_scale, float* out_sumsq, void* workspace, void* stream) {
   DTG_REQUIRE(g && out_sumsq && workspace, "dtg_grad_sumsq: null argument");
   DTG_REQUIRE((reinterpret_cast<uintptr_t>(g) & 15) == 0, "dtg_grad_sumsq: arena must be 16-byte aligned");
-  sumsq_kernel<<<red_blocks(count / 4), kRedThreads, 0, static_cast<cudaStream_t>(stream)>>>(g, count, grad_scale, out_sumsq,
-                                                                                              reinterpret_cast<RedWs*>(workspace));
-  DTG_LAUNCHED();
+  DTG_CHECK_CUDA(launch_k(sumsq_kernel, red_blocks(count / 4), kRedThreads, 0, static_cast<cudaStream_t>(stream), g, count, grad_scale, out_sumsq,
+                                                                                              reinterpret_cast<RedWs*>(workspace)));
   return DTG_OK;
 }
 
@@ -255,14 +255,12 @@ extern "C" int dtg_adam_clip(float* p, float* g, float* m, float* v, size_t coun
                              const int32_t* step_dev, float grad_scale, void* stream) {
   DTG_REQUIRE(p && g && m && v && hyper && sumsq && step_dev, "dtg_adam_clip: null argument");
   const int grid = static_cast<int>(std::max<size_t>(1, std::min<size_t>((count + 255) / 256, 148 * 8)));
-  adam_clip_kernel<<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(p, g, m, v, count, hyper, sumsq, step_dev, grad_scale);
-  DTG_LAUNCHED();
+  DTG_CHECK_CUDA(launch_k(adam_clip_kernel, grid, 256, 0, static_cast<cudaStream_t>(stream), p, g, m, v, count, hyper, sumsq, step_dev, grad_scale));
   return DTG_OK;
 }
 
 extern "C" int dtg_step_increment(int32_t* step_dev, void* stream) {
   DTG_REQUIRE(step_dev, "dtg_step_increment: null");
-  step_inc_kernel<<<1, 1, 0, static_cast<cudaStream_t>(stream)>>>(step_dev);
-  DTG_LAUNCHED();
+  DTG_CHECK_CUDA(launch_k(step_inc_kernel, 1, 1, 0, static_cast<cudaStream_t>(stream), step_dev));
   return DTG_OK;
 }

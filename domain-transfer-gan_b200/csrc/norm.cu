@@ -45,6 +45,7 @@ __device__ __forceinline__ void block_reduce_store(float (&s1)[V], float (&s2)[V
 template <typename T>
 __global__ void __launch_bounds__(kNormThreads) norm_stats_kernel(dtg_plane x, int cg, int splits, int use_shift,
                                                                   float* __restrict__ partial) {
+  pdl_enter();
   constexpr int V = Vec<T>::N;
   __shared__ float smem[kNormThreads * V * 2];
   const int nv = cg / V;
@@ -78,6 +79,7 @@ __global__ void __launch_bounds__(kNormThreads) norm_bwd_reduce_kernel(dtg_plane
                                                                        dtg_plane x, const float* __restrict__ stats,
                                                                        int mode, int act, int cg, int splits,
                                                                        float* __restrict__ partial) {
+  pdl_enter();
   constexpr int V = Vec<T>::N;
   __shared__ float smem[kNormThreads * V * 2];
   const int nv = cg / V;
@@ -120,6 +122,7 @@ __global__ void __launch_bounds__(kNormThreads) norm_bwd_reduce_kernel(dtg_plane
 
 // batch norm: collapse partial[s][n][c] over (s, n) -> bnsum[c][2]
 __global__ void bn_collapse_kernel(const float* __restrict__ partial, int splits, int n, int c, float* __restrict__ bnsum) {
+  pdl_enter();
   const int ch = blockIdx.x * blockDim.x + threadIdx.x;
   if (ch >= c) return;
   float a = 0.f, b = 0.f;
@@ -139,6 +142,7 @@ __global__ void norm_fwd_finalize_kernel(const float* __restrict__ partial, cons
                                          float eps, float momentum, int world, const float* __restrict__ gamma,
                                          const float* __restrict__ beta, float* __restrict__ bn_running,
                                          float* __restrict__ stats, float* __restrict__ coef) {
+  pdl_enter();
   const int idx = blockIdx.x * blockDim.x + threadIdx.x;
   if (mode == DTG_NORM_BATCH) {
     if (idx >= c) return;
@@ -191,6 +195,7 @@ __global__ void norm_fwd_finalize_kernel(const float* __restrict__ partial, cons
 template <typename T>
 __global__ void __launch_bounds__(kNormThreads) norm_apply_kernel(dtg_plane x, dtg_plane res, const float* __restrict__ coef,
                                                                   int has_coef, int act, dtg_plane out) {
+  pdl_enter();
   constexpr int V = Vec<T>::N;
   const int nvc = x.c / V;
   const size_t total = static_cast<size_t>(x.n) * x.h * x.w * nvc;
@@ -233,6 +238,7 @@ __global__ void __launch_bounds__(kNormThreads) norm_apply_kernel(dtg_plane x, d
 __global__ void norm_bwd_sums_kernel(const float* __restrict__ partial, int splits, int n, int c, int hw, int mode,
                                      const float* __restrict__ stats, const float* __restrict__ gamma,
                                      float* __restrict__ sums, float* __restrict__ kcoef) {
+  pdl_enter();
   const int idx = blockIdx.x * blockDim.x + threadIdx.x;
   if (idx >= n * c) return;
   const int ch = idx % c;
@@ -259,6 +265,7 @@ __global__ void norm_bwd_sums_kernel(const float* __restrict__ partial, int spli
 __global__ void __launch_bounds__(256) norm_bwd_channel_kernel(const float* __restrict__ sums, int n, int c, int mode,
                                                                  float* __restrict__ bnsum, float* __restrict__ d_gamma,
                                                                  float* __restrict__ d_beta) {
+  pdl_enter();
   __shared__ float2 sh[8][32];
   const int cl = threadIdx.x & 31, nl = threadIdx.x >> 5;
   const int ch = blockIdx.x * 32 + cl;
@@ -294,6 +301,7 @@ __global__ void __launch_bounds__(256) norm_bwd_channel_kernel(const float* __re
 __global__ void norm_bwd_bn_kcoef_kernel(const float* __restrict__ bnsum, int n, int c, int hw, int world,
                                          const float* __restrict__ stats, const float* __restrict__ gamma,
                                          float* __restrict__ kcoef) {
+  pdl_enter();
   const int idx = blockIdx.x * blockDim.x + threadIdx.x;
   if (idx >= n * c) return;
   const int ch = idx % c;
@@ -309,6 +317,7 @@ __global__ void __launch_bounds__(kNormThreads) norm_bwd_apply_kernel(dtg_plane 
                                                                       const float* __restrict__ stats,
                                                                       const float* __restrict__ kcoef, int mode, int act,
                                                                       dtg_plane dx, dtg_plane dres) {
+  pdl_enter();
   constexpr int V = Vec<T>::N;
   const int nvc = dx.c / V;
   const size_t total = static_cast<size_t>(dx.n) * dx.h * dx.w * nvc;
@@ -345,6 +354,7 @@ __global__ void __launch_bounds__(kNormThreads) norm_bwd_apply_kernel(dtg_plane 
 __global__ void cin_affine_fwd_kernel(const float* __restrict__ z, const float* __restrict__ ws, const float* __restrict__ bs,
                                       const float* __restrict__ wb, const float* __restrict__ bb, int n, int c, int nz,
                                       float* __restrict__ gamma, float* __restrict__ beta) {
+  pdl_enter();
   const int idx = blockIdx.x * blockDim.x + threadIdx.x;
   if (idx >= n * c) return;
   const int ch = idx % c, i = idx / c;
@@ -366,6 +376,7 @@ __global__ void __launch_bounds__(128) cin_affine_bwd_kernel(const float* __rest
                                                                int n, int c, int nz, float* __restrict__ d_ws,
                                                                float* __restrict__ d_bs, float* __restrict__ d_wb,
                                                                float* __restrict__ d_bb, float* __restrict__ d_z) {
+  pdl_enter();
   __shared__ float4 sh[8][16];
   const int l = threadIdx.x >> 4;
   for (int k0 = 0; k0 < nz; k0 += 16) {     // latent columns in groups of 16
@@ -478,32 +489,28 @@ extern "C" int dtg_norm_fwd(const dtg_norm_args* a, const dtg_plane* x, const dt
     if (a->phase == 0 || a->phase == 1) {
       dim3 grid(x->c / cg, x->n, splits);
       if (bf)
-        norm_stats_kernel<__nv_bfloat16><<<grid, kNormThreads, 0, stream>>>(*x, cg, splits, mode != DTG_NORM_BATCH, part);
+        DTG_CHECK_CUDA(launch_k(norm_stats_kernel<__nv_bfloat16>, grid, kNormThreads, 0, stream, *x, cg, splits, mode != DTG_NORM_BATCH, part));
       else
-        norm_stats_kernel<float><<<grid, kNormThreads, 0, stream>>>(*x, cg, splits, mode != DTG_NORM_BATCH, part);
-      DTG_LAUNCHED();
+        DTG_CHECK_CUDA(launch_k(norm_stats_kernel<float>, grid, kNormThreads, 0, stream, *x, cg, splits, mode != DTG_NORM_BATCH, part));
       if (mode == DTG_NORM_BATCH) {
-        bn_collapse_kernel<<<(x->c + 127) / 128, 128, 0, stream>>>(part, splits, x->n, x->c, bnsum);
-        DTG_LAUNCHED();
+        DTG_CHECK_CUDA(launch_k(bn_collapse_kernel, (x->c + 127) / 128, 128, 0, stream, part, splits, x->n, x->c, bnsum));
       }
       if (a->phase == 1) return DTG_OK;
     }
     const int world = a->world_size > 0 ? a->world_size : 1;
     const int cnt = mode == DTG_NORM_BATCH ? x->c : x->n * x->c;
-    norm_fwd_finalize_kernel<<<(cnt + 127) / 128, 128, 0, stream>>>(part, bnsum, x->ptr, x->dtype, splits, x->n, x->c, hw,
+    DTG_CHECK_CUDA(launch_k(norm_fwd_finalize_kernel, (cnt + 127) / 128, 128, 0, stream, part, bnsum, x->ptr, x->dtype, splits, x->n, x->c, hw,
                                                                    mode, a->eps, a->momentum, world, gamma, beta,
-                                                                   bn_running, stats, coef);
-    DTG_LAUNCHED();
+                                                                   bn_running, stats, coef));
   } else if (a->phase == 1) {
     return DTG_OK;
   }
   const dtg_plane res = (residual && residual->ptr) ? *residual : kNullPlane;
   const size_t total = static_cast<size_t>(x->n) * hw * (x->c / V);
   if (bf)
-    norm_apply_kernel<__nv_bfloat16><<<elemwise_grid(total), kNormThreads, 0, stream>>>(*x, res, coef, mode != DTG_NORM_NONE, a->act, *out);
+    DTG_CHECK_CUDA(launch_k(norm_apply_kernel<__nv_bfloat16>, elemwise_grid(total), kNormThreads, 0, stream, *x, res, coef, mode != DTG_NORM_NONE, a->act, *out));
   else
-    norm_apply_kernel<float><<<elemwise_grid(total), kNormThreads, 0, stream>>>(*x, res, coef, mode != DTG_NORM_NONE, a->act, *out);
-  DTG_LAUNCHED();
+    DTG_CHECK_CUDA(launch_k(norm_apply_kernel<float>, elemwise_grid(total), kNormThreads, 0, stream, *x, res, coef, mode != DTG_NORM_NONE, a->act, *out));
   return DTG_OK;
 }
 
@@ -541,8 +548,7 @@ extern "C" int dtg_norm_bwd(const dtg_norm_args* a, const dtg_plane* dy, const d
     if (rc < 0) return rc;
     if (rc == 0) {
       if (mode == DTG_NORM_INSTANCE && (d_beta || d_gamma)) {
-        norm_bwd_channel_kernel<<<(c + 31) / 32, 256, 0, stream>>>(sums_buf, n, c, mode, bnsum, d_gamma, d_beta);
-        DTG_LAUNCHED();
+        DTG_CHECK_CUDA(launch_k(norm_bwd_channel_kernel, (c + 31) / 32, 256, 0, stream, sums_buf, n, c, mode, bnsum, d_gamma, d_beta));
       }
       return DTG_OK;
     }
@@ -550,38 +556,32 @@ extern "C" int dtg_norm_bwd(const dtg_norm_args* a, const dtg_plane* dy, const d
   if ((a->phase == 0 || a->phase == 1) && need_reduce) {
     dim3 grid(c / cg, n, splits);
     if (bf)
-      norm_bwd_reduce_kernel<__nv_bfloat16><<<grid, kNormThreads, 0, stream>>>(*dy, p_dy2, p_y, p_x, stats, mode, a->act, cg, splits, part);
+      DTG_CHECK_CUDA(launch_k(norm_bwd_reduce_kernel<__nv_bfloat16>, grid, kNormThreads, 0, stream, *dy, p_dy2, p_y, p_x, stats, mode, a->act, cg, splits, part));
     else
-      norm_bwd_reduce_kernel<float><<<grid, kNormThreads, 0, stream>>>(*dy, p_dy2, p_y, p_x, stats, mode, a->act, cg, splits, part);
-    DTG_LAUNCHED();
-    norm_bwd_sums_kernel<<<(nc + 127) / 128, 128, 0, stream>>>(part, splits, n, c, hw, mode, stats, gamma, sums_buf, kcoef);
-    DTG_LAUNCHED();
+      DTG_CHECK_CUDA(launch_k(norm_bwd_reduce_kernel<float>, grid, kNormThreads, 0, stream, *dy, p_dy2, p_y, p_x, stats, mode, a->act, cg, splits, part));
+    DTG_CHECK_CUDA(launch_k(norm_bwd_sums_kernel, (nc + 127) / 128, 128, 0, stream, part, splits, n, c, hw, mode, stats, gamma, sums_buf, kcoef));
     if (mode != DTG_NORM_COND_INSTANCE && (mode == DTG_NORM_BATCH || d_beta || d_gamma)) {
-      norm_bwd_channel_kernel<<<(c + 31) / 32, 256, 0, stream>>>(sums_buf, n, c, mode, bnsum, d_gamma, d_beta);
-      DTG_LAUNCHED();
+      DTG_CHECK_CUDA(launch_k(norm_bwd_channel_kernel, (c + 31) / 32, 256, 0, stream, sums_buf, n, c, mode, bnsum, d_gamma, d_beta));
     }
   }
   if (a->phase == 1) return DTG_OK;
   if (mode == DTG_NORM_BATCH) {
     const int world = a->world_size > 0 ? a->world_size : 1;
-    norm_bwd_bn_kcoef_kernel<<<(nc + 127) / 128, 128, 0, stream>>>(bnsum, n, c, hw, world, stats, gamma, kcoef);
-    DTG_LAUNCHED();
+    DTG_CHECK_CUDA(launch_k(norm_bwd_bn_kcoef_kernel, (nc + 127) / 128, 128, 0, stream, bnsum, n, c, hw, world, stats, gamma, kcoef));
   }
   const dtg_plane p_res = (d_res && d_res->ptr) ? *d_res : kNullPlane;
   const size_t total = static_cast<size_t>(n) * hw * (c / V);
   if (bf)
-    norm_bwd_apply_kernel<__nv_bfloat16><<<elemwise_grid(total), kNormThreads, 0, stream>>>(*dy, p_dy2, p_y, p_x, stats, kcoef, mode, a->act, *dx, p_res);
+    DTG_CHECK_CUDA(launch_k(norm_bwd_apply_kernel<__nv_bfloat16>, elemwise_grid(total), kNormThreads, 0, stream, *dy, p_dy2, p_y, p_x, stats, kcoef, mode, a->act, *dx, p_res));
   else
-    norm_bwd_apply_kernel<float><<<elemwise_grid(total), kNormThreads, 0, stream>>>(*dy, p_dy2, p_y, p_x, stats, kcoef, mode, a->act, *dx, p_res);
-  DTG_LAUNCHED();
+    DTG_CHECK_CUDA(launch_k(norm_bwd_apply_kernel<float>, elemwise_grid(total), kNormThreads, 0, stream, *dy, p_dy2, p_y, p_x, stats, kcoef, mode, a->act, *dx, p_res));
   return DTG_OK;
 }
 
 extern "C" int dtg_cin_affine_fwd(const float* z, const float* ws, const float* bs, const float* wb, const float* bb,
                                   int n, int c, int nz, float* gamma, float* beta, void* stream) {
   DTG_REQUIRE(z && ws && bs && wb && bb && gamma && beta, "dtg_cin_affine_fwd: null argument");
-  cin_affine_fwd_kernel<<<(n * c + 127) / 128, 128, 0, static_cast<cudaStream_t>(stream)>>>(z, ws, bs, wb, bb, n, c, nz, gamma, beta);
-  DTG_LAUNCHED();
+  DTG_CHECK_CUDA(launch_k(cin_affine_fwd_kernel, (n * c + 127) / 128, 128, 0, static_cast<cudaStream_t>(stream), z, ws, bs, wb, bb, n, c, nz, gamma, beta));
   return DTG_OK;
 }
 
@@ -589,8 +589,7 @@ extern "C" int dtg_cin_affine_bwd(const float* z, const float* ws, const float* 
                                   const float* sums, int n, int c, int nz, float* d_ws, float* d_bs, float* d_wb,
                                   float* d_bb, float* d_z, void* stream) {
   DTG_REQUIRE(z && ws && wb && gamma && beta && sums && d_ws && d_bs && d_wb && d_bb, "dtg_cin_affine_bwd: null argument");
-  cin_affine_bwd_kernel<<<c + (d_z ? n : 0), 128, 0, static_cast<cudaStream_t>(stream)>>>(z, ws, wb, gamma, beta, sums, n, c, nz, d_ws,
-                                                                                           d_bs, d_wb, d_bb, d_z);
-  DTG_LAUNCHED();
+  DTG_CHECK_CUDA(launch_k(cin_affine_bwd_kernel, c + (d_z ? n : 0), 128, 0, static_cast<cudaStream_t>(stream), z, ws, wb, gamma, beta, sums, n, c, nz, d_ws,
+                                                                                           d_bs, d_wb, d_bb, d_z));
   return DTG_OK;
 }

@@ -70,6 +70,7 @@ __global__ void __launch_bounds__(kFT) norm_fwd_fused_kernel(dtg_plane x, dtg_pl
                                                              const float* __restrict__ gamma,
                                                              const float* __restrict__ beta, float* __restrict__ stats,
                                                              int mode, int act, float eps, int nv, int chunk) {
+  pdl_enter();
   constexpr int V = Vec<T>::N;
   __shared__ float red[kFT * V * 2];
   __shared__ float part[kSlabCh * 2];
@@ -274,6 +275,7 @@ __global__ void __launch_bounds__(kFT, 3) norm_bwd_fused_kernel(dtg_plane dy, dt
                                                                 const float* __restrict__ gamma, float* __restrict__ sums,
                                                                 dtg_plane dx, dtg_plane dres, int mode, int nv,
                                                                 int chunk) {
+  pdl_enter();
   constexpr int V = Vec<T>::N;
   __shared__ float red[kFT * V * 2];
   __shared__ float part[kSlabCh * 2];
@@ -377,6 +379,7 @@ __global__ void __launch_bounds__(kFT, 2) norm_bwd_reg_kernel(dtg_plane dy, dtg_
                                                               const float* __restrict__ gamma, float* __restrict__ sums,
                                                               dtg_plane dx, dtg_plane dres, int mode, int nv, int chunk,
                                                               int dbg) {
+  pdl_enter();
   constexpr int V = Vec<T>::N;
   __shared__ float red[kFT * V * 2];
   __shared__ float part[kSlabCh * 2];
@@ -579,13 +582,15 @@ static int launch_cluster(K kernel, dim3 grid, int cs, cudaStream_t stream, Args
   cfg.blockDim = dim3(kFT, 1, 1);
   cfg.dynamicSmemBytes = 0;
   cfg.stream = stream;
-  cudaLaunchAttribute at[1];
+  cudaLaunchAttribute at[2];
   at[0].id = cudaLaunchAttributeClusterDimension;
   at[0].val.clusterDim.x = 1;
   at[0].val.clusterDim.y = 1;
   at[0].val.clusterDim.z = cs;
+  at[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  at[1].val.programmaticStreamSerializationAllowed = 1;
   cfg.attrs = at;
-  cfg.numAttrs = 1;
+  cfg.numAttrs = pdl_enabled() ? 2 : 1;
   static const bool dbg_occ = getenv("DTG_DEBUG_OCC") != nullptr;
   if (dbg_occ) {
     int ncl = -1;

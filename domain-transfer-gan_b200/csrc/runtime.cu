@@ -1,6 +1,7 @@
 // Error plumbing, version, and the cuTensorMapEncodeTiled trampoline (resolved through
 // cudaGetDriverEntryPoint so the library has no link-time dependency on libcuda).
 #include <stdarg.h>
+#include <stdlib.h>
 
 #include <atomic>
 #include <mutex>
@@ -13,6 +14,11 @@ static thread_local char g_err[512] = "";
 static std::atomic<unsigned long long> g_launches{0};
 
 void count_launch() { g_launches.fetch_add(1, std::memory_order_relaxed); }
+
+bool pdl_enabled() {
+  static const bool on = getenv("DTG_NO_PDL") == nullptr;
+  return on;
+}
 
 void set_error(const char* fmt, ...) {
   va_list ap;

@@ -9,7 +9,7 @@
 #include "../domain-transfer-gan_b200/csrc/common.cuh"
 using namespace dtg;
 
-struct Cfg { int N, rb, layout, a_sbo, a_shift_rows, ksteps, R; };
+struct Cfg { int N, rb, layout, a_sbo, a_shift_rows, ksteps, R, M; };
 
 template <int KS, int PITCH, int RB, int SHIFT>
 __global__ void __launch_bounds__(128, 1) k(Cfg c, long long* out) {
@@ -29,7 +29,7 @@ __global__ void __launch_bounds__(128, 1) k(Cfg c, long long* out) {
   uint32_t tm = *slot;
   long long t0 = 0, t1 = 0;
   if (warp == 0) {
-    const uint32_t idesc = umma_idesc(1, 0, 0, 128, c.N);
+    const uint32_t idesc = umma_idesc(1, 0, 0, c.M, c.N);
     const uint32_t sa = smem_u32(smem), sb = smem_u32(smem + 96 * 1024);
     const uint32_t a_hi = ((uint32_t)c.a_sbo >> 4) | (1u << 14) | ((uint32_t)c.layout << 29);
     const uint32_t b_hi = ((8u * c.rb) >> 4) | (1u << 14) | ((uint32_t)c.layout << 29);
@@ -65,16 +65,16 @@ int main() {
   long long* d; cudaMalloc(&d, 148 * 8);
   const int R = 2304;
   int Ns[] = {16, 32, 64, 128, 256};
-#define RUN(NAME, KS, PITCH, RB, LAYOUT, SHIFT)                                                              \
+#define RUN(NAME, KS, PITCH, RB, LAYOUT, SHIFT, MM)                                                              \
   for (int N : Ns) {                                                                                         \
     if (9 * N * RB > 64 * 1024) continue;                                                                    \
-    Cfg c{N, RB, LAYOUT, PITCH * RB, SHIFT, KS, R};                                                          \
+    Cfg c{N, RB, LAYOUT, PITCH * RB, SHIFT, KS, R, MM};                                                      \
     k<KS, PITCH, RB, SHIFT><<<148, 128, 180 * 1024>>>(c, d);                                                 \
     cudaError_t e = cudaDeviceSynchronize();                                                                 \
     if (e != cudaSuccess) { printf("%s N=%d: CUDA error %s\n", NAME, N, cudaGetErrorString(e)); return 1; }  \
     long long h[148]; cudaMemcpy(h, d, sizeof(h), cudaMemcpyDeviceToHost);                                   \
     long long mx = 0; for (int i = 0; i < 148; ++i) mx = h[i] > mx ? h[i] : mx;                              \
-    printf("%s N=%3d: %.1f clk/MMA (floor %d)\n", NAME, N, (double)mx / (R / (9 * KS) * 9 * KS), N / 2 > 8 ? N / 2 : 8); \
+    printf("%s M=%3d N=%3d: %.1f clk/MMA (floor %d)\n", NAME, MM, N, (double)mx / (R / (9 * KS) * 9 * KS), N / 2 > 8 ? N / 2 : 8); \
   }
   cudaFuncSetAttribute(k<4, 8, 128, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
   cudaFuncSetAttribute(k<1, 8, 128, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
@@ -84,13 +84,14 @@ int main() {
   cudaFuncSetAttribute(k<2, 10, 64, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
   cudaFuncSetAttribute(k<1, 8, 32, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
   cudaFuncSetAttribute(k<1, 14, 32, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
-  RUN("sw128 aligned  ks4", 4, 8, 128, 2, 0)
-  RUN("sw128 aligned  ks1", 1, 8, 128, 2, 0)
-  RUN("sw128 patch10  ks4", 4, 10, 128, 2, 1)
-  RUN("sw128 patch10  ks1", 1, 10, 128, 2, 1)
-  RUN("sw64  aligned  ks2", 2, 8, 64, 4, 0)
-  RUN("sw64  patch10  ks2", 2, 10, 64, 4, 1)
-  RUN("sw32  aligned  ks1", 1, 8, 32, 6, 0)
-  RUN("sw32  patch14  ks1", 1, 14, 32, 6, 3)
+  RUN("sw128 aligned  ks4", 4, 8, 128, 2, 0, 64)
+  RUN("sw128 aligned  ks4", 4, 8, 128, 2, 0, 128)
+  RUN("sw128 aligned  ks1", 1, 8, 128, 2, 0, 128)
+  RUN("sw128 patch10  ks4", 4, 10, 128, 2, 1, 128)
+  RUN("sw128 patch10  ks1", 1, 10, 128, 2, 1, 128)
+  RUN("sw64  aligned  ks2", 2, 8, 64, 4, 0, 128)
+  RUN("sw64  patch10  ks2", 2, 10, 64, 4, 1, 128)
+  RUN("sw32  aligned  ks1", 1, 8, 32, 6, 0, 128)
+  RUN("sw32  patch14  ks1", 1, 14, 32, 6, 3, 128)
   return 0;
 }
