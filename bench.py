@@ -12,8 +12,10 @@ JSON line keys: see the task contract; in short
   value   : global images / s, CUDA-event timed over exactly K CUDA-graph replays, inputs resident in HBM
   e2e     : same through the public API with HOST (pinned) inputs: H2D of real_A/real_B/prior_z and the D2H of
             the packed loss vector inside the timed region, every step
-  roofline: tensor-core kernels (igemm fwd/dgrad + wgrad), algorithmic FLOPs / CUDA-event time per launch,
-            measured in an instrumented eager pass on the launching stream, vs MEASURED_PEAKS.json (sustained)
+  roofline: tensor-core kernels (conv fwd/dgrad = igemm_kernel + pconv_kernel, weight gradient = wgrad_kernel),
+            algorithmic FLOPs / CUDA-event time per launch, measured live in an instrumented pass on the launching
+            stream, vs MEASURED_PEAKS.json (sustained bf16); `traffic` = DRAM bytes per launch of the dominant kernel's
+            heaviest layer from the committed ncu --set full capture (profiles/), null if absent
   cpu_baseline: oracle port (restatement of the reference's train_instance, torch CPU fp32) on the host cores
 """
 import argparse
@@ -84,6 +86,17 @@ class ClockSampler(threading.Thread):
             out["sm_mhz"] = sm[len(sm) // 2]
         out["reasons"] = sorted(reasons)
         return out
+
+
+def _ncu_traffic():
+    """DRAM bytes per launch (dram__bytes_read.sum + dram__bytes_write.sum) of the residual-stack conv, from the committed
+    ncu --set full summary; None when the profile is not in the tree."""
+    try:
+        d = json.load(open(os.path.join(ROOT, "profiles", "r1_ncu_summary.json")))
+        k = d["igemm_kernel_res_conv"]
+        return k["dram_bytes_read"] + k["dram_bytes_write"]
+    except Exception:
+        return None
 
 
 def run_reference(args):
@@ -308,8 +321,9 @@ def main():
         tot_fl = sum(v["flops"] for v in summ.values())
         dom = max(summ, key=lambda k: summ[k]["ms"])
         ach = summ[dom]["flops"] / (summ[dom]["ms"] * 1e-3) / 1e12
-        line["roofline"] = {"bound": "tensor", "kernel": dom, "achieved": ach, "peak": peak, "unit": "TFLOP/s",
-                            "frac": ach / peak, "traffic": None,
+        line["roofline"] = {"bound": "tensor", "kernel": dom + " (conv fwd/dgrad: igemm_kernel + pconv_kernel)" if dom == "igemm_kernel" else dom,
+                            "achieved": ach, "peak": peak, "unit": "TFLOP/s",
+                            "frac": ach / peak, "traffic": _ncu_traffic(),
                             "peak_source": "MEASURED_PEAKS.json bf16_tflops_sustained" if peaks else "fallback 1.59 PF x 0.88",
                             "per_kernel": {k: {"tflops": v["flops"] / (v["ms"] * 1e-3) / 1e12, "ms_per_step": v["ms"] / 2,
                                                "launches_per_step": v["launches"] // 2} for k, v in summ.items()},

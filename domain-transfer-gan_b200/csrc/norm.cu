@@ -543,11 +543,11 @@ extern "C" int dtg_norm_bwd(const dtg_norm_args* a, const dtg_plane* dy, const d
   const bool need_reduce = mode != DTG_NORM_NONE || d_beta != nullptr || sums != nullptr;
   float* sums_buf = sums ? sums : kcoef + static_cast<size_t>(n) * c * 4;   // scratch when the caller wants none
   const int nc = n * c;
-  if (mode == DTG_NORM_INSTANCE || mode == DTG_NORM_COND_INSTANCE) {
+  if (mode == DTG_NORM_INSTANCE || mode == DTG_NORM_COND_INSTANCE || (mode == DTG_NORM_NONE && d_beta != nullptr)) {
     const int rc = try_norm_bwd_fused(a, dy, dy2, y, &p_x, stats, gamma, sums_buf, dx, d_res, stream);
     if (rc < 0) return rc;
     if (rc == 0) {
-      if (mode == DTG_NORM_INSTANCE && (d_beta || d_gamma)) {
+      if (mode != DTG_NORM_COND_INSTANCE && (d_beta || d_gamma)) {
         DTG_CHECK_CUDA(launch_k(norm_bwd_channel_kernel, (c + 31) / 32, 256, 0, stream, sums_buf, n, c, mode, bnsum, d_gamma, d_beta));
       }
       return DTG_OK;

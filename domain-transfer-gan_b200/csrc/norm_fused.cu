@@ -407,12 +407,18 @@ __global__ void __launch_bounds__(kFT, 2) norm_bwd_reg_kernel(dtg_plane dy, dtg_
   uint8_t* drb = dres.ptr ? reinterpret_cast<uint8_t*>(dres.ptr) + (static_cast<size_t>(n) * hw * dres.c + c) * es : nullptr;
   if (dbg & 2) drb = nullptr;
 
+  // mode NONE = activation-only layer (conv bias + ReLU, modules.py:211-213): dx = g, sums = (sum g, -)
+  const bool has_norm = mode != DTG_NORM_NONE;
   float mean[V], rstd[V];
 #pragma unroll
   for (int i = 0; i < V; ++i) {
-    const float2 mr = *reinterpret_cast<const float2*>(stats + (static_cast<size_t>(n) * x.c + c + i) * 2);
-    mean[i] = mr.x;
-    rstd[i] = mr.y;
+    mean[i] = 0.f;
+    rstd[i] = 0.f;
+    if (has_norm) {
+      const float2 mr = *reinterpret_cast<const float2*>(stats + (static_cast<size_t>(n) * x.c + c + i) * 2);
+      mean[i] = mr.x;
+      rstd[i] = mr.y;
+    }
   }
   float g[PPT][V], xh[PPT][V];
   // phase A: every load of this thread is issued before any arithmetic (a warp issues in order: a use-after-load
@@ -436,7 +442,7 @@ __global__ void __launch_bounds__(kFT, 2) norm_bwd_reg_kernel(dtg_plane dy, dtg_
       r_dy[j] = *reinterpret_cast<const uint4*>(dyb + static_cast<size_t>(o0) * pitch);
       if (dy2b) r_d2[j] = *reinterpret_cast<const uint4*>(dy2b + static_cast<size_t>(p) * pitch);
       if (ACT != DTG_ACT_NONE) r_y[j] = *reinterpret_cast<const uint4*>(yb + static_cast<size_t>(o1) * pitch);
-      r_x[j] = *reinterpret_cast<const uint4*>(xb + static_cast<size_t>(p) * pitch);
+      r_x[j] = has_norm ? *reinterpret_cast<const uint4*>(xb + static_cast<size_t>(p) * pitch) : make_uint4(0u, 0u, 0u, 0u);
       bo0[j] = o0;
       bdr[j] = (HAL && hdy == 1) ? (py == 1 ? -2 * wdy : (py == dy.h - 2 ? 2 * wdy : 0)) : 0;
       bdc[j] = (HAL && hdy == 1) ? (px == 1 ? -2 : (px == dy.w - 2 ? 2 : 0)) : 0;
@@ -507,8 +513,12 @@ __global__ void __launch_bounds__(kFT, 2) norm_bwd_reg_kernel(dtg_plane dy, dtg_
     const size_t nc = static_cast<size_t>(n) * x.c + ch;
     const float m = static_cast<float>(hw);
     const float d = mode == DTG_NORM_COND_INSTANCE ? m - 1.f : m;
-    const float ga = mode == DTG_NORM_COND_INSTANCE ? gamma[nc] : gamma[ch];
-    kco[t] = make_float4(stats[nc * 2 + 1] * ga, A / m, B / d, 0.f);
+    if (has_norm) {
+      const float ga = mode == DTG_NORM_COND_INSTANCE ? gamma[nc] : gamma[ch];
+      kco[t] = make_float4(stats[nc * 2 + 1] * ga, A / m, B / d, 0.f);
+    } else {
+      kco[t] = make_float4(1.f, 0.f, 0.f, 0.f);
+    }
     if (rank == 0) {
       sums[nc * 2] = A;
       sums[nc * 2 + 1] = B;
@@ -620,9 +630,10 @@ int try_norm_fwd_fused(const dtg_norm_args* a, const dtg_plane* x, const dtg_pla
 int try_norm_bwd_fused(const dtg_norm_args* a, const dtg_plane* dy, const dtg_plane* dy2, const dtg_plane* y,
                        const dtg_plane* x, const float* stats, const float* gamma, float* sums, const dtg_plane* dx,
                        const dtg_plane* d_res, cudaStream_t stream) {
-  if (a->phase != 0 || (a->mode != DTG_NORM_INSTANCE && a->mode != DTG_NORM_COND_INSTANCE)) return 1;
+  if (a->phase != 0 || a->mode == DTG_NORM_BATCH) return 1;
   FusedGeom g;
   if (!fused_geom(x, &g)) return 1;
+  if (a->mode == DTG_NORM_NONE && g.reg_cs == 0) return 1;     // activation-only: register-resident kernel only
   const dtg_plane p_dy2 = (dy2 && dy2->ptr) ? *dy2 : kNull;
   const dtg_plane p_y = (y && y->ptr) ? *y : kNull;
   const dtg_plane p_res = (d_res && d_res->ptr) ? *d_res : kNull;
@@ -637,6 +648,7 @@ int try_norm_bwd_fused(const dtg_norm_args* a, const dtg_plane* dy, const dtg_pl
   const bool reg_ok = dy->halo == 0 || (dy->halo == 1 && dy->h >= 4 && dy->w >= 4);
 #define DTG_BWD_LAUNCH(TT, AA)                                                                                          \
   do {                                                                                                                  \
+    if (a->mode == DTG_NORM_NONE && !(g.reg_cs > 0 && !no_reg && reg_ok)) return 1;                                     \
     if (g.reg_cs > 0 && !no_reg && reg_ok) {                                                                            \
       if (hal)                                                                                                          \
         return launch_cluster(norm_bwd_reg_kernel<TT, AA, true, kRegPPT>, rgrid, g.reg_cs, stream, *dy, p_dy2, p_y, *x,   \
