@@ -18,8 +18,9 @@
 namespace dtg {
 
 constexpr int kWMaxTaps = 64;
-constexpr int kKP = 64;                 // pixels (K rows) per stage
-constexpr int kBlkBytes = kKP * 128;    // one 128-byte-wide channel block of a tile: 8 KB
+constexpr int kKP = 64;                 // pixels (K rows) per stage (patch mode may use 128: WgradParams::kp)
+constexpr int kBlkBytes = kKP * 128;    // one 128-byte-wide channel block of a 64-pixel tile: 8 KB
+constexpr int kOffTab = 128;            // patch-mode window-offset table entries (taps per group x k-steps)
 constexpr int kWThreads = 192;
 
 struct WgradParams {
@@ -43,7 +44,11 @@ struct WgradParams {
   int rows_per_group;
   int q_blk_bytes;            // pw * ph * 128
   int stage_bytes;
-  unsigned short b_off[kWMaxTaps];   // [local tap][k-step] window start inside the patch, 16-byte units
+  unsigned short b_off[kOffTab];     // [local tap][k-step] window start inside the patch, 16-byte units
+  int kp;                            // pixels per stage (64 or 128)
+  int blk_bytes;                     // kp * 128: one channel block of the p tile
+  int a_load_blocks;                 // p channel blocks actually loaded; the others read a shared all-zero block
+  int zero_off;                      // byte offset of the zero block from the smem base
   float* ws;
 };
 
@@ -57,7 +62,7 @@ __global__ void __launch_bounds__(kWThreads, 1) wgrad_kernel(const __grid_consta
   const int split = blockIdx.x, group = blockIdx.y, mblock = blockIdx.z;
   const int tap0 = group * p.tpg;
   const int ntl = min(p.tpg, p.ntaps - tap0);
-  const int a_bytes = p.nblkA * kBlkBytes;
+  const int a_bytes = p.a_load_blocks * p.blk_bytes;
   const int stage_bytes = p.stage_bytes;
   const int S = p.stages;
   uint64_t* bar_full = reinterpret_cast<uint64_t*>(smem + S * stage_bytes);
@@ -91,8 +96,14 @@ __global__ void __launch_bounds__(kWThreads, 1) wgrad_kernel(const __grid_consta
   const int T = p.tiles_w * p.tiles_h * p.tiles_n;
   const int t_begin = split * p.tiles_per_split;
   const int t_end = min(T, t_begin + p.tiles_per_split);
-  const uint32_t tx_bytes = p.patch ? static_cast<uint32_t>(p.nblkA * kBlkBytes + p.nblkB * p.q_blk_bytes)
-                                    : static_cast<uint32_t>((p.nblkA + ntl * p.nblkB) * kBlkBytes);
+  const uint32_t tx_bytes = p.patch ? static_cast<uint32_t>(a_bytes + p.nblkB * p.q_blk_bytes)
+                                    : static_cast<uint32_t>(a_bytes + ntl * p.nblkB * p.blk_bytes);
+  if (p.a_load_blocks < p.nblkA) {     // all-zero p block for the channel blocks that hold no data (pa <= 64)
+    for (int i = threadIdx.x * 16; i < p.blk_bytes; i += kWThreads * 16)
+      *reinterpret_cast<uint4*>(smem + p.zero_off + i) = make_uint4(0u, 0u, 0u, 0u);
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    __syncthreads();
+  }
 
   if (warp == 0) {
     {   // warp-uniform loop; only the TMA / mbarrier instructions are predicated on elect.sync
@@ -109,8 +120,8 @@ __global__ void __launch_bounds__(kWThreads, 1) wgrad_kernel(const __grid_consta
         uint8_t* s = smem + stage * stage_bytes;
         if (elect_one()) mbar_expect_tx(&bar_full[stage], tx_bytes);
         __syncwarp();
-        for (int blk = 0; blk < p.nblkA; ++blk)
-          if (elect_one()) tma_load_4d(s + blk * kBlkBytes, &p.tmP, &bar_full[stage], mblock * 128 + blk * CH, b0, a0, n0);
+        for (int blk = 0; blk < p.a_load_blocks; ++blk)
+          if (elect_one()) tma_load_4d(s + blk * p.blk_bytes, &p.tmP, &bar_full[stage], mblock * 128 + blk * CH, b0, a0, n0);
         if (p.patch) {
           for (int blk = 0; blk < p.nblkB; ++blk)
             if (elect_one())
@@ -121,7 +132,7 @@ __global__ void __launch_bounds__(kWThreads, 1) wgrad_kernel(const __grid_consta
             const int t = tap0 + tl;
             for (int blk = 0; blk < p.nblkB; ++blk)
               if (elect_one())
-                tma_load_4d(s + a_bytes + (tl * p.nblkB + blk) * kBlkBytes, &p.tmQ[p.tap_map[t]], &bar_full[stage],
+                tma_load_4d(s + a_bytes + (tl * p.nblkB + blk) * p.blk_bytes, &p.tmQ[p.tap_map[t]], &bar_full[stage],
                             blk * CH, b0 + p.tap_dw[t], a0 + p.tap_dh[t], n0);
           }
         }
@@ -141,26 +152,29 @@ __global__ void __launch_bounds__(kWThreads, 1) wgrad_kernel(const __grid_consta
       tc_fence_after();
       {
         const uint32_t sa = smem_u32(smem + stage * stage_bytes);
-        const uint64_t ad0 = umma_desc_sw128(sa, kBlkBytes, TF32 ? 512 : 1024, TF32 ? 1 : 2);
+        // second p channel block: either loaded right behind the first or the shared zero block (LBO reaches it)
+        const uint32_t a_lbo = p.a_load_blocks < p.nblkA ? smem_u32(smem + p.zero_off) - sa : static_cast<uint32_t>(p.blk_bytes);
+        const uint64_t ad0 = umma_desc_sw128(sa, a_lbo, TF32 ? 512 : 1024, TF32 ? 1 : 2);
+        const int nk = p.kp / UK;
         if (p.patch) {
           const uint64_t bq0 = umma_desc_sw128(sa + a_bytes, p.q_blk_bytes, TF32 ? 512 : 1024, TF32 ? 1 : 2);
           if (elect_one()) {
             const uint32_t acc = tile > t_begin ? 1u : 0u;
             for (int tl = 0; tl < ntl; ++tl) {
               const uint32_t d = tmem_base + tl * p.n_umma;
-#pragma unroll
-              for (int j = 0; j < kKP / UK; ++j)
-                tc_mma<TF32>(d, ad0 + j * (UK * 128 / 16), bq0 + p.b_off[tl * (kKP / UK) + j], idesc, j > 0 ? 1u : acc);
+#pragma unroll 4
+              for (int j = 0; j < nk; ++j)
+                tc_mma<TF32>(d, ad0 + j * (UK * 128 / 16), bq0 + p.b_off[tl * nk + j], idesc, j > 0 ? 1u : acc);
             }
           }
         } else {
           for (int tl = 0; tl < ntl; ++tl) {
-            const uint32_t sb = sa + a_bytes + tl * p.nblkB * kBlkBytes;
-            const uint64_t bd0 = umma_desc_sw128(sb, kBlkBytes, TF32 ? 512 : 1024, TF32 ? 1 : 2);
+            const uint32_t sb = sa + a_bytes + tl * p.nblkB * p.blk_bytes;
+            const uint64_t bd0 = umma_desc_sw128(sb, p.blk_bytes, TF32 ? 512 : 1024, TF32 ? 1 : 2);
             const uint32_t d = tmem_base + tl * p.n_umma;
             if (elect_one()) {
-#pragma unroll
-              for (int j = 0; j < kKP / UK; ++j)
+#pragma unroll 4
+              for (int j = 0; j < nk; ++j)
                 tc_mma<TF32>(d, ad0 + j * (UK * 128 / 16), bd0 + j * (UK * 128 / 16), idesc, (tile > t_begin || j > 0) ? 1u : 0u);
             }
           }
@@ -278,7 +292,7 @@ __global__ void __launch_bounds__(256) wgrad_reduce_kernel(const float* __restri
 struct WgradPlan {
   int bw, bh, bn, tiles_w, tiles_h, tiles_n, T;
   int ntaps, tpg, ngroups, mblocks, nblkA, nblkB, n_umma, stages, tmem_cols, splits, tiles_per_split;
-  int patch, pw, ph, rows_per_group, stage_bytes;
+  int patch, pw, ph, rows_per_group, stage_bytes, kp, a_load_blocks;
   size_t ws_bytes;
 };
 
@@ -315,54 +329,62 @@ static int make_plan(const dtg_wgrad_args* a, const dtg_plane* pp, const dtg_pla
   pl->ntaps = fold ? a->kh : a->kh * a->kw;
   const int pa_eff = fold == 2 ? CH : a->pa;     // folded operand: 8 kw slots x 16 bytes = one 128-byte channel block
   const int qb_eff = fold == 1 ? CH : a->qb;
+  pl->kp = kKP;
   pl->bw = std::min(pow2ceil(pp->w), kKP);
   pl->bh = std::min(pow2ceil(pp->h), kKP / pl->bw);
   pl->bn = kKP / (pl->bw * pl->bh);
-  pl->tiles_w = (pp->w + pl->bw - 1) / pl->bw;
-  pl->tiles_h = (pp->h + pl->bh - 1) / pl->bh;
-  pl->tiles_n = (pp->n + pl->bn - 1) / pl->bn;
-  pl->T = pl->tiles_w * pl->tiles_h * pl->tiles_n;
   pl->mblocks = (pa_eff + 127) / 128;
   pl->nblkA = 128 / CH;
+  // p channel blocks that hold data in the LAST (or only) M block; with one M block and <= 64 channels the second
+  // block is never loaded: the A descriptor's LBO points at a shared all-zero block instead
+  pl->a_load_blocks = (pl->nblkA == 2 && pl->mblocks == 1 && pa_eff <= CH) ? 1 : pl->nblkA;
   pl->n_umma = (qb_eff + CH - 1) / CH * CH;
   DTG_REQUIRE(pl->n_umma <= 256, "wgrad: q channels %d > 256", a->qb);
   pl->nblkB = pl->n_umma / CH;
   const int tmem_max = 512 / pl->n_umma;
-  const int smem_max = (100 * 1024 - pl->nblkA * kBlkBytes) / (pl->nblkB * kBlkBytes);
+  const int smem_max = (100 * 1024 - pl->a_load_blocks * kBlkBytes) / (pl->nblkB * kBlkBytes);
   const int tpg_max = std::max(1, std::min(tmem_max, smem_max));
   pl->ngroups = (pl->ntaps + tpg_max - 1) / tpg_max;
   pl->tpg = (pl->ntaps + pl->ngroups - 1) / pl->ngroups;
   pl->ngroups = (pl->ntaps + pl->tpg - 1) / pl->tpg;
-  int stage_bytes = (pl->nblkA + pl->tpg * pl->nblkB) * kBlkBytes;
-  // patch mode: groups are whole filter rows (kh_eff x kw_eff taps, folded layers have kw_eff = 1)
+  int stage_bytes = (pl->a_load_blocks + pl->tpg * pl->nblkB) * kBlkBytes;
+  // patch mode: groups are whole filter rows (kh_eff x kw_eff taps, folded layers have kw_eff = 1); 128-pixel stages
+  // (32 x 4 tiles) when they fit, so that the haloed patch amortises over more pixels
   pl->patch = 0;
   {
     static const bool no_patch = getenv("DTG_NO_WGRAD_PATCH") != nullptr;
     const int kh_eff = a->kh, kw_eff = fold ? 1 : a->kw;
     const int UKp = tf32 ? 8 : 16;
-    if (!no_patch && a->stride == 1 && pl->bn == 1 && pl->bw >= UKp && kw_eff * pl->n_umma <= 512) {
-      int r = 0;
+    for (int kp = 128; kp >= 64 && !pl->patch && !no_patch; kp -= 64) {
+      const int bw = std::min(pow2ceil(pp->w), kp == 128 ? 32 : kKP);
+      const int bh = std::min(pow2ceil(pp->h), kp / bw);
+      if (a->stride != 1 || bw * bh != kp || bw < UKp || kw_eff * pl->n_umma > 512) continue;
       for (int cand = kh_eff; cand >= 1; --cand) {
-        if (kh_eff % cand != 0 || cand * kw_eff * pl->n_umma > 512 || cand * kw_eff * (kKP / UKp) > kWMaxTaps) continue;
-        const int sb = pl->nblkA * kBlkBytes + pl->nblkB * (pl->bw + kw_eff - 1) * (pl->bh + cand - 1) * 128;
-        if (2 * ((sb + 1023) & ~1023) > 200 * 1024) continue;
-        r = cand;
-        break;
-      }
-      if (r > 0) {
+        if (kh_eff % cand != 0 || cand * kw_eff * pl->n_umma > 512 || cand * kw_eff * (kp / UKp) > kOffTab) continue;
+        const int sb = pl->a_load_blocks * kp * 128 + pl->nblkB * (bw + kw_eff - 1) * (bh + cand - 1) * 128;
+        if ((kp == 128 ? 3 : 2) * ((sb + 1023) & ~1023) > 180 * 1024) continue;
         pl->patch = 1;
-        pl->rows_per_group = r;
-        pl->pw = pl->bw + kw_eff - 1;
-        pl->ph = pl->bh + r - 1;
-        pl->tpg = r * kw_eff;
-        pl->ngroups = kh_eff / r;
-        stage_bytes = pl->nblkA * kBlkBytes + pl->nblkB * pl->pw * pl->ph * 128;
+        pl->kp = kp;
+        pl->bw = bw;
+        pl->bh = bh;
+        pl->bn = 1;
+        pl->rows_per_group = cand;
+        pl->pw = bw + kw_eff - 1;
+        pl->ph = bh + cand - 1;
+        pl->tpg = cand * kw_eff;
+        pl->ngroups = kh_eff / cand;
+        stage_bytes = sb;
+        break;
       }
     }
   }
+  pl->tiles_w = (pp->w + pl->bw - 1) / pl->bw;
+  pl->tiles_h = (pp->h + pl->bh - 1) / pl->bh;
+  pl->tiles_n = (pp->n + pl->bn - 1) / pl->bn;
+  pl->T = pl->tiles_w * pl->tiles_h * pl->tiles_n;
   stage_bytes = (stage_bytes + 1023) & ~1023;
   pl->stage_bytes = stage_bytes;
-  pl->stages = std::max(2, std::min(6, (200 * 1024) / stage_bytes));
+  pl->stages = std::max(2, std::min(6, (180 * 1024) / stage_bytes));
   int cols = 32;
   while (cols < pl->tpg * pl->n_umma) cols <<= 1;
   pl->tmem_cols = cols;
@@ -410,6 +432,10 @@ extern "C" int dtg_conv_wgrad(const dtg_wgrad_args* a, const dtg_plane* pp, cons
   p.patch = pl.patch; p.pw = pl.pw; p.ph = pl.ph; p.rows_per_group = pl.rows_per_group;
   p.q_blk_bytes = pl.pw * pl.ph * 128;
   p.stage_bytes = pl.stage_bytes;
+  p.kp = pl.kp;
+  p.blk_bytes = pl.kp * 128;
+  p.a_load_blocks = pl.a_load_blocks;
+  p.zero_off = pl.stages * pl.stage_bytes + 1024;      // behind the stages and the barrier block
   p.ws = reinterpret_cast<float*>(workspace);
 
   const int s = a->stride, hl = q->halo;
@@ -438,7 +464,7 @@ extern "C" int dtg_conv_wgrad(const dtg_wgrad_args* a, const dtg_plane* pp, cons
     // tap (kh, kw) of group g = kh / r reads q at tile pixel + (tap_dh, tap_dw); patch origin = offsets of the group's
     // first tap; local tap order is kh-major, matching the global tap index t = kh * kw_eff + kw
     const int kw_eff = fold ? 1 : a->kw;
-    const int UKp = tf32 ? 8 : 16, nk = kKP / UKp, segs = pl.bw / UKp;
+    const int UKp = tf32 ? 8 : 16, nk = pl.kp / UKp, segs = pl.bw / UKp;
     p.q_org_h = p.tap_dh[0];
     p.q_org_w = p.tap_dw[0];
     for (int tl = 0; tl < pl.tpg; ++tl) {
@@ -500,7 +526,7 @@ extern "C" int dtg_conv_wgrad(const dtg_wgrad_args* a, const dtg_plane* pp, cons
       attr_set[tf32 ? 1 : 0] = true;
     }
   }
-  const size_t smem = static_cast<size_t>(pl.stages) * pl.stage_bytes + 1024 + 256;
+  const size_t smem = static_cast<size_t>(pl.stages) * pl.stage_bytes + 1024 + 1024 + pl.kp * 128;
   dim3 grid(pl.splits, pl.ngroups, pl.mblocks);
   if (tf32)
     DTG_CHECK_CUDA(launch_k(wgrad_kernel<true>, grid, kWThreads, smem, stream, p));
