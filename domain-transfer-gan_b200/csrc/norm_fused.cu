@@ -24,11 +24,11 @@ constexpr int kFT = 256;          // threads per CTA
 constexpr int kSlabCh = 64;       // max channels of a slab (128 B of bf16)
 
 // fixed-order block reduction of per-thread (s1[V], s2[V]) over the pixel lanes into part[ch][2]
-template <int V>
+template <int V, int NT = kFT>
 __device__ __forceinline__ void block_reduce_part(const float (&s1)[V], const float (&s2)[V], int nv, float* red,
                                                   float* part) {
   const int t = threadIdx.x;
-  const int lanes = kFT / nv;
+  const int lanes = NT / nv;
 #pragma unroll
   for (int i = 0; i < V; ++i) {
     red[(t * V + i) * 2] = s1[i];
@@ -373,21 +373,21 @@ __global__ void __launch_bounds__(kFT, 3) norm_bwd_fused_kernel(dtg_plane dy, dt
 // Register-resident variant for slabs of <= 8 * lanes * PPT pixels (the 32x32 residual-stack planes): every thread
 // issues ALL its loads up front (PPT pixels x {dy, dy2, y, x}), keeps g and xhat in registers across the cluster
 // reduction, and pass 2 is pure arithmetic + stores: one HBM read, one HBM write, one memory round trip.
-template <typename T, int ACT, bool HAL, int PPT>
-__global__ void __launch_bounds__(kFT, 2) norm_bwd_reg_kernel(dtg_plane dy, dtg_plane dy2, dtg_plane yp, dtg_plane x,
+template <typename T, int ACT, bool HAL, int PPT, int NT>
+__global__ void __launch_bounds__(NT, 512 / NT) norm_bwd_reg_kernel(dtg_plane dy, dtg_plane dy2, dtg_plane yp, dtg_plane x,
                                                               const float* __restrict__ stats,
                                                               const float* __restrict__ gamma, float* __restrict__ sums,
                                                               dtg_plane dx, dtg_plane dres, int mode, int nv, int chunk,
                                                               int dbg) {
   pdl_enter();
   constexpr int V = Vec<T>::N;
-  __shared__ float red[kFT * V * 2];
+  __shared__ float red[NT * V * 2];
   __shared__ float part[kSlabCh * 2];
   __shared__ float4 kco[kSlabCh];
   cg::cluster_group cl = cg::this_cluster();
   const int cs = cl.num_blocks(), rank = cl.block_rank();
   const int slab_ch = nv * V;
-  const int v = threadIdx.x % nv, lane = threadIdx.x / nv, lanes = kFT / nv;
+  const int v = threadIdx.x % nv, lane = threadIdx.x / nv, lanes = NT / nv;
   const int n = blockIdx.y;
   const int c = blockIdx.x * slab_ch + v * V;
   const int hw = x.h * x.w;
@@ -499,7 +499,7 @@ __global__ void __launch_bounds__(kFT, 2) norm_bwd_reg_kernel(dtg_plane dy, dtg_
       s1[i] += g[j][i];
       s2[i] += g[j][i] * xh[j][i];
     }
-  block_reduce_part<V>(s1, s2, nv, red, part);
+  block_reduce_part<V, NT>(s1, s2, nv, red, part);
   if (dbg & 1) __syncthreads(); else cl.sync();
   if (threadIdx.x < slab_ch) {
     const int t = threadIdx.x;
@@ -550,6 +550,7 @@ __global__ void __launch_bounds__(kFT, 2) norm_bwd_reg_kernel(dtg_plane dy, dtg_
 static const dtg_plane kNull = {nullptr, 0, 0, 0, 0, 0, 0};
 
 constexpr int kRegPPT = 4;     // pixels per thread of the register-resident backward
+constexpr int kRegNT = 256;    // its threads per CTA (512 x 2 pixels measured slower: 83 vs 69 us)
 
 struct FusedGeom {
   int nv, cblocks, cs, chunk;
@@ -573,7 +574,7 @@ static bool fused_geom(const dtg_plane* x, FusedGeom* g) {
   g->cs = cs;
   g->chunk = (hw + cs - 1) / cs;
   // register-resident backward: one CTA covers lanes * kRegPPT pixels, a cluster (<= 8 CTAs) covers the slab
-  const int per_cta = (kFT / g->nv) * kRegPPT;
+  const int per_cta = (kRegNT / g->nv) * kRegPPT;
   g->reg_cs = 0;
   for (int r = 1; r <= 8; r *= 2)
     if (r * per_cta >= hw) {
@@ -585,11 +586,11 @@ static bool fused_geom(const dtg_plane* x, FusedGeom* g) {
 }
 
 template <typename K, typename... Args>
-static int launch_cluster(K kernel, dim3 grid, int cs, cudaStream_t stream, Args... args) {
+static int launch_cluster_nt(K kernel, dim3 grid, int nt, int cs, cudaStream_t stream, Args... args) {
   cudaLaunchConfig_t cfg;
   memset(&cfg, 0, sizeof(cfg));
   cfg.gridDim = grid;
-  cfg.blockDim = dim3(kFT, 1, 1);
+  cfg.blockDim = dim3(nt, 1, 1);
   cfg.dynamicSmemBytes = 0;
   cfg.stream = stream;
   cudaLaunchAttribute at[2];
@@ -611,6 +612,11 @@ static int launch_cluster(K kernel, dim3 grid, int cs, cudaStream_t stream, Args
   DTG_CHECK_CUDA(cudaLaunchKernelEx(&cfg, kernel, args...));
   DTG_LAUNCHED();
   return DTG_OK;
+}
+
+template <typename K, typename... Args>
+static int launch_cluster(K kernel, dim3 grid, int cs, cudaStream_t stream, Args... args) {
+  return launch_cluster_nt(kernel, grid, kFT, cs, stream, args...);
 }
 
 int try_norm_fwd_fused(const dtg_norm_args* a, const dtg_plane* x, const dtg_plane* residual, const float* gamma,
@@ -651,9 +657,9 @@ int try_norm_bwd_fused(const dtg_norm_args* a, const dtg_plane* dy, const dtg_pl
     if (a->mode == DTG_NORM_NONE && !(g.reg_cs > 0 && !no_reg && reg_ok)) return 1;                                     \
     if (g.reg_cs > 0 && !no_reg && reg_ok) {                                                                            \
       if (hal)                                                                                                          \
-        return launch_cluster(norm_bwd_reg_kernel<TT, AA, true, kRegPPT>, rgrid, g.reg_cs, stream, *dy, p_dy2, p_y, *x,   \
+        return launch_cluster_nt(norm_bwd_reg_kernel<TT, AA, true, kRegPPT, kRegNT>, rgrid, kRegNT, g.reg_cs, stream, *dy, p_dy2, p_y, *x,   \
                               stats, gamma, sums, *dx, p_res, static_cast<int>(a->mode), g.nv, g.reg_chunk, dbgv);       \
-      return launch_cluster(norm_bwd_reg_kernel<TT, AA, false, kRegPPT>, rgrid, g.reg_cs, stream, *dy, p_dy2, p_y, *x,    \
+      return launch_cluster_nt(norm_bwd_reg_kernel<TT, AA, false, kRegPPT, kRegNT>, rgrid, kRegNT, g.reg_cs, stream, *dy, p_dy2, p_y, *x,    \
                             stats, gamma, sums, *dx, p_res, static_cast<int>(a->mode), g.nv, g.reg_chunk, dbgv);         \
     }                                                                                                                   \
     if (hal)                                                                                                            \
