@@ -198,6 +198,17 @@ def main():
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
+    verbose = os.environ.get("DTG_BENCH_VERBOSE") is not None
+
+    def say(msg):
+        if verbose:
+            sys.stderr.write("[bench rank %d %.1fs] %s\n" % (rank, time.perf_counter() - T0, msg))
+            sys.stderr.flush()
+
+    T0 = time.perf_counter()
+    if verbose:
+        import faulthandler
+        faulthandler.dump_traceback_later(int(os.environ.get("DTG_BENCH_VERBOSE") or 60), exit=True)
     local = int(os.environ.get("LOCAL_RANK", "0"))
     if not torch.cuda.is_available():
         raise SystemExit("bench.py: no CUDA device (there is no CPU fallback for the product path)")
@@ -205,6 +216,7 @@ def main():
     import torch.distributed as dist
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    say("process group up")
 
     import dtg  # noqa: F401
     from dtg_b200 import _lib, engine, model as dmodel, ops, parallel
@@ -218,9 +230,11 @@ def main():
     torch.manual_seed(1234)
     m = dmodel.AugmentedCycleGAN(opt, testing=True)
     m.prepare()
+    say("model built")
     if world > 1:
         m.dp = parallel.DataParallelPlan(sync_bn=not args.no_sync_bn)
         m.dp.broadcast_model(m)
+    say("replicas broadcast")
     a, b, z = ostep.synthetic_batch(n, seed=4321 + rank)
     host = [t.pin_memory() for t in (a, b, z)]
     dev = [t.cuda() for t in host]
@@ -251,6 +265,7 @@ def main():
         m._graph = None
         for _ in range(W):
             m.train_instance(*dev, use_graph=False, report=False)
+    say("warm-up done (graph=%s)" % graph_ok)
     # kernels per step: count one eager pass (a graph replay launches exactly the captured set)
     snap = m._snapshot()
     lc0 = _lib.lib().dtg_launch_count()
@@ -272,6 +287,7 @@ def main():
     barrier()
     ms = max_over_ranks(e0.elapsed_time(e1))
     value = world * n * K / (ms * 1e-3)
+    say("timed region 1 done: %.2f ms/step" % (ms / K))
 
     # ---- timed region 2: end to end through the public API, host inputs ------------------------------
     stage = [torch.empty_like(t) for t in dev]
@@ -303,20 +319,22 @@ def main():
             "clocks": clocks,
             "conv_roofline_frac_of_step": value / world * FLOP_PER_IMAGE / ((_peaks() or {}).get("bf16_tflops_sustained", 1418.6) * 1e12)}
 
+    # ---- roofline of the dominant (tensor-core) kernels: instrumented eager pass.  EVERY rank runs the two steps
+    # (they contain the gradient / batch-norm collectives); rank 0 reports its own timings.
+    snap = m._snapshot()
+    ops.PROFILE = ops.KernelProfile()
+    for _ in range(2):
+        m._step_device(*dev)
+    torch.cuda.synchronize()
+    summ = ops.PROFILE.summary()
+    ops.PROFILE = None
+    m._restore(snap)
+    say("instrumented pass done")
     if rank == 0:
-        # ---- roofline of the dominant (tensor-core) kernels: instrumented eager pass -------------------
         peaks = _peaks()
         peak = (peaks or {}).get("bf16_tflops_sustained", 1590.0 * 0.88)
         if args.precision == "tf32":
             peak = peak / 2.0
-        snap = m._snapshot()
-        ops.PROFILE = ops.KernelProfile()
-        for _ in range(2):
-            m._step_device(*dev)
-        torch.cuda.synchronize()
-        summ = ops.PROFILE.summary()
-        ops.PROFILE = None
-        m._restore(snap)
         tot_ms = sum(v["ms"] for v in summ.values())
         tot_fl = sum(v["flops"] for v in summ.values())
         dom = max(summ, key=lambda k: summ[k]["ms"])
@@ -337,8 +355,15 @@ def main():
             line["cpu_baseline"] = cpu_baseline()
         print(json.dumps(line))
     if world > 1:
+        # release the captured graph (it holds NCCL kernels) before tearing the communicator down; the teardown of a
+        # communicator that was used under graph capture can block for minutes, so leave without it
+        m._graph = None
+        torch.cuda.synchronize()
         dist.barrier()
-        dist.destroy_process_group()
+        say("leaving")
+        sys.stdout.flush()
+        sys.stderr.flush()
+        os._exit(0)
 
 
 if __name__ == "__main__":
