@@ -49,6 +49,7 @@ struct IgemmParams {
   short tap_dh[kMaxTaps], tap_dw[kMaxTaps];
   unsigned char tap_map[kMaxTaps], tap_w[kMaxTaps];
   int kchunks;
+  int ksteps;  // tcgen05.mma per stage (4 = full 128-byte chunk)
   int n_umma;  // = packed weight rows per tap
   int stages;
   int tmem_cols;
@@ -178,6 +179,10 @@ __device__ __forceinline__ void epilogue_tma(const EpiParams& p, uint32_t taddr,
     ++cnt;
   }
 }
+
+// Streamed-weight, two-tiles-per-item variant for 128-channel 3x3 layers (conv_patch2.cu); same return convention.
+int try_launch_pconv2(const IgemmParams& p, const dtg_plane* in, const void* w, int w_rows, int w_cols, int taps_total,
+                      cudaStream_t stream);
 
 // One warp (TMEM lane quadrant) drains its 32 accumulator rows.  Row `lane` is output pixel (n, oh, ow)
 // (valid = inside the output); taddr addresses the quadrant's lanes at the accumulator's first column.

@@ -133,7 +133,8 @@ __global__ void __launch_bounds__(kThreads, 1) igemm_kernel(const __grid_constan
           const uint64_t bd0 = umma_desc_sw128(sb, 16, 1024);
           if (elect_one()) {
 #pragma unroll
-            for (int j = 0; j < 4; ++j) tc_mma<TF32>(d_tmem, ad0 + 2 * j, bd0 + 2 * j, idesc, (k > 0 || j > 0) ? 1u : 0u);
+            for (int j = 0; j < 4; ++j)
+              if (j < p.ksteps) tc_mma<TF32>(d_tmem, ad0 + 2 * j, bd0 + 2 * j, idesc, (k > 0 || j > 0) ? 1u : 0u);
             tc_commit(&bar_empty[stage]);
           }
         }
@@ -269,6 +270,8 @@ extern "C" int dtg_conv(const dtg_conv_args* a, const dtg_plane* in, const void*
   p.n_umma = w_rows;
   p.e.n_umma = w_rows;
   p.kchunks = a->fold_w ? 1 : (std::min(w_cols, in->c) + KC - 1) / KC;
+  // 32-byte k-steps that hold data (small-channel layers fill only part of the single 128-byte chunk)
+  p.ksteps = (a->fold_w || p.kchunks > 1) ? 4 : std::max(1, (std::min(w_cols, in->c) * es + 31) / 32);
   p.e.act = a->act;
   p.e.bias = bias;
   p.e.cvalid = a->cout;
@@ -424,6 +427,8 @@ extern "C" int dtg_conv(const dtg_conv_args* a, const dtg_plane* in, const void*
                                     static_cast<cudaStream_t>(stream));
     if (rc <= 0) return rc;   // launched (0) or failed (<0); 1 = not eligible
     DTG_REQUIRE(!a->fold_w, "dtg_conv fold_w: geometry not supported by the patch kernel");
+    const int rc2 = try_launch_pconv2(p, in, w, w_rows, w_cols, a->kh * a->kw, static_cast<cudaStream_t>(stream));
+    if (rc2 <= 0) return rc2;
   }
 
   // activation tensor maps
