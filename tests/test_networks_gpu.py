@@ -190,3 +190,66 @@ def test_latent_nets(prec):
     op = ref[3]
     assert _rel(enc.conv_modules[3].running_mean, op["conv_modules.3.running_mean"]) < 2e-2
     assert _rel(enc.conv_modules[12].running_var, op["conv_modules.12.running_var"]) < 2e-2
+
+
+@pytest.mark.parametrize("prec", ["tf32", "bf16"])
+def test_inference_sweep_config5(prec):
+    """BASELINE config 5 (evaluate.py-style sweep, model.py:687-696 / 647-662): one input x 64 sampled z through
+    G_A_B (generate_multi), plus predict_enc_params (E_B on cat(real_A, real_B)); forward-only, against the oracle."""
+    import argparse
+    from dtg_b200 import model as dmodel
+    from oracle import step as ostep
+    engine.set_precision(prec)
+    opt = argparse.Namespace(**vars(ostep.default_opt()), expr_dir="/tmp", niter_decay=25)
+    m = dmodel.AugmentedCycleGAN(opt, testing=True)
+    for name, net in m._nets().items():
+        _load(net, STATE[name])
+    g = torch.Generator().manual_seed(5)
+    real_A = (torch.rand(1, 3, 64, 64, generator=g) * 2 - 1).to(DEV)
+    zs = torch.randn(64, 16, 1, 1, generator=g).to(DEV)
+    out = m.generate_multi(real_A, zs)
+    assert out.shape == (64, 3, 64, 64)
+    with torch.no_grad():
+        ref = onets.cin_resnet_generator(_oracle_params(STATE["netG_A_B"]), real_A.repeat(64, 1, 1, 1), zs)
+    assert _rel(out, ref) < OUT_TOL[prec]
+    a = (torch.rand(8, 3, 64, 64, generator=g) * 2 - 1).to(DEV)
+    b = (torch.rand(8, 3, 64, 64, generator=g) * 2 - 1).to(DEV)
+    (mu,) = m.predict_enc_params(a, b)
+    with torch.no_grad():
+        rmu, _ = onets.latent_encoder(_oracle_params(STATE["netE_B"]), torch.cat([a, b], 1))
+    assert mu.shape == (8, 16) and _rel(mu, rmu.reshape(8, -1)) < OUT_TOL[prec]
+    fake_A = m.predict_A(b)
+    with torch.no_grad():
+        rA = onets.resnet_generator(_oracle_params(STATE["netG_B_A"]), b)
+    assert _rel(fake_A, rA) < OUT_TOL[prec]
+
+
+@pytest.mark.parametrize("size", [128])
+def test_fully_convolutional_nets_at_128(size):
+    """BASELINE configs 3/4 shapes: generators and PatchGAN discriminators are fully convolutional (SURVEY section 0);
+    forward + backward at 128x128 (climate-field shaped: 3 -> 1 channels for the deterministic generator)."""
+    prec = "bf16"
+    engine.set_precision(prec)
+    g = torch.Generator().manual_seed(9)
+    sd = STATE["netG_A_B"]
+    net = networks.CINResnetGenerator(16, 3, 3, 32).to(DEV)
+    _load(net, sd)
+    x = (torch.rand(2, 3, size, size, generator=g) * 2 - 1).to(DEV).requires_grad_(True)
+    z = torch.randn(2, 16, 1, 1, generator=g).to(DEV).requires_grad_(True)
+    wgt = torch.randn(2, 3, size, size, generator=g).to(DEV)
+    y = net(x, z)
+    (y * wgt).sum().backward()
+    ref = _run_oracle(onets.cin_resnet_generator, sd, [x, z], wgt)
+    low = _run_oracle(onets.cin_resnet_generator, sd, [x, z], wgt, prec)
+    _compare("netG_A_B", prec, net, [y], [x.grad, z.grad], ref, low)
+    sd = STATE["netD_B"]
+    d = networks.Discriminator(3, 64, norm_layer=networks.get_norm_layer("instance")).to(DEV)
+    _load(d, sd)
+    xd = (torch.rand(2, 3, size, size, generator=g) * 2 - 1).to(DEV).requires_grad_(True)
+    yd = d(xd)
+    assert yd.shape == (2, 1, size // 4 - 3, size // 4 - 3)
+    wd = torch.randn(*yd.shape, generator=g).to(DEV)
+    (yd * wd).sum().backward()
+    refd = _run_oracle(onets.discriminator, sd, [xd], wd)
+    lowd = _run_oracle(onets.discriminator, sd, [xd], wd, prec)
+    _compare("netD_B", prec, d, [yd], [xd.grad], refd, lowd)
