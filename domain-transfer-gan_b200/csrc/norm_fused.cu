@@ -23,10 +23,15 @@ namespace dtg {
 constexpr int kFT = 256;          // threads per CTA
 constexpr int kSlabCh = 64;       // max channels of a slab (128 B of bf16)
 
-// fixed-order block reduction of per-thread (s1[V], s2[V]) over the pixel lanes into part[ch][2]
+constexpr int kMaxCluster = 8;
+
+// Fixed-order block reduction of per-thread (s1[V], s2[V]) over the pixel lanes, then PUSH: the per-channel pair
+// is stored into slot `rank` of every cluster peer's allpart[] through distributed shared memory.  After ONE
+// cluster barrier every CTA owns all partials locally and sums them in rank order (deterministic); nobody reads
+// remote shared memory afterwards, so CTAs may exit independently.
 template <int V, int NT = kFT>
-__device__ __forceinline__ void block_reduce_part(const float (&s1)[V], const float (&s2)[V], int nv, float* red,
-                                                  float* part) {
+__device__ __forceinline__ void block_reduce_push(const float (&s1)[V], const float (&s2)[V], int nv, float* red,
+                                                  float (*allpart)[kSlabCh * 2], cg::cluster_group& cl, int cs, int rank) {
   const int t = threadIdx.x;
   const int lanes = NT / nv;
 #pragma unroll
@@ -38,14 +43,26 @@ __device__ __forceinline__ void block_reduce_part(const float (&s1)[V], const fl
   if (t < nv * V) {
     const int v = t / V, i = t % V;
     float a = 0.f, b = 0.f;
+#pragma unroll 8
     for (int l = 0; l < lanes; ++l) {
       const int src = l * nv + v;
-      a += red[(src * V + i) * 2];
-      b += red[(src * V + i) * 2 + 1];
+      const float2 x = *reinterpret_cast<const float2*>(red + (src * V + i) * 2);
+      a += x.x;
+      b += x.y;
     }
-    part[t * 2] = a;
-    part[t * 2 + 1] = b;
+    float2* mine = reinterpret_cast<float2*>(&allpart[rank][t * 2]);
+    for (int r = 0; r < cs; ++r) *cl.map_shared_rank(mine, r) = make_float2(a, b);
   }
+}
+
+// sum of the cluster's partials for channel t (call after the cluster barrier)
+__device__ __forceinline__ float2 cluster_total(float (*allpart)[kSlabCh * 2], int cs, int t) {
+  float a = 0.f, b = 0.f;
+  for (int r = 0; r < cs; ++r) {
+    a += allpart[r][t * 2];
+    b += allpart[r][t * 2 + 1];
+  }
+  return make_float2(a, b);
 }
 
 struct PixIter {
@@ -73,7 +90,7 @@ __global__ void __launch_bounds__(kFT) norm_fwd_fused_kernel(dtg_plane x, dtg_pl
   pdl_enter();
   constexpr int V = Vec<T>::N;
   __shared__ float red[kFT * V * 2];
-  __shared__ float part[kSlabCh * 2];
+  __shared__ float allpart[kMaxCluster][kSlabCh * 2];
   __shared__ float2 coef[kSlabCh];
   cg::cluster_group cl = cg::this_cluster();
   const int cs = cl.num_blocks(), rank = cl.block_rank();
@@ -102,16 +119,12 @@ __global__ void __launch_bounds__(kFT) norm_fwd_fused_kernel(dtg_plane x, dtg_pl
       s2[i] += d * d;
     }
   }
-  block_reduce_part<V>(s1, s2, nv, red, part);
+  block_reduce_push<V>(s1, s2, nv, red, allpart, cl, cs, rank);
   cl.sync();
   if (threadIdx.x < slab_ch) {
     const int t = threadIdx.x;
-    float a1 = 0.f, a2 = 0.f;
-    for (int r = 0; r < cs; ++r) {
-      const float* rp = cl.map_shared_rank(part, r);
-      a1 += rp[t * 2];
-      a2 += rp[t * 2 + 1];
-    }
+    const float2 tot = cluster_total(allpart, cs, t);
+    const float a1 = tot.x, a2 = tot.y;
     const int ch = blockIdx.x * slab_ch + t;
     const size_t first = static_cast<size_t>(n) * hw * x.c + ch;
     float Kc;
@@ -135,7 +148,7 @@ __global__ void __launch_bounds__(kFT) norm_fwd_fused_kernel(dtg_plane x, dtg_pl
       stats[nc * 2 + 1] = rstd;
     }
   }
-  cl.sync();    // peers have finished reading this CTA's partials; coef[] is visible block-wide
+  __syncthreads();    // coef[] is visible block-wide
 
   // ---- pass 2: y = act(x*a + b (+ residual)), mirrored into the output halo
   float ca[V], cb[V];
@@ -278,7 +291,7 @@ __global__ void __launch_bounds__(kFT, 3) norm_bwd_fused_kernel(dtg_plane dy, dt
   pdl_enter();
   constexpr int V = Vec<T>::N;
   __shared__ float red[kFT * V * 2];
-  __shared__ float part[kSlabCh * 2];
+  __shared__ float allpart[kMaxCluster][kSlabCh * 2];
   __shared__ float4 kco[kSlabCh];
   cg::cluster_group cl = cg::this_cluster();
   const int cs = cl.num_blocks(), rank = cl.block_rank();
@@ -325,16 +338,12 @@ __global__ void __launch_bounds__(kFT, 3) norm_bwd_fused_kernel(dtg_plane dy, dt
       s2[i] += g[i] * (f[i] - mean[i]) * rstd[i];
     }
   }
-  block_reduce_part<V>(s1, s2, nv, red, part);
+  block_reduce_push<V>(s1, s2, nv, red, allpart, cl, cs, rank);
   cl.sync();
   if (threadIdx.x < slab_ch) {
     const int t = threadIdx.x;
-    float A = 0.f, B = 0.f;
-    for (int r = 0; r < cs; ++r) {
-      const float* rp = cl.map_shared_rank(part, r);
-      A += rp[t * 2];
-      B += rp[t * 2 + 1];
-    }
+    const float2 tot = cluster_total(allpart, cs, t);
+    const float A = tot.x, B = tot.y;
     const int ch = blockIdx.x * slab_ch + t;
     const size_t nc = static_cast<size_t>(n) * x.c + ch;
     const float m = static_cast<float>(hw);
@@ -346,7 +355,7 @@ __global__ void __launch_bounds__(kFT, 3) norm_bwd_fused_kernel(dtg_plane dy, dt
       sums[nc * 2 + 1] = B;
     }
   }
-  cl.sync();
+  __syncthreads();
 
   // ---- pass 2 (L2-resident re-read): dx = k0 * (g - kA - xhat * kB); d_res = g
   float k0[V], kA[V], kB[V];
@@ -382,7 +391,7 @@ __global__ void __launch_bounds__(NT, 512 / NT) norm_bwd_reg_kernel(dtg_plane dy
   pdl_enter();
   constexpr int V = Vec<T>::N;
   __shared__ float red[NT * V * 2];
-  __shared__ float part[kSlabCh * 2];
+  __shared__ float allpart[kMaxCluster][kSlabCh * 2];
   __shared__ float4 kco[kSlabCh];
   cg::cluster_group cl = cg::this_cluster();
   const int cs = cl.num_blocks(), rank = cl.block_rank();
@@ -499,16 +508,12 @@ __global__ void __launch_bounds__(NT, 512 / NT) norm_bwd_reg_kernel(dtg_plane dy
       s1[i] += g[j][i];
       s2[i] += g[j][i] * xh[j][i];
     }
-  block_reduce_part<V, NT>(s1, s2, nv, red, part);
-  if (dbg & 1) __syncthreads(); else cl.sync();
+  block_reduce_push<V, NT>(s1, s2, nv, red, allpart, cl, cs, rank);
+  cl.sync();
   if (threadIdx.x < slab_ch) {
     const int t = threadIdx.x;
-    float A = 0.f, B = 0.f;
-    for (int r = 0; r < ((dbg & 1) ? 1 : cs); ++r) {
-      const float* rp = cl.map_shared_rank(part, r);
-      A += rp[t * 2];
-      B += rp[t * 2 + 1];
-    }
+    const float2 tot = cluster_total(allpart, cs, t);
+    const float A = tot.x, B = tot.y;
     const int ch = blockIdx.x * slab_ch + t;
     const size_t nc = static_cast<size_t>(n) * x.c + ch;
     const float m = static_cast<float>(hw);
@@ -524,7 +529,7 @@ __global__ void __launch_bounds__(NT, 512 / NT) norm_bwd_reg_kernel(dtg_plane dy
       sums[nc * 2 + 1] = B;
     }
   }
-  if (dbg & 1) __syncthreads(); else cl.sync();
+  __syncthreads();
   float k0[V], kA[V], kB[V];
 #pragma unroll
   for (int i = 0; i < V; ++i) {
