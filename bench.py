@@ -262,7 +262,7 @@ def main():
             raise
         sys.stderr.write("bench: CUDA-graph capture failed (%s); running eager\n" % str(e).splitlines()[0])
         graph_ok = False
-        m._graph = None
+        m._graphs = {}
         for _ in range(W):
             m.train_instance(*dev, use_graph=False, report=False)
     say("warm-up done (graph=%s)" % graph_ok)
@@ -357,7 +357,7 @@ def main():
     if world > 1:
         # release the captured graph (it holds NCCL kernels) before tearing the communicator down; the teardown of a
         # communicator that was used under graph capture can block for minutes, so leave without it
-        m._graph = None
+        m._graphs = {}
         torch.cuda.synchronize()
         dist.barrier()
         say("leaving")

@@ -8,6 +8,7 @@ There is no CPU / eager fallback: every op raises if the extension is missing.
 """
 from . import _lib, engine, model, modules, networks, ops, parallel  # noqa: F401
 from .engine import set_precision  # noqa: F401
-from .model import AugmentedCycleGAN  # noqa: F401
+from .model import AugmentedCycleGAN, StochCycleGAN  # noqa: F401
 
-__all__ = ["_lib", "ops", "engine", "modules", "networks", "model", "parallel", "set_precision", "AugmentedCycleGAN"]
+__all__ = ["_lib", "ops", "engine", "modules", "networks", "model", "parallel", "set_precision", "AugmentedCycleGAN",
+           "StochCycleGAN"]

@@ -45,13 +45,19 @@ def load():
     return ref_modules, ref_networks, ref_model
 
 
-def build_reference_model(opt, state):
-    """AugmentedCycleGAN(opt, testing=True) with `state` (oracle.nets.init_model_state layout) loaded."""
+def build_reference_model(opt, state, stoch=False, ignore_noise=False):
+    """AugmentedCycleGAN(opt, testing=True) -- or StochCycleGAN(opt, ignore_noise, testing=True) when
+    `stoch` -- with `state` (oracle.nets.init_model_state layout) loaded."""
     _, _, M = load()
     with warnings.catch_warnings():
         warnings.simplefilter("ignore")
-        model = M.AugmentedCycleGAN(opt, testing=True)
+        if stoch:
+            model = M.StochCycleGAN(opt, ignore_noise=ignore_noise, testing=True)
+        else:
+            model = M.AugmentedCycleGAN(opt, testing=True)
     for name, sd in state.items():
+        if not hasattr(model, name):        # StochCycleGAN has no netE_B / netD_z_B
+            continue
         net = getattr(model, name)
         full = net.state_dict()
         new = {}

@@ -1,4 +1,6 @@
-"""Oracle restatement of ``AugmentedCycleGAN.train_instance`` (model.py:402-539).
+"""Oracle restatement of ``AugmentedCycleGAN.train_instance`` (model.py:402-539),
+``AugmentedCycleGAN.supervised_train_instance`` (model.py:541-604) and
+``StochCycleGAN.train_instance`` (model.py:126-208).
 
 Test infrastructure only.  ``OracleModel`` holds the six parameter dicts (reference
 state_dict keys), per-parameter Adam state, and executes the step with torch autograd on
@@ -19,7 +21,7 @@ def default_opt(**kw):
     """Hot-path defaults of options.py:22-83."""
     o = dict(input_nc=3, output_nc=3, ngf=32, nef=32, ndf=64, nlatent=16, lr=2e-4, beta1=0.5,
              max_gnorm=500.0, stoch_enc=False, z_gan=1, enc_A_B=1, lambda_A=1.0, lambda_B=1.0,
-             lambda_z_B=0.025, monitor_gnorm=True, no_lsgan=False, use_dropout=False,
+             lambda_z_B=0.025, lambda_sup_A=0.1, lambda_sup_B=0.1, monitor_gnorm=True, no_lsgan=False, use_dropout=False,
              norm="instance", which_model_netG="resnet", which_model_netD="basic", gpu_ids=[])
     o.update(kw)
     return SimpleNamespace(**o)
@@ -177,12 +179,134 @@ class OracleModel:
             return losses, visuals, gnorms
         return losses, visuals
 
+    # ---- the supervised step (model.py:541-604) -----------------------------------------
+    def supervised_train_instance(self, real_A, real_B, prior_z_B):
+        o = self.opt
+        enc_in = torch.cat((real_A, real_B), 1) if o.enc_A_B else real_B          # :543-547
+        mu, logvar = self.E_B(enc_in)
+        if o.stoch_enc:
+            post_z_B = gauss_reparametrize(mu, logvar)
+        else:
+            post_z_B = mu.reshape(mu.shape[0], mu.shape[1], 1, 1)                 # :552
+            logvar = logvar * 0.0
+        lpz = lsgan(self.D_z_B(post_z_B.detach()), False)                         # :555-557
+        lqz = lsgan(self.D_z_B(prior_z_B), True)
+        loss_D_z_B = 0.5 * (lpz + lqz)
+        self._zero_grad("D_B")                                                    # :559-562
+        loss_D_z_B.backward()
+        gnorm_D_z_B = self._clip("netD_z_B")
+        self._adam("D_B")             # netD_B has no gradient here: torch skips its parameters
+        pred_B = self.G_A_B(real_A, post_z_B)                                     # :564-568
+        pred_A = self.G_B_A(real_B)
+        loss_sup_A = F.l1_loss(pred_A, real_A)
+        loss_sup_B = F.l1_loss(pred_B, real_B)
+        loss_G_z_B = lsgan(self.D_z_B(post_z_B), True)                            # :570-571
+        kld_z_B = kld_std_gauss(mu, logvar).mean(0)                               # :574
+        loss_G = loss_sup_A * o.lambda_sup_A + loss_sup_B * o.lambda_sup_B        # :577
+        if o.stoch_enc:
+            loss_G = loss_G + kld_z_B * o.lambda_z_B
+        if o.z_gan and not o.stoch_enc:
+            loss_G = loss_G + loss_G_z_B
+        self._zero_grad("G_A"); self._zero_grad("G_B")
+        loss_G.backward()
+        gn_GAB = self._clip("netG_A_B"); gn_GBA = self._clip("netG_B_A"); gn_E = self._clip("netE_B")
+        self._adam("G_A"); self._adam("G_B")
+        f = lambda t: float(t.detach())
+        return OrderedDict([("S_A", f(loss_sup_A)), ("S_B", f(loss_sup_B)), ("KLD_z_B", f(kld_z_B)),
+                            ("D_z_B", f(loss_D_z_B)), ("gnorm_G_A_B", gn_GAB), ("gnorm_G_B_A", gn_GBA),
+                            ("gnorm_E_B", gn_E), ("gnorm_D_z_B", gnorm_D_z_B)])
+
+
+class OracleStochModel(OracleModel):
+    """StochCycleGAN (model.py:75-325): the two generators and two image discriminators only; one Adam
+    for both generators (lr) and one for both discriminators (lr/5) (model.py:109-114).  Fully
+    convolutional, so it is the reference-native step at 128x128 / 256x256."""
+    GROUPS = OrderedDict([("G", ("netG_A_B", "netG_B_A")), ("D", ("netD_A", "netD_B"))])
+    NETS = ("netG_A_B", "netG_B_A", "netD_A", "netD_B")
+
+    def __init__(self, opt=None, state=None, device="cpu", dtype=torch.float32, ignore_noise=False):
+        super().__init__(opt, state, device, dtype)
+        for k in ("netE_B", "netD_z_B"):
+            self.nets.pop(k)
+        self.lr = {"G": self.opt.lr, "D": self.opt.lr / 5.0}
+        self.ignore_noise = ignore_noise
+
+    def train_instance(self, real_A, real_B, prior_z_B, hooks=None):
+        o = self.opt
+        hooks = hooks or {}
+        if self.ignore_noise:
+            prior_z_B = prior_z_B * 0.0 + 1.0                                     # model.py:128-129
+        fake_B = self.G_A_B(real_A, prior_z_B)                                    # :132
+        fake_A = self.G_B_A(real_B)                                               # :135
+        pred_fake_A = self.D_A(fake_A.detach()); lfA = lsgan(pred_fake_A, False)  # :139-152
+        pred_true_A = self.D_A(real_A); ltA = lsgan(pred_true_A, True)
+        pred_fake_B = self.D_B(fake_B.detach()); lfB = lsgan(pred_fake_B, False)
+        pred_true_B = self.D_B(real_B); ltB = lsgan(pred_true_B, True)
+        loss_D_A = 0.5 * (lfA + ltA)
+        loss_D_B = 0.5 * (lfB + ltB)
+        loss_D = loss_D_A + loss_D_B
+        self._zero_grad("D")
+        loss_D.backward()
+        gnorm_D_A = self._clip("netD_A"); gnorm_D_B = self._clip("netD_B")
+        if "after_D_backward" in hooks:
+            hooks["after_D_backward"](self)
+        self._adam("D")
+        pred_fake_A = self.D_A(fake_A); loss_G_A = lsgan(pred_fake_A, True)       # :168-172
+        pred_fake_B = self.D_B(fake_B); loss_G_B = lsgan(pred_fake_B, True)
+        rec_A = self.G_B_A(fake_B); loss_cycle_A = F.l1_loss(rec_A, real_A)       # :175-176
+        rec_B = self.G_A_B(fake_A, prior_z_B); loss_cycle_B = F.l1_loss(rec_B, real_B)   # :179-180
+        loss_cycle = loss_cycle_A * o.lambda_A + loss_cycle_B * o.lambda_B
+        loss_G = loss_G_A + loss_G_B + loss_cycle
+        self._zero_grad("G")
+        loss_G.backward()
+        gn_GAB = self._clip("netG_A_B"); gn_GBA = self._clip("netG_B_A")
+        if "after_G_backward" in hooks:
+            hooks["after_G_backward"](self)
+        self._adam("G")
+        f = lambda t: float(t.detach())
+        losses = OrderedDict([("D_A", f(loss_D_A)), ("G_A", f(loss_G_A)), ("Cyc_A", f(loss_cycle_A)),
+                              ("D_B", f(loss_D_B)), ("G_B", f(loss_G_B)), ("Cyc_B", f(loss_cycle_B)),
+                              ("P_t_A", f(pred_true_A.mean())), ("P_f_A", f(pred_fake_A.mean())),
+                              ("P_t_B", f(pred_true_B.mean())), ("P_f_B", f(pred_fake_B.mean()))])
+        visuals = OrderedDict([("real_A", real_A.detach()), ("fake_B", fake_B.detach()), ("rec_A", rec_A.detach()),
+                               ("real_B", real_B.detach()), ("fake_A", fake_A.detach()), ("rec_B", rec_B.detach())])
+        gnorms = OrderedDict([("gnorm_G_A_B", gn_GAB), ("gnorm_G_B_A", gn_GBA),
+                              ("gnorm_D_B", gnorm_D_B), ("gnorm_D_A", gnorm_D_A)])
+        if o.monitor_gnorm:
+            return losses, visuals, gnorms
+        return losses, visuals
+
+    def supervised_train_instance(self, *a, **k):
+        raise AttributeError("StochCycleGAN has no supervised_train_instance (model.py:75-325)")
+
 
 def synthetic_batch(n, size=64, seed=4321, input_nc=3, output_nc=3, nlatent=16, kind="edges2shoes"):
     """Synthetic edges2shoes-shaped data: A = sparse +-1 edge maps, B = smooth colour
-    fields, both float32 NCHW in [-1,1]; z ~ N(0,1) [N,Z,1,1]."""
+    fields, both float32 NCHW in [-1,1]; z ~ N(0,1) [N,Z,1,1].
+    kind="climate": Livneh-style gridded fields (BASELINE config 3): low-pass Gaussian random fields times a
+    fixed land mask (~45 % ocean), scaled per sample and channel to [-1,1] with masked cells -> 0, the way
+    dataloader.py:17-33 treats the NaN ocean cells of the .npz grids."""
     g = torch.Generator().manual_seed(seed)
-    if kind == "uniform":
+    if kind == "climate":
+        gm = torch.Generator().manual_seed(2718)                  # the mask is a property of the domain, not the batch
+        k1 = torch.exp(-0.5 * ((torch.arange(33) - 16.0) / 8.0) ** 2)
+        k1 = (k1 / k1.sum()).view(1, 1, 1, 33)
+
+        def smooth(t):                                            # separable 8-px Gaussian blur, reflect borders
+            c = t.shape[1]
+            t = F.conv2d(F.pad(t, (16, 16, 0, 0), mode="reflect"), k1.expand(c, 1, 1, 33), groups=c)
+            return F.conv2d(F.pad(t, (0, 0, 16, 16), mode="reflect"), k1.transpose(2, 3).expand(c, 1, 33, 1), groups=c)
+
+        lf = smooth(torch.randn(1, 1, size, size, generator=gm))
+        land = (lf > lf.flatten().kthvalue(int(0.45 * size * size)).values).float()
+
+        def fields(c):
+            f = smooth(torch.randn(n, c, size, size, generator=g))
+            lo = f.amin(dim=(2, 3), keepdim=True); hi = f.amax(dim=(2, 3), keepdim=True)
+            return ((f - lo) / (hi - lo).clamp_min(1e-12) * 2 - 1) * land
+
+        a, b = fields(input_nc), fields(output_nc)
+    elif kind == "uniform":
         a = torch.rand(n, input_nc, size, size, generator=g) * 2 - 1
         b = torch.rand(n, output_nc, size, size, generator=g) * 2 - 1
     else:

@@ -1,6 +1,6 @@
 """Generate tests/golden/*.pt from the LIVE reference (/root/reference) -- run in the build container.
 
-    python tests/golden/make_golden.py
+    python tests/golden/make_golden.py [aug|stoch]
 
 The reference ships no golden vectors, so these are produced by executing the
 unmodified reference modules (oracle.live_reference) on seeded weights / inputs that the tests can
@@ -90,5 +90,45 @@ def main():
         print(f, os.path.getsize(os.path.join(HERE, f)), "bytes")
 
 
+def main_stoch():
+    """StochCycleGAN.train_instance (model.py:126-208) on BASELINE config 3's shape (climate fields, 3 -> 1
+    channels, 128x128) and AugmentedCycleGAN.supervised_train_instance (model.py:541-604) at 64x64."""
+    warnings.simplefilter("ignore")
+    torch.set_num_threads(8)
+    n, size = 2, 128
+    opt = step.default_opt(output_nc=1)
+    state = nets.init_model_state(seed=SEED_W, perturb=PERTURB, output_nc=1)
+    ref = lr.build_reference_model(copy.deepcopy(opt), state, stoch=True)
+    a, b, z = step.synthetic_batch(n, size=size, seed=SEED_X, output_nc=1, kind="climate")
+    steps = []
+    for it in range(2):
+        losses, visuals, gnorms = ref.train_instance(a, b, z)
+        rec = dict(losses={k: float(v) for k, v in losses.items()},
+                   gnorms={k: float(v) for k, v in gnorms.items()},
+                   visuals={k: sample(v, 1025) for k, v in visuals.items()}, param_norm={})
+        for name in ("netG_A_B", "netG_B_A", "netD_A", "netD_B"):
+            for k, p in getattr(ref, name).named_parameters():
+                rec["param_norm"]["%s/%s" % (name, k)] = float(p.detach().double().norm())
+        steps.append(rec)
+    torch.save(dict(n=n, size=size, output_nc=1, kind="climate", seed_w=SEED_W, seed_x=SEED_X, perturb=PERTURB,
+                    steps=steps), os.path.join(HERE, "golden_stoch_n2.pt"))
+
+    opt = step.default_opt()
+    state = nets.init_model_state(seed=SEED_W, perturb=PERTURB)
+    ref = lr.build_reference_model(copy.deepcopy(opt), state)
+    a, b, z = step.synthetic_batch(n, seed=SEED_X)
+    sup = []
+    for it in range(2):
+        losses = ref.supervised_train_instance(a, b, z)
+        sup.append({k: float(v) for k, v in losses.items()})
+    torch.save(dict(n=n, seed_w=SEED_W, seed_x=SEED_X, perturb=PERTURB, steps=sup),
+               os.path.join(HERE, "golden_sup_n2.pt"))
+    for f in ("golden_stoch_n2.pt", "golden_sup_n2.pt"):
+        print(f, os.path.getsize(os.path.join(HERE, f)), "bytes")
+
+
 if __name__ == "__main__":
-    main()
+    if len(sys.argv) < 2 or sys.argv[1] == "aug":
+        main()
+    if len(sys.argv) < 2 or sys.argv[1] == "stoch":
+        main_stoch()

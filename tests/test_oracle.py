@@ -125,3 +125,78 @@ def test_state_dict_keys_match_reference():
         assert ours <= full
         for k in full - ours:   # only the CINResnetBlock alias keys may be missing
             assert name == "netG_A_B" and k.split(".")[1] in ("10", "11", "12"), (name, k)
+
+
+@pytest.mark.skipif(not lr.available(), reason="/root/reference not present (GPU box)")
+@pytest.mark.parametrize("ignore_noise", [False, True])
+def test_oracle_stoch_matches_live_reference_step(ignore_noise):
+    """StochCycleGAN.train_instance (model.py:126-208) at 64x64 with the climate channel counts (3 -> 1)."""
+    warnings.simplefilter("ignore")
+    opt = step.default_opt(output_nc=1)
+    state = nets.init_model_state(seed=17, perturb=0.03, output_nc=1)
+    ref = lr.build_reference_model(copy.deepcopy(opt), state, stoch=True, ignore_noise=ignore_noise)
+    om = step.OracleStochModel(opt, state, ignore_noise=ignore_noise)
+    a, b, z = step.synthetic_batch(2, seed=5, output_nc=1, kind="climate")
+    for it in range(2):
+        lo, vo, go = om.train_instance(a, b, z)
+        lr_, vr, gr = ref.train_instance(a, b, z)
+        tol = 2e-5 if it == 0 else 2e-3
+        assert list(lo.keys()) == list(lr_.keys()) and list(go.keys()) == list(gr.keys())
+        for k in lo:
+            assert abs(lo[k] - float(lr_[k])) < tol * max(1.0, abs(lo[k])), (it, k)
+        for k in vo:
+            assert (vo[k] - vr[k]).abs().max() < (1e-4 if it == 0 else 1e-2), (it, k)
+        for k in go:
+            assert abs(go[k] - float(gr[k])) < max(tol, 1e-4) * max(1.0, abs(go[k])), (it, k)
+
+
+@pytest.mark.skipif(not lr.available(), reason="/root/reference not present (GPU box)")
+def test_oracle_supervised_matches_live_reference_step():
+    """AugmentedCycleGAN.supervised_train_instance (model.py:541-604)."""
+    warnings.simplefilter("ignore")
+    opt = step.default_opt()
+    state = nets.init_model_state(seed=23, perturb=0.03)
+    ref = lr.build_reference_model(copy.deepcopy(opt), state)
+    om = step.OracleModel(opt, state)
+    a, b, z = step.synthetic_batch(3, seed=31)
+    for it in range(2):
+        lo = om.supervised_train_instance(a, b, z)
+        lr_ = ref.supervised_train_instance(a, b, z)
+        assert list(lo.keys()) == list(lr_.keys())
+        tol = 2e-5 if it == 0 else 5e-3
+        for k in lo:
+            assert abs(lo[k] - float(lr_[k])) < tol * max(1.0, abs(lo[k])), (it, k, lo[k], float(lr_[k]))
+    for name in ("netG_A_B", "netG_B_A", "netE_B", "netD_z_B", "netD_B"):
+        rp = dict(getattr(ref, name).named_parameters())
+        for k, v in om.params(name):
+            assert float((v.detach() - rp[k].detach()).norm()) <= 2e-3 * float(v.detach().norm()) + 1e-5, (name, k)
+
+
+def test_oracle_stoch_matches_golden(golden_dir):
+    """golden_stoch_n2.pt: live reference StochCycleGAN on config 3's shape (climate fields 3 -> 1, 128x128)."""
+    g = torch.load(os.path.join(golden_dir, "golden_stoch_n2.pt"))
+    opt = step.default_opt(output_nc=g["output_nc"])
+    state = nets.init_model_state(seed=g["seed_w"], perturb=g["perturb"], output_nc=g["output_nc"])
+    a, b, z = step.synthetic_batch(g["n"], size=g["size"], seed=g["seed_x"], output_nc=g["output_nc"], kind=g["kind"])
+    om = step.OracleStochModel(opt, state)
+    for it, rec in enumerate(g["steps"]):
+        losses, visuals, gnorms = om.train_instance(a, b, z)
+        tol = 2e-5 if it == 0 else 2e-3
+        for k, v in rec["losses"].items():
+            assert abs(losses[k] - v) <= tol * max(1.0, abs(v)), (it, k, losses[k], v)
+        for k, v in rec["gnorms"].items():
+            assert abs(gnorms[k] - v) <= max(tol, 1e-4) * max(1.0, abs(v)), (it, k, gnorms[k], v)
+        for k, v in rec["visuals"].items():
+            assert _rel(_sample(visuals[k], 1025), v) < (1e-4 if it == 0 else 1e-2), (it, k)
+
+
+def test_oracle_supervised_matches_golden(golden_dir):
+    g = torch.load(os.path.join(golden_dir, "golden_sup_n2.pt"))
+    state = nets.init_model_state(seed=g["seed_w"], perturb=g["perturb"])
+    a, b, z = step.synthetic_batch(g["n"], seed=g["seed_x"])
+    om = step.OracleModel(state=state)
+    for it, rec in enumerate(g["steps"]):
+        losses = om.supervised_train_instance(a, b, z)
+        tol = 2e-5 if it == 0 else 5e-3
+        for k, v in rec.items():
+            assert abs(losses[k] - v) <= tol * max(1.0, abs(v)), (it, k, losses[k], v)
