@@ -323,9 +323,11 @@ def main():
     # (they contain the gradient / batch-norm collectives); rank 0 reports its own timings.
     snap = m._snapshot()
     ops.PROFILE = ops.KernelProfile()
+    m.lanes.enabled = False           # one stream: every kernel is timed alone, not against a concurrent branch
     for _ in range(2):
         m._step_device(*dev)
     torch.cuda.synchronize()
+    m.lanes.enabled = True
     summ = ops.PROFILE.summary()
     ops.PROFILE = None
     m._restore(snap)

@@ -76,7 +76,7 @@ class FusedAdam(object):
             cnt = self.step_dev[i:i + 1]
             ops.step_increment(cnt)
             sq = self.scalars[S_SQ[name]:S_SQ[name] + 1]
-            ops.grad_sumsq(a.grad[:n], grad_scale, sq, self.red_ws)
+            ops.grad_sumsq(a.grad[:n], grad_scale, sq, self.red_ws[ops.lane()])
             ops.adam_clip(a.flat[:n], a.grad[:n], a.m[:n], a.v[:n], self.hyper, sq, cnt, grad_scale)
             ex.repack()
 
@@ -151,7 +151,8 @@ class _FusedCycleModel(object):
         self.device = torch.device("cuda", torch.cuda.current_device())
         self.scalars = torch.zeros(N_SCALARS, dtype=torch.float32, device=self.device)
         self.scalars_host = torch.zeros(N_SCALARS, dtype=torch.float32).pin_memory()
-        self.red_ws = torch.zeros(1024, dtype=torch.float32, device=self.device)
+        self.lanes = ops.Lanes(2, self.device)          # lane 0 = the caller's stream
+        self.red_ws = torch.zeros(3, 1024, dtype=torch.float32, device=self.device)    # reduction scratch, per lane
         self.criterionGAN = functools.partial(criterion_GAN, use_sigmoid=opt.use_sigmoid)
         self.criterionCycle = torch.nn.functional.l1_loss
         self.dp = None                 # parallel.DataParallelPlan when running one process per GPU
@@ -197,7 +198,7 @@ class _FusedCycleModel(object):
     def _d_pair(self, ex, fake, real, n, h, w, s_fake, s_true, s_pf, s_pt):
         """discriminate() (model.py:327-334) for an instance-norm discriminator: fake.detach() and real as ONE
         batch of 2N (instance statistics are per sample, so this is exact); fills the seed gradients."""
-        sc, ws = self.scalars, self.red_ws
+        sc, ws = self.scalars, self.red_ws[0]
         c = ex.new_ctx(2 * n, h, w, "d")
         ops.pack_nchw(fake, c.acts[0].batch_slice(0, n), 0)
         ops.pack_nchw(real, c.acts[0].batch_slice(n, 2 * n), 0)
@@ -212,8 +213,11 @@ class _FusedCycleModel(object):
         c = ex.new_ctx(n, h, w, "g")
         ops.pack_nchw(fake, c.acts[0], 0)
         i = self._head_idx(ex, "out")
-        ops.loss_lsgan(ex.forward(c)["out"], 1.0, 1.0, self.scalars, s_loss, s_pf, c.dyraw[i], self.red_ws)
+        ops.loss_lsgan(ex.forward(c)["out"], 1.0, 1.0, self.scalars, s_loss, s_pf, c.dyraw[i], self._rws())
         return c
+
+    def _rws(self):
+        return self.red_ws[ops.lane()]
 
     def _read_scalars(self):
         """one packed device->host copy of the reporting vector"""
@@ -413,134 +417,173 @@ class AugmentedCycleGAN(_FusedCycleModel):
 
     # ---- the fused step ------------------------------------------------------------------------
     def _step_device(self, real_A, real_B, prior_z_B):
-        """Everything of train_instance that runs on the device (capturable)."""
+        """Everything of train_instance that runs on the device (capturable).
+
+        The step is issued as a DAG over three lanes (ops.Lanes: parallel CUDA streams, parallel branches of the
+        captured graph): lanes 0 and 1 carry the two generators and the image discriminators, lane 2 the launch-bound
+        small networks (E_B, D_z_B), whose kernels fill SMs the big convolutions leave idle.  Each network's
+        forwards / backwards stay on one lane or are ordered by events (BatchNorm running statistics, gradient
+        accumulation into the arena); scratch buffers are per lane.  Issue order below is a valid serial schedule
+        and equals the reference order of model.py:402-515 up to commuting independent operations."""
         o = self.opt
         n, _, h, w = real_A.shape
         nz = o.nlatent
         GAB, GBA, E = self.netG_A_B._ex, self.netG_B_A._ex, self.netE_B._ex
         DA, DB, DZ = self.netD_A._ex, self.netD_B._ex, self.netD_z_B._ex
-        sc, ws = self.scalars, self.red_ws
+        sc = self.scalars
+        ws = self._rws
         dp, sync_bn, gs, ar = self._dp_env()
         z_prior = prior_z_B.reshape(n, nz)
+        z_prior4 = prior_z_B.reshape(n, nz, 1, 1)
         i_mu = self._head_idx(E, "mu")
+        iA, iB, iZ = self._head_idx(DA, "out"), self._head_idx(DB, "out"), self._head_idx(DZ, "out")
+        iGo, iGAo = self._head_idx(GBA, "out"), self._head_idx(GAB, "out")
+        c1, c2, c3 = GAB.new_ctx(n, h, w, "f1"), GBA.new_ctx(n, h, w, "f2"), E.new_ctx(n, h, w, "f3")
+        cdA, cdB = DA.new_ctx(2 * n, h, w, "d"), DB.new_ctx(2 * n, h, w, "d")
+        cz1, cz2, cgZ = DZ.new_ctx(n, 1, 1, "d1"), DZ.new_ctx(n, 1, 1, "d2"), DZ.new_ctx(n, 1, 1, "g")
+        cgA, cgB = DA.new_ctx(n, h, w, "g"), DB.new_ctx(n, h, w, "g")
+        c13, c14, c15 = GBA.new_ctx(n, h, w, "f13"), E.new_ctx(n, h, w, "f14"), GAB.new_ctx(n, h, w, "f15")
+        r = {}
+        wait = (lambda hs: dp.wait(hs)) if dp is not None else (lambda hs: None)
+        for opt_ in self._optimizers():      # model.py:443-444, 507-508 (nothing reads .grad in between)
+            opt_.zero_grad()
+        ln = self.lanes
+        ln.begin()
 
-        # F1 fake_B = G_A_B(real_A, prior_z)                                   model.py:404
-        c1 = GAB.new_ctx(n, h, w, "f1")
-        ops.pack_nchw(real_A, c1.acts[0], 0)
-        c1.z.copy_(z_prior)
-        fake_B = GAB.forward(c1)["out"]
-        # F2 fake_A = G_B_A(real_B)                                            model.py:407
-        c2 = GBA.new_ctx(n, h, w, "f2")
-        ops.pack_nchw(real_B, c2.acts[0], 0)
-        fake_A = GBA.forward(c2)["out"]
-        # F3 mu_z_realB = E_B(cat(fake_A, real_B))                             model.py:409-411
-        c3 = E.new_ctx(n, h, w, "f3")
-        if o.enc_A_B:
-            ops.pack_nchw(fake_A, c3.acts[0], 0)
-            ops.pack_nchw(real_B, c3.acts[0], o.input_nc)
-        else:
-            ops.pack_nchw(real_B, c3.acts[0], 0)
-        mu_realB = E.forward(c3, sync_bn)["mu"]                # [n, nz, 1, 1]; post_z_realB (stoch_enc=False)
-        ops.loss_l1(mu_realB, mu_realB, 0.0, False, sc, -1, S_KLD, None, ws)      # KLD_z_B, mu_min, mu_max
+        def f1():       # fake_B = G_A_B(real_A, prior_z)                          model.py:404
+            ops.pack_nchw(real_A, c1.acts[0], 0)
+            c1.z.copy_(z_prior)
+            r["fake_B"] = GAB.forward(c1)["out"]
+
+        def f2():       # fake_A = G_B_A(real_B)                                   model.py:407
+            ops.pack_nchw(real_B, c2.acts[0], 0)
+            r["fake_A"] = GBA.forward(c2)["out"]
+
+        def f3():       # mu_z_realB = E_B(cat(fake_A, real_B)); KLD_z_B, mu_min, mu_max      model.py:409-421
+            if o.enc_A_B:
+                ops.pack_nchw(r["fake_A"], c3.acts[0], 0)
+                ops.pack_nchw(real_B, c3.acts[0], o.input_nc)
+            else:
+                ops.pack_nchw(real_B, c3.acts[0], 0)
+            r["mu"] = E.forward(c3, sync_bn)["mu"]             # [n, nz, 1, 1]; post_z_realB (stoch_enc=False)
+            ops.loss_l1(r["mu"], r["mu"], 0.0, False, sc, -1, S_KLD, None, ws())
+
+        e_f1 = ln.run(0, f1)
+        e_f2 = ln.run(1, f2)
+        e_f3 = ln.run(2, f3, after=(e_f2,))
 
         # ---- D pass (model.py:423-452): fake.detach() and real as one 2N batch for the IN discriminators
-        cdA = DA.new_ctx(2 * n, h, w, "d")
-        ops.pack_nchw(fake_A, cdA.acts[0].batch_slice(0, n), 0)
-        ops.pack_nchw(real_A, cdA.acts[0].batch_slice(n, 2 * n), 0)
-        pA = DA.forward(cdA)["out"]
-        iA = self._head_idx(DA, "out")
-        ops.loss_lsgan(pA[:n], 0.0, 0.5, sc, S_DFA, S_PFA_D, cdA.dyraw[iA].batch_slice(0, n), ws)
-        ops.loss_lsgan(pA[n:], 1.0, 0.5, sc, S_DTA, S_PTA, cdA.dyraw[iA].batch_slice(n, 2 * n), ws)
-        cdB = DB.new_ctx(2 * n, h, w, "d")
-        ops.pack_nchw(fake_B, cdB.acts[0].batch_slice(0, n), 0)
-        ops.pack_nchw(real_B, cdB.acts[0].batch_slice(n, 2 * n), 0)
-        pB = DB.forward(cdB)["out"]
-        iB = self._head_idx(DB, "out")
-        ops.loss_lsgan(pB[:n], 0.0, 0.5, sc, S_DFB, S_PFB_D, cdB.dyraw[iB].batch_slice(0, n), ws)
-        ops.loss_lsgan(pB[n:], 1.0, 0.5, sc, S_DTB, S_PTB, cdB.dyraw[iB].batch_slice(n, 2 * n), ws)
-        iZ = self._head_idx(DZ, "out")
-        cz1 = DZ.new_ctx(n, 1, 1, "d1")                       # batch-norm net: separate calls, reference order
-        ops.pack_nchw(mu_realB, cz1.acts[0], 0)
-        p1 = DZ.forward(cz1, sync_bn)["out"]
-        ops.loss_lsgan(p1, 0.0, 0.5, sc, S_DPZ, -1, cz1.dyraw[iZ], ws)
-        cz2 = DZ.new_ctx(n, 1, 1, "d2")
-        ops.pack_nchw(prior_z_B.reshape(n, nz, 1, 1), cz2.acts[0], 0)
-        p2 = DZ.forward(cz2, sync_bn)["out"]
-        ops.loss_lsgan(p2, 1.0, 0.5, sc, S_DQZ, -1, cz2.dyraw[iZ], ws)
+        def d_pair(ex, c, i, fake, real, s_fake, s_true, s_pf, s_pt):
+            ops.pack_nchw(fake, c.acts[0].batch_slice(0, n), 0)
+            ops.pack_nchw(real, c.acts[0].batch_slice(n, 2 * n), 0)
+            p = ex.forward(c)["out"]
+            ops.loss_lsgan(p[:n], 0.0, 0.5, sc, s_fake, s_pf, c.dyraw[i].batch_slice(0, n), ws())
+            ops.loss_lsgan(p[n:], 1.0, 0.5, sc, s_true, s_pt, c.dyraw[i].batch_slice(n, 2 * n), ws())
+            ex.backward(c, {"out": True})
+            r[ex] = ar(ex.arena)
 
-        self.optimizer_D_A.zero_grad()
-        self.optimizer_D_B.zero_grad()
-        DA.backward(cdA, {"out": True})
-        ar(DA.arena)
-        DB.backward(cdB, {"out": True})
-        ar(DB.arena)
-        if o.z_gan:
-            DZ.backward(cz1, {"out": True}, sync_bn=sync_bn)
-            DZ.backward(cz2, {"out": True}, sync_bn=sync_bn)
-        ar(DZ.arena)
-        if dp is not None:
-            dp.wait()
-        self.optimizer_D_A.step(gs)
-        self.optimizer_D_B.step(gs)
+        def d_a():
+            d_pair(DA, cdA, iA, r["fake_A"], real_A, S_DFA, S_DTA, S_PFA_D, S_PTA)
+
+        def d_b():
+            d_pair(DB, cdB, iB, r["fake_B"], real_B, S_DFB, S_DTB, S_PFB_D, S_PTB)
+
+        def d_z():      # batch-norm net: separate calls, reference order
+            ops.pack_nchw(r["mu"], cz1.acts[0], 0)
+            ops.loss_lsgan(DZ.forward(cz1, sync_bn)["out"], 0.0, 0.5, sc, S_DPZ, -1, cz1.dyraw[iZ], ws())
+            ops.pack_nchw(z_prior4, cz2.acts[0], 0)
+            ops.loss_lsgan(DZ.forward(cz2, sync_bn)["out"], 1.0, 0.5, sc, S_DQZ, -1, cz2.dyraw[iZ], ws())
+            if o.z_gan:
+                DZ.backward(cz1, {"out": True}, sync_bn=sync_bn)
+                DZ.backward(cz2, {"out": True}, sync_bn=sync_bn)
+            r[DZ] = ar(DZ.arena)
+
+        def step_of(optim, ex, name):
+            def f():
+                wait([r.get(ex)])
+                optim.step(gs, only=(name,))
+            return f
+
+        ln.run(0, d_b)
+        ln.run(1, d_a)
+        ln.run(2, d_z)
+        ln.run(0, step_of(self.optimizer_D_B, DB, "netD_B"))
+        ln.run(1, step_of(self.optimizer_D_A, DA, "netD_A"))
+        ln.run(2, step_of(self.optimizer_D_B, DZ, "netD_z_B"))
 
         # ---- G / E pass with the UPDATED discriminators (model.py:457-515)
-        cgA = DA.new_ctx(n, h, w, "g")
-        ops.pack_nchw(fake_A, cgA.acts[0], 0)
-        ops.loss_lsgan(DA.forward(cgA)["out"], 1.0, 1.0, sc, S_GA, S_PFA, cgA.dyraw[iA], ws)
-        cgB = DB.new_ctx(n, h, w, "g")
-        ops.pack_nchw(fake_B, cgB.acts[0], 0)
-        ops.loss_lsgan(DB.forward(cgB)["out"], 1.0, 1.0, sc, S_GB, S_PFB, cgB.dyraw[iB], ws)
-        cgZ = DZ.new_ctx(n, 1, 1, "g")
-        ops.pack_nchw(mu_realB, cgZ.acts[0], 0)
-        ops.loss_lsgan(DZ.forward(cgZ, sync_bn)["out"], 1.0, 1.0 if o.z_gan else 0.0, sc, S_GZ, -1, cgZ.dyraw[iZ], ws)
-        # F13 rec_A = G_B_A(fake_B)
-        c13 = GBA.new_ctx(n, h, w, "f13")
-        ops.pack_nchw(fake_B, c13.acts[0], 0)
-        rec_A = GBA.forward(c13)["out"]
-        iGo = self._head_idx(GBA, "out")
-        ops.loss_l1(rec_A, real_A, o.lambda_A, True, sc, S_CYCA, -1, c13.dyraw[iGo], ws)
-        # F14 mu_z_fakeB = E_B(cat(real_A, fake_B))
-        c14 = E.new_ctx(n, h, w, "f14")
-        if o.enc_A_B:
-            ops.pack_nchw(real_A, c14.acts[0], 0)
-            ops.pack_nchw(fake_B, c14.acts[0], o.input_nc)
-        else:
-            ops.pack_nchw(fake_B, c14.acts[0], 0)
-        mu_fakeB = E.forward(c14, sync_bn)["mu"]
-        ops.loss_l1(mu_fakeB, prior_z_B.reshape(n, nz, 1, 1), o.lambda_z_B, False, sc, S_CYCZ, -1, c14.dyraw[i_mu], ws)
-        # F15 rec_B = G_A_B(fake_A, post_z_realB)
-        c15 = GAB.new_ctx(n, h, w, "f15")
-        ops.pack_nchw(fake_A, c15.acts[0], 0)
-        c15.z.copy_(mu_realB.reshape(n, nz))
-        rec_B = GAB.forward(c15)["out"]
-        iGAo = self._head_idx(GAB, "out")
-        ops.loss_l1(rec_B, real_B, o.lambda_B, True, sc, S_CYCB, -1, c15.dyraw[iGAo], ws)
+        def g_fwd_0():
+            ops.pack_nchw(r["fake_B"], cgB.acts[0], 0)
+            ops.loss_lsgan(DB.forward(cgB)["out"], 1.0, 1.0, sc, S_GB, S_PFB, cgB.dyraw[iB], ws())
+            ops.pack_nchw(r["fake_B"], c13.acts[0], 0)          # rec_A = G_B_A(fake_B)
+            r["rec_A"] = GBA.forward(c13)["out"]
+            ops.loss_l1(r["rec_A"], real_A, o.lambda_A, True, sc, S_CYCA, -1, c13.dyraw[iGo], ws())
 
-        self.optimizer_G_A.zero_grad()
-        self.optimizer_G_B.zero_grad()
-        g15 = GAB.backward(c15, {"out": True}, want_dx=True, want_dz=True)          # d fake_A (halo 3), dz
-        g14 = E.backward(c14, {"mu": True}, want_dx=True, sync_bn=sync_bn)           # channels 3..5: d fake_B
-        g13 = GBA.backward(c13, {"out": True}, want_dx=True)                         # d fake_B (halo 3)
-        g12 = DZ.backward(cgZ, {"out": True}, want_dx=True, want_dw=False, sync_bn=sync_bn)   # d post_z
-        g11 = DB.backward(cgB, {"out": True}, want_dx=True, want_dw=False)           # d fake_B
-        g10 = DA.backward(cgA, {"out": True}, want_dx=True, want_dw=False)           # d fake_A
-        # d mu_z_realB = D_z dgrad + dz of F15's CIN projections -> seed of F3's mu head
-        ops.grad_gather([g12], [0], nz, out=c3.dyraw[i_mu], add_nchw=c15.dz)
-        g3 = E.backward(c3, {"mu": True}, want_dx=True, sync_bn=sync_bn)             # channels 0..2: d fake_A
-        ar(E.arena)
-        cB = o.input_nc if o.enc_A_B else 0
-        ops.grad_gather([g14, g13, g11], [cB, 0, 0], o.output_nc, out=c1.dyraw[iGAo], tanh_y=fake_B)
-        GAB.backward(c1, {"out": True})
-        ar(GAB.arena)
-        ops.grad_gather([g15, g10, g3], [0, 0, 0], o.input_nc, out=c2.dyraw[iGo], tanh_y=fake_A)
-        GBA.backward(c2, {"out": True})
-        ar(GBA.arena)
-        if dp is not None:
-            dp.wait()
-        self.optimizer_G_A.step(gs)
-        self.optimizer_G_B.step(gs)
-        return OrderedDict([('real_A', real_A), ('fake_B', fake_B), ('rec_A', rec_A),
-                            ('real_B', real_B), ('fake_A', fake_A), ('rec_B', rec_B)])
+        def g_fwd_1():
+            ops.pack_nchw(r["fake_A"], cgA.acts[0], 0)
+            ops.loss_lsgan(DA.forward(cgA)["out"], 1.0, 1.0, sc, S_GA, S_PFA, cgA.dyraw[iA], ws())
+            ops.pack_nchw(r["fake_A"], c15.acts[0], 0)          # rec_B = G_A_B(fake_A, post_z_realB)
+            c15.z.copy_(r["mu"].reshape(n, nz))
+            r["rec_B"] = GAB.forward(c15)["out"]
+            ops.loss_l1(r["rec_B"], real_B, o.lambda_B, True, sc, S_CYCB, -1, c15.dyraw[iGAo], ws())
+
+        def g_fwd_2():
+            ops.pack_nchw(r["mu"], cgZ.acts[0], 0)
+            ops.loss_lsgan(DZ.forward(cgZ, sync_bn)["out"], 1.0, 1.0 if o.z_gan else 0.0, sc, S_GZ, -1, cgZ.dyraw[iZ], ws())
+            if o.enc_A_B:                                        # mu_z_fakeB = E_B(cat(real_A, fake_B))
+                ops.pack_nchw(real_A, c14.acts[0], 0)
+                ops.pack_nchw(r["fake_B"], c14.acts[0], o.input_nc)
+            else:
+                ops.pack_nchw(r["fake_B"], c14.acts[0], 0)
+            mu_fakeB = E.forward(c14, sync_bn)["mu"]
+            ops.loss_l1(mu_fakeB, z_prior4, o.lambda_z_B, False, sc, S_CYCZ, -1, c14.dyraw[i_mu], ws())
+
+        ln.run(0, g_fwd_0)
+        ln.run(1, g_fwd_1, after=(e_f3,))
+        ln.run(2, g_fwd_2, after=(e_f1,))
+
+        def g_bwd_1():
+            r["g15"] = GAB.backward(c15, {"out": True}, want_dx=True, want_dz=True)          # d fake_A (halo 3), dz
+            r["g10"] = DA.backward(cgA, {"out": True}, want_dx=True, want_dw=False)          # d fake_A
+
+        def g_bwd_0():
+            r["g13"] = GBA.backward(c13, {"out": True}, want_dx=True)                        # d fake_B (halo 3)
+            r["g11"] = DB.backward(cgB, {"out": True}, want_dx=True, want_dw=False)          # d fake_B
+
+        def g_bwd_2a():
+            r["g14"] = E.backward(c14, {"mu": True}, want_dx=True, sync_bn=sync_bn)          # channels 3..5: d fake_B
+            r["g12"] = DZ.backward(cgZ, {"out": True}, want_dx=True, want_dw=False, sync_bn=sync_bn)   # d post_z
+
+        def g_bwd_2b():
+            # d mu_z_realB = D_z dgrad + dz of F15's CIN projections -> seed of F3's mu head
+            ops.grad_gather([r["g12"]], [0], nz, out=c3.dyraw[i_mu], add_nchw=c15.dz)
+            r["g3"] = E.backward(c3, {"mu": True}, want_dx=True, sync_bn=sync_bn)            # channels 0..2: d fake_A
+            r[E] = ar(E.arena)
+
+        e_b1 = ln.run(1, g_bwd_1)
+        e_b0 = ln.run(0, g_bwd_0)
+        e_b2a = ln.run(2, g_bwd_2a)
+        e_b2b = ln.run(2, g_bwd_2b, after=(e_b1,))
+
+        def g_last_0():
+            cB = o.input_nc if o.enc_A_B else 0
+            ops.grad_gather([r["g14"], r["g13"], r["g11"]], [cB, 0, 0], o.output_nc, out=c1.dyraw[iGAo], tanh_y=r["fake_B"])
+            GAB.backward(c1, {"out": True})
+            r[GAB] = ar(GAB.arena)
+
+        def g_last_1():
+            ops.grad_gather([r["g15"], r["g10"], r["g3"]], [0, 0, 0], o.input_nc, out=c2.dyraw[iGo], tanh_y=r["fake_A"])
+            GBA.backward(c2, {"out": True})
+            r[GBA] = ar(GBA.arena)
+
+        ln.run(0, g_last_0, after=(e_b2a, e_b1))       # e_b1: c15's backward wrote G_A_B's gradient arena
+        ln.run(1, g_last_1, after=(e_b2b, e_b0))       # e_b0: c13's backward wrote G_B_A's gradient arena
+        ln.run(0, step_of(self.optimizer_G_B, GAB, "netG_A_B"))
+        ln.run(1, step_of(self.optimizer_G_A, GBA, "netG_B_A"))
+        ln.run(2, step_of(self.optimizer_G_B, E, "netE_B"))
+        ln.end()
+        return OrderedDict([('real_A', real_A), ('fake_B', r["fake_B"]), ('rec_A', r["rec_A"]),
+                            ('real_B', real_B), ('fake_A', r["fake_A"]), ('rec_B', r["rec_B"])])
 
     def _check_inputs(self, real_A, real_B, prior_z_B):
         ins = self._check_common(real_A, real_B, prior_z_B)
@@ -571,7 +614,7 @@ class AugmentedCycleGAN(_FusedCycleModel):
         n, _, h, w = real_A.shape
         nz = o.nlatent
         GAB, GBA, E, DZ = self.netG_A_B._ex, self.netG_B_A._ex, self.netE_B._ex, self.netD_z_B._ex
-        sc, ws = self.scalars, self.red_ws
+        sc, ws = self.scalars, self.red_ws[0]
         dp, sync_bn, gs, ar = self._dp_env()
         i_mu, iZ = self._head_idx(E, "mu"), self._head_idx(DZ, "out")
         iGAo, iGo = self._head_idx(GAB, "out"), self._head_idx(GBA, "out")
@@ -731,7 +774,7 @@ class StochCycleGAN(_FusedCycleModel):
         n, _, h, w = real_A.shape
         nz = o.nlatent
         GAB, GBA, DA, DB = self.netG_A_B._ex, self.netG_B_A._ex, self.netD_A._ex, self.netD_B._ex
-        sc, ws = self.scalars, self.red_ws
+        sc, ws = self.scalars, self.red_ws[0]
         dp, sync_bn, gs, ar = self._dp_env()
         iGAo, iGo = self._head_idx(GAB, "out"), self._head_idx(GBA, "out")
         z = self._z(prior_z_B).reshape(n, nz)

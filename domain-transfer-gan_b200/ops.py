@@ -16,6 +16,63 @@ def _stream():
     return C.c_void_p(torch.cuda.current_stream().cuda_stream)
 
 
+# ---- lanes: independent branches of a step on parallel CUDA streams ------------------------------------------------
+_LANE = 0
+
+
+def lane():
+    """index of the lane (stream) the caller is issuing on; scratch buffers are per lane"""
+    return _LANE
+
+
+class Lanes(object):
+    """Fork / join of independent branches of one step onto side CUDA streams.  Lane 0 is the caller's current
+    stream (under torch.cuda.graph: the capturing stream, so the side streams join the capture through the fork
+    event and the branches become parallel paths of the SAME CUDA graph).  Tasks on one lane run in issue order;
+    cross-lane dependencies are the events returned by run().  With enabled=False every task runs on lane 0 in
+    issue order (the issue order must therefore be a valid serial schedule)."""
+
+    def __init__(self, n_side, device):
+        self.side = [torch.cuda.Stream(device=device) for _ in range(n_side)]
+        self.enabled = True
+        self.streams = None
+
+    def begin(self):
+        main = torch.cuda.current_stream()
+        self.streams = [main] + (self.side if self.enabled else [])
+        if self.enabled:
+            ev = torch.cuda.Event()
+            ev.record(main)
+            for s in self.side:
+                s.wait_event(ev)
+
+    def run(self, lane_idx, fn, after=()):
+        """issue fn() on lane `lane_idx` after the events in `after`; returns the completion event"""
+        global _LANE
+        if not self.enabled:
+            fn()
+            return None
+        s = self.streams[lane_idx]
+        for ev in after:
+            if ev is not None:
+                s.wait_event(ev)
+        prev, _LANE = _LANE, lane_idx
+        try:
+            with torch.cuda.stream(s):
+                fn()
+        finally:
+            _LANE = prev
+        ev = torch.cuda.Event()
+        ev.record(s)
+        return ev
+
+    def end(self):
+        if self.enabled:
+            for s in self.side:
+                self.streams[0].wait_stream(s)
+        self.streams = None
+
+
 def _ptr(t):
     return C.c_void_p(t.data_ptr()) if t is not None else C.c_void_p(0)
 
@@ -214,7 +271,7 @@ _ws_cache = {}
 
 def workspace(nbytes, device="cuda", tag="default"):
     """Grow-only scratch buffer per (device, tag); contents are never assumed to persist."""
-    key = (str(device), tag)
+    key = (str(device), tag, _LANE)
     t = _ws_cache.get(key)
     if t is None or t.numel() < nbytes:
         t = torch.empty(max(nbytes, 1 << 20), dtype=torch.uint8, device=device)
@@ -304,7 +361,7 @@ _cs_ws = {}
 
 
 def channel_sum(x, c, d_bias):
-    dev = str(d_bias.device)
+    dev = (str(d_bias.device), _LANE)
     if dev not in _cs_ws:
         _cs_ws[dev] = torch.zeros(2048, dtype=torch.float32, device=d_bias.device)
     L.check(L.lib().dtg_channel_sum(x.s, c, _ptr(d_bias), _ptr(_cs_ws[dev]), _stream()), "channel_sum")

@@ -45,17 +45,22 @@ class DataParallelPlan(object):
     def allreduce_arena(self, arena):
         """start the all-reduce of one network's gradient arena (call right after its last backward)"""
         if self.world_size == 1:
-            return
+            return None
         g = arena.grad[:arena.active_count]
         if self.overlap:
-            self._pending.append(dist.all_reduce(g, op=dist.ReduceOp.SUM, group=self.group, async_op=True))
-        else:
-            dist.all_reduce(g, op=dist.ReduceOp.SUM, group=self.group)
+            h = dist.all_reduce(g, op=dist.ReduceOp.SUM, group=self.group, async_op=True)
+            self._pending.append(h)
+            return h
+        dist.all_reduce(g, op=dist.ReduceOp.SUM, group=self.group)
+        return None
 
-    def wait(self):
-        for w in self._pending:
-            w.wait()
-        self._pending = []
+    def wait(self, handles=None):
+        """make the current stream wait for the given all-reduces (default: all outstanding ones)"""
+        for w in (list(self._pending) if handles is None else handles):
+            if w is not None:
+                w.wait()
+                if w in self._pending:
+                    self._pending.remove(w)
 
     def allreduce_grads(self, arenas):
         for a in arenas:
