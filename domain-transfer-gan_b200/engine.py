@@ -342,12 +342,7 @@ class NetExec:
                     pending[ly.residual] = (d_res, d1) if d0 is None else (d0, d_res)
             # weight gradient
             if want_dw:
-                dw = A.g(ly.conv.weight)
-                if ly.transposed:
-                    ops.conv_wgrad(a_in, dyr, dw, kh=ly.k, kw=ly.k, stride=ly.stride, pad=ly.pad, pa=ly.cin, qb=ly.cout)
-                else:
-                    ops.conv_wgrad(dyr, a_in, dw, kh=ly.k, kw=ly.k, stride=ly.stride, pad=ly.pad, pa=ly.cout, qb=ly.cin,
-                                   fold=1 if ly.fold_in else (2 if ly.fold_out else 0))
+                ops.off_chain(self._wgrad_fn(ly, a_in, dyr, A.g(ly.conv.weight)))
             # data gradient
             if ly.src > 0 or want_dx:
                 gin = self._gact(c, ly.src, i)
@@ -362,7 +357,18 @@ class NetExec:
                 d0, d1 = pending.get(ly.src, (None, None))
                 assert d0 is None or d1 is None, "more than two gradient contributions for one activation"
                 pending[ly.src] = (gin, d1) if d0 is None else (gin, d0)
+        if want_dw:
+            ops.off_chain_join()        # the arena is complete when backward() returns (in stream order)
         return pending.get(0, (None, None))[0] if want_dx else None
+
+    @staticmethod
+    def _wgrad_fn(ly, a_in, dyr, dw):
+        """the weight gradient of one layer: off the norm-backward / dgrad chain (ops.off_chain)"""
+        if ly.transposed:
+            return lambda: ops.conv_wgrad(a_in, dyr, dw, kh=ly.k, kw=ly.k, stride=ly.stride, pad=ly.pad, pa=ly.cin,
+                                          qb=ly.cout)
+        return lambda: ops.conv_wgrad(dyr, a_in, dw, kh=ly.k, kw=ly.k, stride=ly.stride, pad=ly.pad, pa=ly.cout,
+                                      qb=ly.cin, fold=1 if ly.fold_in else (2 if ly.fold_out else 0))
 
     def _scratch_cin(self, sc):
         key = ("cin_scratch", sc.weight.shape)

@@ -34,12 +34,16 @@ class Lanes(object):
 
     def __init__(self, n_side, device):
         self.side = [torch.cuda.Stream(device=device) for _ in range(n_side)]
+        self.comp = [torch.cuda.Stream(device=device) for _ in range(n_side + 1)]   # companion stream of each lane
         self.enabled = True
+        self.companions = True
         self.streams = None
 
     def begin(self):
+        global ACTIVE
         main = torch.cuda.current_stream()
         self.streams = [main] + (self.side if self.enabled else [])
+        ACTIVE = self if self.enabled else None
         if self.enabled:
             ev = torch.cuda.Event()
             ev.record(main)
@@ -67,10 +71,51 @@ class Lanes(object):
         return ev
 
     def end(self):
+        global ACTIVE
         if self.enabled:
             for s in self.side:
                 self.streams[0].wait_stream(s)
         self.streams = None
+        ACTIVE = None
+
+    # A lane's companion stream carries work that hangs off the lane's chain without feeding it back (the weight
+    # gradients of a backward pass: each depends on one node of the norm-backward / dgrad chain and only the
+    # optimizer consumes it), so it overlaps the chain instead of lengthening it.
+    def companion_run(self, fn):
+        """issue fn() on the companion stream of the lane now issuing, after everything issued on the lane so far"""
+        global _LANE
+        if not self.companions:
+            fn()
+            return
+        cur, cs = torch.cuda.current_stream(), self.comp[_LANE]
+        cs.wait_stream(cur)
+        prev, _LANE = _LANE, _LANE + len(self.comp)
+        try:
+            with torch.cuda.stream(cs):
+                fn()
+        finally:
+            _LANE = prev
+
+    def companion_join(self):
+        """the lane now issuing waits for its companion stream"""
+        if self.companions:
+            torch.cuda.current_stream().wait_stream(self.comp[_LANE])
+
+
+ACTIVE = None       # the Lanes object between begin() and end()
+
+
+def off_chain(fn):
+    """run fn on the current lane's companion stream when a lane schedule is active, else inline"""
+    if ACTIVE is not None:
+        ACTIVE.companion_run(fn)
+    else:
+        fn()
+
+
+def off_chain_join():
+    if ACTIVE is not None:
+        ACTIVE.companion_join()
 
 
 def _ptr(t):

@@ -229,6 +229,11 @@ def test_checkpoint_reference_format_roundtrip(tmp_path):
     om = ostep.OracleModel(ostep.default_opt(), state, device=DEV)
     om.train_instance(a, b, z)
     chk = {name: {k: v.detach().clone() for k, v in om.nets[name].items()} for name in onets.NET_NAMES}
+    # the reference's CINResnetBlock registers its layers twice (modules.py:145-146), so its state_dict also holds
+    # the alias keys model.1x.{1,4,5}.* next to model.1x.conv_block.{1,4,5}.*
+    for k in list(chk["netG_A_B"].keys()):
+        if ".conv_block." in k:
+            chk["netG_A_B"][k.replace(".conv_block.", ".")] = chk["netG_A_B"][k]
     for grp in ("G_A", "G_B", "D_A", "D_B"):
         chk["optimizer_" + grp] = _torch_adam_state(om, grp)
     path = os.path.join(str(tmp_path), "ref_format.pth")
