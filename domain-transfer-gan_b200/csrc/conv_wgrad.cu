@@ -195,9 +195,12 @@ __global__ void __launch_bounds__(kWThreads, 1) wgrad_kernel(const __grid_consta
     mbar_wait(bar_done, 0);
     tc_fence_after();
     const bool any = t_end > t_begin;
+    // workspace layout [split][tap][column / 4][row][4]: the 32 lanes of a warp hold 32 consecutive rows, so every
+    // float4 store instruction writes 512 contiguous bytes
     for (int tl = 0; tl < ntl; ++tl) {
       const int t = tap0 + tl;
-      float* dst = p.ws + ((static_cast<size_t>(split) * p.ntaps + t) * p.mtot + mblock * 128 + row) * p.n_umma;
+      float4* dst = reinterpret_cast<float4*>(p.ws) + (static_cast<size_t>(split) * p.ntaps + t) * (p.n_umma / 4) * p.mtot +
+                    mblock * 128 + row;
       const uint32_t taddr = tmem_base + (static_cast<uint32_t>(quad * 32) << 16) + tl * p.n_umma;
       for (int c0 = 0; c0 < p.n_umma; c0 += 16) {
         uint32_t v[16];
@@ -208,7 +211,7 @@ __global__ void __launch_bounds__(kWThreads, 1) wgrad_kernel(const __grid_consta
           float4 o = any ? make_float4(__uint_as_float(v[4 * q]), __uint_as_float(v[4 * q + 1]),
                                        __uint_as_float(v[4 * q + 2]), __uint_as_float(v[4 * q + 3]))
                          : make_float4(0.f, 0.f, 0.f, 0.f);
-          reinterpret_cast<float4*>(dst + c0)[q] = o;
+          dst[static_cast<size_t>(c0 / 4 + q) * p.mtot] = o;
         }
       }
     }
@@ -222,7 +225,7 @@ __global__ void __launch_bounds__(kWThreads, 1) wgrad_kernel(const __grid_consta
   }
 }
 
-// dw[(a*qb + b)*ntaps + t] += sum_s ws[((s*ntaps + t)*mtot + a)*n_umma + b]
+// dw[(a*qb + b)*ntaps + t] += sum_s ws[(((s*ntaps + t)*(n_umma/4) + b/4)*mtot + a)*4 + b%4]
 // fold = 1: accumulator column b' = j*fc + b holds filter column kw = j          (t = kh, KW real columns)
 // fold = 2: accumulator row    a' = j*fc + a holds filter column kw = KW - 1 - j
 __global__ void __launch_bounds__(256) wgrad_reduce_kernel(const float* __restrict__ ws, float* __restrict__ dw, int splits,
@@ -240,10 +243,10 @@ __global__ void __launch_bounds__(256) wgrad_reduce_kernel(const float* __restri
   for (int i0 = blockIdx.x * 32; i0 < total; i0 += gridDim.x * 32) {
     const int i = i0 + cl;
     const bool ok = i < total;
-    const int c4 = ok ? i % ncol4 : 0;
-    const int row = ok ? (i / ncol4) % rows : 0;
+    const int row = ok ? i % rows : 0;
+    const int c4 = ok ? (i / rows) % ncol4 : 0;
     const int t = ok ? i / (ncol4 * rows) : 0;
-    const float* src = ws + (static_cast<size_t>(t) * mtot + row) * n_umma + c4 * 4;
+    const float* src = ws + ((static_cast<size_t>(t) * ncol4 + c4) * mtot + row) * 4;
     float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
     if (ok) {
 #pragma unroll 4

@@ -28,6 +28,7 @@ opt = argparse.Namespace(**vars(ostep.default_opt()), expr_dir="/tmp", niter_dec
 torch.manual_seed(1234)
 m = dmodel.AugmentedCycleGAN(opt, testing=True)
 m.prepare()
+m.lanes.enabled = False      # serial issue: ops are replayed one by one below
 a, b, z = [t.cuda() for t in ostep.synthetic_batch(args.batch, seed=4321)]
 for _ in range(2):
     m._step_device(a, b, z)
