@@ -151,7 +151,7 @@ class _FusedCycleModel(object):
         self.device = torch.device("cuda", torch.cuda.current_device())
         self.scalars = torch.zeros(N_SCALARS, dtype=torch.float32, device=self.device)
         self.scalars_host = torch.zeros(N_SCALARS, dtype=torch.float32).pin_memory()
-        self.lanes = ops.Lanes(2, self.device)          # lane 0 = the caller's stream
+        self.lanes = ops.Lanes(3, self.device)
         self.red_ws = torch.zeros(3, 1024, dtype=torch.float32, device=self.device)    # reduction scratch, per lane
         self.criterionGAN = functools.partial(criterion_GAN, use_sigmoid=opt.use_sigmoid)
         self.criterionCycle = torch.nn.functional.l1_loss

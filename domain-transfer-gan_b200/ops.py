@@ -26,29 +26,38 @@ def lane():
 
 
 class Lanes(object):
-    """Fork / join of independent branches of one step onto side CUDA streams.  Lane 0 is the caller's current
-    stream (under torch.cuda.graph: the capturing stream, so the side streams join the capture through the fork
-    event and the branches become parallel paths of the SAME CUDA graph).  Tasks on one lane run in issue order;
+    """Fork / join of independent branches of one step onto lane CUDA streams.  begin() forks the lanes off the
+    caller's current stream (under torch.cuda.graph: the capturing stream, so the lanes join the capture through the
+    fork event and the branches become parallel paths of the SAME CUDA graph); end() joins them back.  Tasks on one lane run in issue order;
     cross-lane dependencies are the events returned by run().  With enabled=False every task runs on lane 0 in
     issue order (the issue order must therefore be a valid serial schedule)."""
 
-    def __init__(self, n_side, device):
-        self.side = [torch.cuda.Stream(device=device) for _ in range(n_side)]
-        self.comp = [torch.cuda.Stream(device=device) for _ in range(n_side + 1)]   # companion stream of each lane
+    def __init__(self, n_lanes, device, chain_priority=0, comp_priority=0):
+        import os
+        if os.environ.get("DTG_LANE_PRIO"):
+            chain_priority, comp_priority = [int(v) for v in os.environ["DTG_LANE_PRIO"].split(",")]
+        # the lanes carry dependency chains (forward / norm-backward / dgrad): high priority, so that a chain kernel
+        # is dispatched ahead of the queued off-chain work (weight gradients on the companion streams, priority 0)
+        self.lane_streams = [torch.cuda.Stream(device=device, priority=chain_priority) for _ in range(n_lanes)]
+        self.comp = [torch.cuda.Stream(device=device, priority=comp_priority) for _ in range(n_lanes)]   # companion of each lane
         self.enabled = True
         self.companions = True
         self.streams = None
+        self.main = None
 
     def begin(self):
         global ACTIVE
-        main = torch.cuda.current_stream()
-        self.streams = [main] + (self.side if self.enabled else [])
-        ACTIVE = self if self.enabled else None
-        if self.enabled:
-            ev = torch.cuda.Event()
-            ev.record(main)
-            for s in self.side:
-                s.wait_event(ev)
+        self.main = torch.cuda.current_stream()
+        if not self.enabled:
+            self.streams = [self.main]
+            ACTIVE = None
+            return
+        self.streams = self.lane_streams
+        ACTIVE = self
+        ev = torch.cuda.Event()
+        ev.record(self.main)
+        for s in self.streams:
+            s.wait_event(ev)
 
     def run(self, lane_idx, fn, after=()):
         """issue fn() on lane `lane_idx` after the events in `after`; returns the completion event"""
@@ -73,8 +82,8 @@ class Lanes(object):
     def end(self):
         global ACTIVE
         if self.enabled:
-            for s in self.side:
-                self.streams[0].wait_stream(s)
+            for s in self.streams:
+                self.main.wait_stream(s)
         self.streams = None
         ACTIVE = None
 

@@ -200,3 +200,30 @@ def test_oracle_supervised_matches_golden(golden_dir):
         tol = 2e-5 if it == 0 else 5e-3
         for k, v in rec.items():
             assert abs(losses[k] - v) <= tol * max(1.0, abs(v)), (it, k, losses[k], v)
+
+
+@pytest.mark.skipif(not lr.available(), reason="/root/reference not present (GPU box)")
+def test_parameter_order_matches_reference():
+    """torch.optim.Adam state_dicts index parameters by position (model.py:379-389 build the optimizers from
+    itertools.chain(net.parameters() ...)), so reference-format checkpoints only interoperate if the drop-in modules
+    register their parameters in the reference's order with the reference's shapes."""
+    warnings.simplefilter("ignore")
+    import dtg  # noqa: F401
+    from dtg_b200 import networks as N
+    opt = step.default_opt()
+    ref = lr.build_reference_model(copy.deepcopy(opt), nets.init_model_state(seed=1))
+    ours = {
+        "netG_A_B": N.define_stochastic_G(nlatent=16, input_nc=3, output_nc=3, ngf=32, which_model_netG="resnet",
+                                          norm="instance", use_dropout=False, gpu_ids=[]),
+        "netG_B_A": N.define_G(input_nc=3, output_nc=3, ngf=32, which_model_netG="resnet", norm="instance",
+                               use_dropout=False, gpu_ids=[]),
+        "netE_B": N.define_E(nlatent=16, input_nc=6, nef=32, norm="batch", gpu_ids=[]),
+        "netD_A": N.define_D_A(input_nc=3, ndf=32, which_model_netD="basic", norm="instance", use_sigmoid=False, gpu_ids=[]),
+        "netD_B": N.define_D_B(input_nc=3, ndf=64, which_model_netD="basic", norm="instance", use_sigmoid=False, gpu_ids=[]),
+        "netD_z_B": N.define_LAT_D(nlatent=16, ndf=64, use_sigmoid=False, gpu_ids=[]),
+    }
+    for k, net in ours.items():
+        a = [(n, tuple(p.shape)) for n, p in getattr(ref, k).named_parameters()]
+        b = [(n, tuple(p.shape)) for n, p in net.named_parameters()]
+        assert a == b, k
+        assert list(getattr(ref, k).state_dict().keys()) == list(net.state_dict().keys()), k

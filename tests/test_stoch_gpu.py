@@ -205,12 +205,15 @@ def test_supervised_matches_golden(golden_dir):
 
 
 # ---- checkpoints -------------------------------------------------------------------------------------------------
-def _torch_adam_state(om, group):
+def _torch_adam_state(om, group, model):
     """the state_dict torch.optim.Adam(itertools.chain(net.parameters() ...)) of the reference would hold after the
-    oracle's steps (model.py:379-389): per-parameter step / exp_avg / exp_avg_sq in param_groups order"""
+    oracle's steps (model.py:379-389): per-parameter step / exp_avg / exp_avg_sq in param_groups order, i.e. the
+    reference modules' parameter registration order (= ours: tests/test_oracle.py::test_parameter_order_matches_reference)"""
     state, idx = {}, 0
     for net in om.GROUPS[group]:
-        for k, v in om.params(net):
+        have = dict(om.params(net))
+        for k, _ in getattr(model, net).named_parameters():
+            assert k in have, (net, k)
             st = om.adam.get((net, k))
             if st is not None:
                 state[idx] = {"step": torch.tensor(float(st["step"])), "exp_avg": st["m"].clone(), "exp_avg_sq": st["v"].clone()}
@@ -234,12 +237,12 @@ def test_checkpoint_reference_format_roundtrip(tmp_path):
     for k in list(chk["netG_A_B"].keys()):
         if ".conv_block." in k:
             chk["netG_A_B"][k.replace(".conv_block.", ".")] = chk["netG_A_B"][k]
-    for grp in ("G_A", "G_B", "D_A", "D_B"):
-        chk["optimizer_" + grp] = _torch_adam_state(om, grp)
-    path = os.path.join(str(tmp_path), "ref_format.pth")
-    torch.save(chk, path)
     ours = dmodel.AugmentedCycleGAN(_opt(expr_dir=str(tmp_path)), testing=True)
     ours.prepare()
+    for grp in ("G_A", "G_B", "D_A", "D_B"):
+        chk["optimizer_" + grp] = _torch_adam_state(om, grp, ours)
+    path = os.path.join(str(tmp_path), "ref_format.pth")
+    torch.save(chk, path)
     ours.load(path)
     assert ours.optimizer_G_B.step_dev.tolist() == [1, 1] and ours.optimizer_D_B.step_dev.tolist() == [1, 1]
     l_ours, _, g_ours = ours.train_instance(a, b, z)
