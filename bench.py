@@ -37,6 +37,27 @@ UNIT = "img/s"
 WORKLOAD = ("Augmented CycleGAN 64x64 edges2shoes-shaped, batch %d per GPU, bf16, one train_instance step "
             "(G_A_B, G_B_A, E_B, D_A, D_B, D_z_B fwd+bwd, clip, Adam)" % BATCH)
 FLOP_PER_IMAGE = 36.003e9          # useful conv+linear FLOPs per image per step at 64x64
+# --workload: the default is the BASELINE.json metric's configuration (configs[1]); the others time the parity-test
+# configurations 3 and 4 through the same harness (StochCycleGAN is the reference-native step above 64x64)
+WORKLOADS = {
+    "aug64": dict(model="aug", size=64, output_nc=3, kind="edges2shoes", batch=BATCH, desc=WORKLOAD),
+    "stoch128": dict(model="stoch", size=128, output_nc=1, kind="climate", batch=40,
+                     desc="StochCycleGAN 128x128 Livneh-style climate fields (3 -> 1 channels), batch %d per GPU, bf16, "
+                          "one train_instance step (G_A_B, G_B_A, D_A, D_B fwd+bwd, clip, Adam)"),
+    "stoch256": dict(model="stoch", size=256, output_nc=3, kind="edges2shoes", batch=10,
+                     desc="StochCycleGAN 256x256 edges2shoes-shaped (the reference's 3-block generators), batch %d per GPU, "
+                          "bf16, one train_instance step (G_A_B, G_B_A, D_A, D_B fwd+bwd, clip, Adam)"),
+}
+
+
+def _oracle_for(wl, device="cpu"):
+    """(oracle model, batch maker) of a workload: the CPU / cuDNN restatement of the same step"""
+    from oracle import nets as onets, step as ostep
+    opt = ostep.default_opt(output_nc=wl["output_nc"])
+    state = onets.init_model_state(seed=1234, output_nc=wl["output_nc"])
+    om = (ostep.OracleModel if wl["model"] == "aug" else ostep.OracleStochModel)(opt, state, device=device)
+    mk = lambda n, seed=4321: ostep.synthetic_batch(n, size=wl["size"], seed=seed, output_nc=wl["output_nc"], kind=wl["kind"])
+    return om, mk
 
 
 def _peaks():
@@ -105,13 +126,12 @@ def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    from oracle import nets as onets, step as ostep
+    wl = WORKLOADS[args.workload]
     cores = os.cpu_count() or 1
     torch.set_num_threads(cores)
-    sample_n = 8
-    state = onets.init_model_state(seed=1234)
-    om = ostep.OracleModel(ostep.default_opt(), state)
-    a, b, z = ostep.synthetic_batch(sample_n, seed=4321)
+    sample_n = 8 if wl["size"] == 64 else 2
+    om, mk = _oracle_for(wl)
+    a, b, z = mk(sample_n)
     for _ in range(max(1, min(args.warmup, 2))):
         om.train_instance(a, b, z)
     steps = max(1, min(args.steps, 5))
@@ -123,7 +143,7 @@ def run_reference(args):
     line = {"impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": args.gpus, "steps": steps,
             "warmup": max(1, min(args.warmup, 2)), "ms_per_step": 1e3 * dt / steps, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": WORKLOAD, "sample": "batch %d of the batch-%d workload per step" % (sample_n, BATCH)},
+            "config": {"workload": _desc(wl, args), "sample": "batch %d of the batch-%d workload per step" % (sample_n, args.batch or wl["batch"])},
             "cpu_baseline": {"value": v, "unit": UNIT, "cores": cores, "kind": "port",
                              "sample": "%d train_instance steps at batch %d, torch %s CPU fp32, %d threads"
                                        % (steps, sample_n, torch.__version__, cores)},
@@ -131,13 +151,17 @@ def run_reference(args):
     print(json.dumps(line))
 
 
-def cpu_baseline():
-    from oracle import nets as onets, step as ostep
+def _desc(wl, args):
+    n = args.batch or wl["batch"]
+    return wl["desc"] % n if "%d" in wl["desc"] else wl["desc"].replace("batch %d" % BATCH, "batch %d" % n)
+
+
+def cpu_baseline(wl):
     cores = os.cpu_count() or 1
     torch.set_num_threads(cores)
-    n = 8
-    om = ostep.OracleModel(ostep.default_opt(), onets.init_model_state(seed=1234))
-    a, b, z = ostep.synthetic_batch(n, seed=4321)
+    n = 8 if wl["size"] == 64 else 2
+    om, mk = _oracle_for(wl)
+    a, b, z = mk(n)
     om.train_instance(a, b, z)
     steps, t0 = 0, time.perf_counter()
     while steps < 3 or (time.perf_counter() - t0 < 10.0 and steps < 20):
@@ -145,21 +169,21 @@ def cpu_baseline():
         steps += 1
     dt = time.perf_counter() - t0
     return {"value": n * steps / dt, "unit": UNIT, "cores": cores, "kind": "port",
-            "sample": "%d train_instance steps at batch %d (config 1), torch %s CPU fp32, %d threads"
-                      % (steps, n, torch.__version__, cores)}
+            "sample": "%d train_instance steps at batch %d%s, torch %s CPU fp32, %d threads"
+                      % (steps, n, " (config 1)" if wl["model"] == "aug" else " at %dx%d" % (wl["size"], wl["size"]),
+                         torch.__version__, cores)}
 
 
-def torch_gpu_baseline(n):
+def torch_gpu_baseline(n, wl):
     """The reference's PyTorch path on this B200 (oracle port = same torch ops / cuDNN kernels), as the
     denominator of north_star's >=15x target: best of fp32(TF32 conv) and bf16 autocast."""
-    from oracle import nets as onets, step as ostep
     res = {}
-    a, b, z = [t.cuda() for t in ostep.synthetic_batch(n, seed=4321)]
+    a, b, z = [t.cuda() for t in _oracle_for(wl)[1](n)]
     for name in ("tf32", "bf16_autocast"):
         torch.backends.cudnn.allow_tf32 = True
         torch.backends.cuda.matmul.allow_tf32 = True
         torch.backends.cudnn.benchmark = True
-        om = ostep.OracleModel(ostep.default_opt(), onets.init_model_state(seed=1234), device="cuda")
+        om = _oracle_for(wl, "cuda")[0]
 
         def one():
             if name == "tf32":
@@ -187,7 +211,8 @@ def main():
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours")
-    ap.add_argument("--batch", type=int, default=BATCH)
+    ap.add_argument("--batch", type=int, default=0, help="images per GPU (default: the workload's)")
+    ap.add_argument("--workload", default="aug64", choices=sorted(WORKLOADS))
     ap.add_argument("--precision", default="bf16", choices=["bf16", "tf32"])
     ap.add_argument("--no-graph", action="store_true")
     ap.add_argument("--no-baselines", action="store_true", help="skip cpu_baseline / torch_gpu_baseline legs")
@@ -215,6 +240,7 @@ def main():
     torch.cuda.set_device(local)
     import torch.distributed as dist
     if world > 1:
+        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")    # keep stdout to the one JSON line (NCCL's version banner)
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     say("process group up")
 
@@ -225,17 +251,18 @@ def main():
     engine.set_precision(args.precision)
     W = max(3, args.warmup)
     K = max(1, args.steps)
-    n = args.batch
-    opt = argparse.Namespace(**vars(ostep.default_opt()), expr_dir="/tmp", niter_decay=25)
+    wl = WORKLOADS[args.workload]
+    n = args.batch or wl["batch"]
+    opt = argparse.Namespace(**vars(ostep.default_opt(output_nc=wl["output_nc"])), expr_dir="/tmp", niter_decay=25)
     torch.manual_seed(1234)
-    m = dmodel.AugmentedCycleGAN(opt, testing=True)
+    m = (dmodel.AugmentedCycleGAN if wl["model"] == "aug" else dmodel.StochCycleGAN)(opt, testing=True)
     m.prepare()
     say("model built")
     if world > 1:
         m.dp = parallel.DataParallelPlan(sync_bn=not args.no_sync_bn)
         m.dp.broadcast_model(m)
     say("replicas broadcast")
-    a, b, z = ostep.synthetic_batch(n, seed=4321 + rank)
+    a, b, z = ostep.synthetic_batch(n, size=wl["size"], seed=4321 + rank, output_nc=wl["output_nc"], kind=wl["kind"])
     host = [t.pin_memory() for t in (a, b, z)]
     dev = [t.cuda() for t in host]
     use_graph = not args.no_graph
@@ -311,7 +338,7 @@ def main():
     line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W,
             "ms_per_step": ms / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": args.precision, "data": "synthetic",
-            "config": {"workload": WORKLOAD if n == BATCH else WORKLOAD.replace("batch %d" % BATCH, "batch %d" % n),
+            "config": {"workload": _desc(wl, args),
                        "global_batch": world * n, "parallelism": "dp%d" % world, "cuda_graph": bool(graph_ok),
                        "sync_bn": bool(world > 1 and not args.no_sync_bn),
                        "l2": "no flush needed: each step streams > 4 GB of activations, far above the 126 MB L2"},
@@ -339,6 +366,8 @@ def main():
             peak = peak / 2.0
         tot_ms = sum(v["ms"] for v in summ.values())
         tot_fl = sum(v["flops"] for v in summ.values())
+        if wl["model"] != "aug":     # algorithmic conv FLOPs of this workload = what the step's launches add up to
+            line["conv_roofline_frac_of_step"] = (tot_fl / 2) / (ms / K * 1e-3) / (peak * 1e12)
         dom = max(summ, key=lambda k: summ[k]["ms"])
         ach = summ[dom]["flops"] / (summ[dom]["ms"] * 1e-3) / 1e12
         line["roofline"] = {"bound": "tensor", "kernel": dom + " (conv fwd/dgrad: igemm_kernel + pconv_kernel)" if dom == "igemm_kernel" else dom,
@@ -351,10 +380,10 @@ def main():
                             "all_tensor_kernels_tflops": tot_fl / (tot_ms * 1e-3) / 1e12}
         if world == 1 and not args.no_baselines:
             try:
-                line["torch_gpu_baseline"] = torch_gpu_baseline(n)
+                line["torch_gpu_baseline"] = torch_gpu_baseline(n, wl)
             except Exception as e:
                 line["torch_gpu_baseline"] = {"error": str(e).splitlines()[0][:200]}
-            line["cpu_baseline"] = cpu_baseline()
+            line["cpu_baseline"] = cpu_baseline(wl)
         print(json.dumps(line))
     if world > 1:
         # release the captured graph (it holds NCCL kernels) before tearing the communicator down; the teardown of a

@@ -769,62 +769,103 @@ class StochCycleGAN(_FusedCycleModel):
         return ins
 
     def _step_device(self, real_A, real_B, prior_z_B):
-        """model.py:126-208 on the device (capturable)."""
+        """model.py:126-208 on the device (capturable), issued over two lanes like AugmentedCycleGAN._step_device:
+        lane 0 carries G_A_B's first forward / D_B / G_B_A(fake_B), lane 1 the mirror image."""
         o = self.opt
         n, _, h, w = real_A.shape
         nz = o.nlatent
         GAB, GBA, DA, DB = self.netG_A_B._ex, self.netG_B_A._ex, self.netD_A._ex, self.netD_B._ex
-        sc, ws = self.scalars, self.red_ws[0]
+        sc = self.scalars
+        ws = self._rws
         dp, sync_bn, gs, ar = self._dp_env()
         iGAo, iGo = self._head_idx(GAB, "out"), self._head_idx(GBA, "out")
+        iA, iB = self._head_idx(DA, "out"), self._head_idx(DB, "out")
         z = self._z(prior_z_B).reshape(n, nz)
-        # fake_B = G_A_B(real_A, z); fake_A = G_B_A(real_B)                      model.py:132-135
-        c1 = GAB.new_ctx(n, h, w, "f1")
-        ops.pack_nchw(real_A, c1.acts[0], 0)
-        c1.z.copy_(z)
-        fake_B = GAB.forward(c1)["out"]
-        c2 = GBA.new_ctx(n, h, w, "f2")
-        ops.pack_nchw(real_B, c2.acts[0], 0)
-        fake_A = GBA.forward(c2)["out"]
-        # ---- D pass (model.py:137-163)
-        cdA = self._d_pair(DA, fake_A, real_A, n, h, w, S_DFA, S_DTA, S_PFA_D, S_PTA)
-        cdB = self._d_pair(DB, fake_B, real_B, n, h, w, S_DFB, S_DTB, S_PFB_D, S_PTB)
+        c1, c2 = GAB.new_ctx(n, h, w, "f1"), GBA.new_ctx(n, h, w, "f2")
+        cdA, cdB = DA.new_ctx(2 * n, h, w, "d"), DB.new_ctx(2 * n, h, w, "d")
+        cgA, cgB = DA.new_ctx(n, h, w, "g"), DB.new_ctx(n, h, w, "g")
+        c13, c15 = GBA.new_ctx(n, h, w, "f13"), GAB.new_ctx(n, h, w, "f15")
+        r = {}
+        wait = (lambda hs: dp.wait(hs)) if dp is not None else (lambda hs: None)
         self.optimizer_D.zero_grad()
-        DA.backward(cdA, {"out": True})
-        ar(DA.arena)
-        DB.backward(cdB, {"out": True})
-        ar(DB.arena)
-        if dp is not None:
-            dp.wait()
-        self.optimizer_D.step(gs)
-        # ---- G pass with the UPDATED discriminators (model.py:165-191)
-        cgA = self._g_adv(DA, fake_A, n, h, w, S_GA, S_PFA)
-        cgB = self._g_adv(DB, fake_B, n, h, w, S_GB, S_PFB)
-        c13 = GBA.new_ctx(n, h, w, "f13")                                        # rec_A = G_B_A(fake_B)
-        ops.pack_nchw(fake_B, c13.acts[0], 0)
-        rec_A = GBA.forward(c13)["out"]
-        ops.loss_l1(rec_A, real_A, o.lambda_A, True, sc, S_CYCA, -1, c13.dyraw[iGo], ws)
-        c15 = GAB.new_ctx(n, h, w, "f15")                                        # rec_B = G_A_B(fake_A, z)
-        ops.pack_nchw(fake_A, c15.acts[0], 0)
-        c15.z.copy_(z)
-        rec_B = GAB.forward(c15)["out"]
-        ops.loss_l1(rec_B, real_B, o.lambda_B, True, sc, S_CYCB, -1, c15.dyraw[iGAo], ws)
         self.optimizer_G.zero_grad()
-        g15 = GAB.backward(c15, {"out": True}, want_dx=True)                     # d fake_A
-        g13 = GBA.backward(c13, {"out": True}, want_dx=True)                     # d fake_B
-        g11 = DB.backward(cgB, {"out": True}, want_dx=True, want_dw=False)       # d fake_B
-        g10 = DA.backward(cgA, {"out": True}, want_dx=True, want_dw=False)       # d fake_A
-        ops.grad_gather([g13, g11], [0, 0], o.output_nc, out=c1.dyraw[iGAo], tanh_y=fake_B)
-        GAB.backward(c1, {"out": True})
-        ar(GAB.arena)
-        ops.grad_gather([g15, g10], [0, 0], o.input_nc, out=c2.dyraw[iGo], tanh_y=fake_A)
-        GBA.backward(c2, {"out": True})
-        ar(GBA.arena)
-        if dp is not None:
-            dp.wait()
-        self.optimizer_G.step(gs)
-        return OrderedDict([('real_A', real_A), ('fake_B', fake_B), ('rec_A', rec_A),
-                            ('real_B', real_B), ('fake_A', fake_A), ('rec_B', rec_B)])
+        ln = self.lanes
+        ln.begin()
+
+        def f1():       # fake_B = G_A_B(real_A, z)                                 model.py:132
+            ops.pack_nchw(real_A, c1.acts[0], 0)
+            c1.z.copy_(z)
+            r["fake_B"] = GAB.forward(c1)["out"]
+
+        def f2():       # fake_A = G_B_A(real_B)                                    model.py:135
+            ops.pack_nchw(real_B, c2.acts[0], 0)
+            r["fake_A"] = GBA.forward(c2)["out"]
+
+        ln.run(0, f1)
+        ln.run(1, f2)
+
+        # ---- D pass (model.py:137-163): fake.detach() and real as one 2N batch (instance statistics are per sample)
+        def d_pair(ex, c, i, fake, real, s_fake, s_true, s_pf, s_pt):
+            ops.pack_nchw(fake, c.acts[0].batch_slice(0, n), 0)
+            ops.pack_nchw(real, c.acts[0].batch_slice(n, 2 * n), 0)
+            p = ex.forward(c)["out"]
+            ops.loss_lsgan(p[:n], 0.0, 0.5, sc, s_fake, s_pf, c.dyraw[i].batch_slice(0, n), ws())
+            ops.loss_lsgan(p[n:], 1.0, 0.5, sc, s_true, s_pt, c.dyraw[i].batch_slice(n, 2 * n), ws())
+            ex.backward(c, {"out": True})
+            r[ex] = ar(ex.arena)
+
+        def step_of(optim, ex, name):
+            def f():
+                wait([r.get(ex)])
+                optim.step(gs, only=(name,))
+            return f
+
+        e_f1 = ln.run(0, lambda: d_pair(DB, cdB, iB, r["fake_B"], real_B, S_DFB, S_DTB, S_PFB_D, S_PTB))
+        e_f2 = ln.run(1, lambda: d_pair(DA, cdA, iA, r["fake_A"], real_A, S_DFA, S_DTA, S_PFA_D, S_PTA))
+        ln.run(0, step_of(self.optimizer_D, DB, "netD_B"))
+        ln.run(1, step_of(self.optimizer_D, DA, "netD_A"))
+
+        # ---- G pass with the UPDATED discriminators (model.py:165-191)
+        def g_fwd_0():
+            ops.pack_nchw(r["fake_B"], cgB.acts[0], 0)
+            ops.loss_lsgan(DB.forward(cgB)["out"], 1.0, 1.0, sc, S_GB, S_PFB, cgB.dyraw[iB], ws())
+            ops.pack_nchw(r["fake_B"], c13.acts[0], 0)          # rec_A = G_B_A(fake_B)
+            r["rec_A"] = GBA.forward(c13)["out"]
+            ops.loss_l1(r["rec_A"], real_A, o.lambda_A, True, sc, S_CYCA, -1, c13.dyraw[iGo], ws())
+            r["g13"] = GBA.backward(c13, {"out": True}, want_dx=True)                        # d fake_B
+            r["g11"] = DB.backward(cgB, {"out": True}, want_dx=True, want_dw=False)          # d fake_B
+
+        def g_fwd_1():
+            ops.pack_nchw(r["fake_A"], cgA.acts[0], 0)
+            ops.loss_lsgan(DA.forward(cgA)["out"], 1.0, 1.0, sc, S_GA, S_PFA, cgA.dyraw[iA], ws())
+            ops.pack_nchw(r["fake_A"], c15.acts[0], 0)          # rec_B = G_A_B(fake_A, z)
+            c15.z.copy_(z)
+            r["rec_B"] = GAB.forward(c15)["out"]
+            ops.loss_l1(r["rec_B"], real_B, o.lambda_B, True, sc, S_CYCB, -1, c15.dyraw[iGAo], ws())
+            r["g15"] = GAB.backward(c15, {"out": True}, want_dx=True)                        # d fake_A
+            r["g10"] = DA.backward(cgA, {"out": True}, want_dx=True, want_dw=False)          # d fake_A
+
+        # c13 runs G_B_A (lane 1 produced fake_A with it: read-only) on fake_B from lane 0, and vice versa
+        e_b0 = ln.run(0, g_fwd_0)
+        e_b1 = ln.run(1, g_fwd_1)
+
+        def g_last_0():
+            ops.grad_gather([r["g13"], r["g11"]], [0, 0], o.output_nc, out=c1.dyraw[iGAo], tanh_y=r["fake_B"])
+            GAB.backward(c1, {"out": True})
+            r[GAB] = ar(GAB.arena)
+
+        def g_last_1():
+            ops.grad_gather([r["g15"], r["g10"]], [0, 0], o.input_nc, out=c2.dyraw[iGo], tanh_y=r["fake_A"])
+            GBA.backward(c2, {"out": True})
+            r[GBA] = ar(GBA.arena)
+
+        ln.run(0, g_last_0, after=(e_b1,))      # e_b1: c15's backward wrote G_A_B's gradient arena
+        ln.run(1, g_last_1, after=(e_b0,))      # e_b0: c13's backward wrote G_B_A's gradient arena
+        ln.run(0, step_of(self.optimizer_G, GAB, "netG_A_B"))
+        ln.run(1, step_of(self.optimizer_G, GBA, "netG_B_A"))
+        ln.end()
+        return OrderedDict([('real_A', real_A), ('fake_B', r["fake_B"]), ('rec_A', r["rec_A"]),
+                            ('real_B', real_B), ('fake_A', r["fake_A"]), ('rec_B', r["rec_B"])])
 
     def _report(self):
         """model.py:193-206"""

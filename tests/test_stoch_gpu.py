@@ -254,7 +254,10 @@ def test_checkpoint_reference_format_roundtrip(tmp_path):
         for k, v in om.params(name):
             if onets.is_noise_grad(name, k):
                 continue
-            assert float((sd[k] - v.detach()).norm()) <= 3e-3 * float(v.detach().norm()) + 1e-5, (name, k)
+            # an Adam update moves every weight by <= lr; tf32 rounding flips the sign of near-zero gradients, so
+            # allow a fraction of that budget on top of the relative tolerance
+            lim = 3e-3 * float(v.detach().norm()) + 0.25 * 2e-4 * v.numel() ** 0.5
+            assert float((sd[k] - v.detach()).norm()) <= lim + 1e-5, (name, k)
     # (2) our own save/load
     ours.save("ours.pth")
     fresh = dmodel.AugmentedCycleGAN(_opt(expr_dir=str(tmp_path)), testing=True)
