@@ -151,8 +151,8 @@ class _FusedCycleModel(object):
         self.device = torch.device("cuda", torch.cuda.current_device())
         self.scalars = torch.zeros(N_SCALARS, dtype=torch.float32, device=self.device)
         self.scalars_host = torch.zeros(N_SCALARS, dtype=torch.float32).pin_memory()
-        self.lanes = ops.Lanes(3, self.device)
-        self.red_ws = torch.zeros(3, 1024, dtype=torch.float32, device=self.device)    # reduction scratch, per lane
+        self.lanes = ops.Lanes(5, self.device)
+        self.red_ws = torch.zeros(5, 1024, dtype=torch.float32, device=self.device)    # reduction scratch, per lane
         self.criterionGAN = functools.partial(criterion_GAN, use_sigmoid=opt.use_sigmoid)
         self.criterionCycle = torch.nn.functional.l1_loss
         self.dp = None                 # parallel.DataParallelPlan when running one process per GPU
@@ -419,12 +419,15 @@ class AugmentedCycleGAN(_FusedCycleModel):
     def _step_device(self, real_A, real_B, prior_z_B):
         """Everything of train_instance that runs on the device (capturable).
 
-        The step is issued as a DAG over three lanes (ops.Lanes: parallel CUDA streams, parallel branches of the
-        captured graph): lanes 0 and 1 carry the two generators and the image discriminators, lane 2 the launch-bound
-        small networks (E_B, D_z_B), whose kernels fill SMs the big convolutions leave idle.  Each network's
-        forwards / backwards stay on one lane or are ordered by events (BatchNorm running statistics, gradient
-        accumulation into the arena); scratch buffers are per lane.  Issue order below is a valid serial schedule
-        and equals the reference order of model.py:402-515 up to commuting independent operations."""
+        The step is issued as a DAG over five lanes (ops.Lanes: parallel CUDA streams, parallel branches of the
+        captured graph).  Lanes 0 and 1 carry the generator chains: first forward, then -- without waiting for the
+        discriminators -- the cycle forward and its backward, finally the first forward's backward.  Lanes 3 and 4
+        carry D_B and D_A (D pass, Adam, generator-side adversarial forward + dgrad), lane 2 the launch-bound small
+        networks (E_B, D_z_B); their kernels fill the SMs the big convolutions leave idle, and the weight gradients
+        of every backward run on the lanes' companion streams.  Each network's forwards / backwards stay on one
+        lane or are ordered by events (BatchNorm running statistics, gradient accumulation into the arena); scratch
+        buffers are per lane.  The issue order below is a valid serial schedule and equals the reference order of
+        model.py:402-515 up to commuting independent operations."""
         o = self.opt
         n, _, h, w = real_A.shape
         nz = o.nlatent
@@ -472,7 +475,27 @@ class AugmentedCycleGAN(_FusedCycleModel):
         e_f2 = ln.run(1, f2)
         e_f3 = ln.run(2, f3, after=(e_f2,))
 
-        # ---- D pass (model.py:423-452): fake.detach() and real as one 2N batch for the IN discriminators
+        # ---- second generator forwards + their backward (model.py:467-468, 493-494): they need fake_A / fake_B / mu
+        # only, NOT the updated discriminators, so they follow the first forwards on lanes 0 / 1 while the whole D pass
+        # runs beside them on lanes 2-4
+        def g_cyc_0():
+            ops.pack_nchw(r["fake_B"], c13.acts[0], 0)          # rec_A = G_B_A(fake_B)
+            r["rec_A"] = GBA.forward(c13)["out"]
+            ops.loss_l1(r["rec_A"], real_A, o.lambda_A, True, sc, S_CYCA, -1, c13.dyraw[iGo], ws())
+            r["g13"] = GBA.backward(c13, {"out": True}, want_dx=True)                        # d fake_B (halo 3)
+
+        def g_cyc_1():
+            ops.pack_nchw(r["fake_A"], c15.acts[0], 0)          # rec_B = G_A_B(fake_A, post_z_realB)
+            c15.z.copy_(r["mu"].reshape(n, nz))
+            r["rec_B"] = GAB.forward(c15)["out"]
+            ops.loss_l1(r["rec_B"], real_B, o.lambda_B, True, sc, S_CYCB, -1, c15.dyraw[iGAo], ws())
+            r["g15"] = GAB.backward(c15, {"out": True}, want_dx=True, want_dz=True)          # d fake_A (halo 3), dz
+
+        e_b0 = ln.run(0, g_cyc_0)
+        e_b1 = ln.run(1, g_cyc_1, after=(e_f3,))
+
+        # ---- D pass (model.py:423-452): fake.detach() and real as one 2N batch for the IN discriminators; then the
+        # generator-side adversarial terms with the UPDATED discriminators (model.py:457-464) on the same lane
         def d_pair(ex, c, i, fake, real, s_fake, s_true, s_pf, s_pt):
             ops.pack_nchw(fake, c.acts[0].batch_slice(0, n), 0)
             ops.pack_nchw(real, c.acts[0].batch_slice(n, 2 * n), 0)
@@ -482,11 +505,23 @@ class AugmentedCycleGAN(_FusedCycleModel):
             ex.backward(c, {"out": True})
             r[ex] = ar(ex.arena)
 
-        def d_a():
-            d_pair(DA, cdA, iA, r["fake_A"], real_A, S_DFA, S_DTA, S_PFA_D, S_PTA)
+        def step_of(optim, ex, name):
+            wait([r.get(ex)])
+            optim.step(gs, only=(name,))
 
         def d_b():
             d_pair(DB, cdB, iB, r["fake_B"], real_B, S_DFB, S_DTB, S_PFB_D, S_PTB)
+            step_of(self.optimizer_D_B, DB, "netD_B")
+            ops.pack_nchw(r["fake_B"], cgB.acts[0], 0)
+            ops.loss_lsgan(DB.forward(cgB)["out"], 1.0, 1.0, sc, S_GB, S_PFB, cgB.dyraw[iB], ws())
+            r["g11"] = DB.backward(cgB, {"out": True}, want_dx=True, want_dw=False)          # d fake_B
+
+        def d_a():
+            d_pair(DA, cdA, iA, r["fake_A"], real_A, S_DFA, S_DTA, S_PFA_D, S_PTA)
+            step_of(self.optimizer_D_A, DA, "netD_A")
+            ops.pack_nchw(r["fake_A"], cgA.acts[0], 0)
+            ops.loss_lsgan(DA.forward(cgA)["out"], 1.0, 1.0, sc, S_GA, S_PFA, cgA.dyraw[iA], ws())
+            r["g10"] = DA.backward(cgA, {"out": True}, want_dx=True, want_dw=False)          # d fake_A
 
         def d_z():      # batch-norm net: separate calls, reference order
             ops.pack_nchw(r["mu"], cz1.acts[0], 0)
@@ -497,73 +532,32 @@ class AugmentedCycleGAN(_FusedCycleModel):
                 DZ.backward(cz1, {"out": True}, sync_bn=sync_bn)
                 DZ.backward(cz2, {"out": True}, sync_bn=sync_bn)
             r[DZ] = ar(DZ.arena)
-
-        def step_of(optim, ex, name):
-            def f():
-                wait([r.get(ex)])
-                optim.step(gs, only=(name,))
-            return f
-
-        ln.run(0, d_b)
-        ln.run(1, d_a)
-        ln.run(2, d_z)
-        ln.run(0, step_of(self.optimizer_D_B, DB, "netD_B"))
-        ln.run(1, step_of(self.optimizer_D_A, DA, "netD_A"))
-        ln.run(2, step_of(self.optimizer_D_B, DZ, "netD_z_B"))
-
-        # ---- G / E pass with the UPDATED discriminators (model.py:457-515)
-        def g_fwd_0():
-            ops.pack_nchw(r["fake_B"], cgB.acts[0], 0)
-            ops.loss_lsgan(DB.forward(cgB)["out"], 1.0, 1.0, sc, S_GB, S_PFB, cgB.dyraw[iB], ws())
-            ops.pack_nchw(r["fake_B"], c13.acts[0], 0)          # rec_A = G_B_A(fake_B)
-            r["rec_A"] = GBA.forward(c13)["out"]
-            ops.loss_l1(r["rec_A"], real_A, o.lambda_A, True, sc, S_CYCA, -1, c13.dyraw[iGo], ws())
-
-        def g_fwd_1():
-            ops.pack_nchw(r["fake_A"], cgA.acts[0], 0)
-            ops.loss_lsgan(DA.forward(cgA)["out"], 1.0, 1.0, sc, S_GA, S_PFA, cgA.dyraw[iA], ws())
-            ops.pack_nchw(r["fake_A"], c15.acts[0], 0)          # rec_B = G_A_B(fake_A, post_z_realB)
-            c15.z.copy_(r["mu"].reshape(n, nz))
-            r["rec_B"] = GAB.forward(c15)["out"]
-            ops.loss_l1(r["rec_B"], real_B, o.lambda_B, True, sc, S_CYCB, -1, c15.dyraw[iGAo], ws())
-
-        def g_fwd_2():
+            step_of(self.optimizer_D_B, DZ, "netD_z_B")
             ops.pack_nchw(r["mu"], cgZ.acts[0], 0)
             ops.loss_lsgan(DZ.forward(cgZ, sync_bn)["out"], 1.0, 1.0 if o.z_gan else 0.0, sc, S_GZ, -1, cgZ.dyraw[iZ], ws())
-            if o.enc_A_B:                                        # mu_z_fakeB = E_B(cat(real_A, fake_B))
+
+        def e_cyc():    # mu_z_fakeB = E_B(cat(real_A, fake_B)) and its backward (model.py:471-486)
+            if o.enc_A_B:
                 ops.pack_nchw(real_A, c14.acts[0], 0)
                 ops.pack_nchw(r["fake_B"], c14.acts[0], o.input_nc)
             else:
                 ops.pack_nchw(r["fake_B"], c14.acts[0], 0)
             mu_fakeB = E.forward(c14, sync_bn)["mu"]
             ops.loss_l1(mu_fakeB, z_prior4, o.lambda_z_B, False, sc, S_CYCZ, -1, c14.dyraw[i_mu], ws())
-
-        ln.run(0, g_fwd_0)
-        ln.run(1, g_fwd_1, after=(e_f3,))
-        ln.run(2, g_fwd_2, after=(e_f1,))
-
-        def g_bwd_1():
-            r["g15"] = GAB.backward(c15, {"out": True}, want_dx=True, want_dz=True)          # d fake_A (halo 3), dz
-            r["g10"] = DA.backward(cgA, {"out": True}, want_dx=True, want_dw=False)          # d fake_A
-
-        def g_bwd_0():
-            r["g13"] = GBA.backward(c13, {"out": True}, want_dx=True)                        # d fake_B (halo 3)
-            r["g11"] = DB.backward(cgB, {"out": True}, want_dx=True, want_dw=False)          # d fake_B
-
-        def g_bwd_2a():
             r["g14"] = E.backward(c14, {"mu": True}, want_dx=True, sync_bn=sync_bn)          # channels 3..5: d fake_B
             r["g12"] = DZ.backward(cgZ, {"out": True}, want_dx=True, want_dw=False, sync_bn=sync_bn)   # d post_z
 
-        def g_bwd_2b():
+        def e_first():
             # d mu_z_realB = D_z dgrad + dz of F15's CIN projections -> seed of F3's mu head
             ops.grad_gather([r["g12"]], [0], nz, out=c3.dyraw[i_mu], add_nchw=c15.dz)
             r["g3"] = E.backward(c3, {"mu": True}, want_dx=True, sync_bn=sync_bn)            # channels 0..2: d fake_A
             r[E] = ar(E.arena)
 
-        e_b1 = ln.run(1, g_bwd_1)
-        e_b0 = ln.run(0, g_bwd_0)
-        e_b2a = ln.run(2, g_bwd_2a)
-        e_b2b = ln.run(2, g_bwd_2b, after=(e_b1,))
+        e_db = ln.run(3, d_b, after=(e_f1,))
+        e_da = ln.run(4, d_a, after=(e_f2,))
+        ln.run(2, d_z)
+        e_b2a = ln.run(2, e_cyc, after=(e_f1,))
+        e_b2b = ln.run(2, e_first, after=(e_b1,))
 
         def g_last_0():
             cB = o.input_nc if o.enc_A_B else 0
@@ -576,11 +570,11 @@ class AugmentedCycleGAN(_FusedCycleModel):
             GBA.backward(c2, {"out": True})
             r[GBA] = ar(GBA.arena)
 
-        ln.run(0, g_last_0, after=(e_b2a, e_b1))       # e_b1: c15's backward wrote G_A_B's gradient arena
-        ln.run(1, g_last_1, after=(e_b2b, e_b0))       # e_b0: c13's backward wrote G_B_A's gradient arena
-        ln.run(0, step_of(self.optimizer_G_B, GAB, "netG_A_B"))
-        ln.run(1, step_of(self.optimizer_G_A, GBA, "netG_B_A"))
-        ln.run(2, step_of(self.optimizer_G_B, E, "netE_B"))
+        ln.run(0, g_last_0, after=(e_b2a, e_db, e_b1))     # e_b1: c15's backward wrote G_A_B's gradient arena
+        ln.run(1, g_last_1, after=(e_b2b, e_da, e_b0))     # e_b0: c13's backward wrote G_B_A's gradient arena
+        ln.run(0, lambda: step_of(self.optimizer_G_B, GAB, "netG_A_B"))
+        ln.run(1, lambda: step_of(self.optimizer_G_A, GBA, "netG_B_A"))
+        ln.run(2, lambda: step_of(self.optimizer_G_B, E, "netE_B"))
         ln.end()
         return OrderedDict([('real_A', real_A), ('fake_B', r["fake_B"]), ('rec_A', r["rec_A"]),
                             ('real_B', real_B), ('fake_A', r["fake_A"]), ('rec_B', r["rec_B"])])
@@ -769,8 +763,8 @@ class StochCycleGAN(_FusedCycleModel):
         return ins
 
     def _step_device(self, real_A, real_B, prior_z_B):
-        """model.py:126-208 on the device (capturable), issued over two lanes like AugmentedCycleGAN._step_device:
-        lane 0 carries G_A_B's first forward / D_B / G_B_A(fake_B), lane 1 the mirror image."""
+        """model.py:126-208 on the device (capturable), issued over four lanes like AugmentedCycleGAN._step_device:
+        lanes 0 / 1 carry the generator chains, lanes 3 / 4 the D_B / D_A passes."""
         o = self.opt
         n, _, h, w = real_A.shape
         nz = o.nlatent
@@ -801,8 +795,8 @@ class StochCycleGAN(_FusedCycleModel):
             ops.pack_nchw(real_B, c2.acts[0], 0)
             r["fake_A"] = GBA.forward(c2)["out"]
 
-        ln.run(0, f1)
-        ln.run(1, f2)
+        e_f1 = ln.run(0, f1)
+        e_f2 = ln.run(1, f2)
 
         # ---- D pass (model.py:137-163): fake.detach() and real as one 2N batch (instance statistics are per sample)
         def d_pair(ex, c, i, fake, real, s_fake, s_true, s_pf, s_pt):
@@ -820,34 +814,39 @@ class StochCycleGAN(_FusedCycleModel):
                 optim.step(gs, only=(name,))
             return f
 
-        e_f1 = ln.run(0, lambda: d_pair(DB, cdB, iB, r["fake_B"], real_B, S_DFB, S_DTB, S_PFB_D, S_PTB))
-        e_f2 = ln.run(1, lambda: d_pair(DA, cdA, iA, r["fake_A"], real_A, S_DFA, S_DTA, S_PFA_D, S_PTA))
-        ln.run(0, step_of(self.optimizer_D, DB, "netD_B"))
-        ln.run(1, step_of(self.optimizer_D, DA, "netD_A"))
-
-        # ---- G pass with the UPDATED discriminators (model.py:165-191)
-        def g_fwd_0():
+        def d_b():
+            d_pair(DB, cdB, iB, r["fake_B"], real_B, S_DFB, S_DTB, S_PFB_D, S_PTB)
+            step_of(self.optimizer_D, DB, "netD_B")()
             ops.pack_nchw(r["fake_B"], cgB.acts[0], 0)
             ops.loss_lsgan(DB.forward(cgB)["out"], 1.0, 1.0, sc, S_GB, S_PFB, cgB.dyraw[iB], ws())
+            r["g11"] = DB.backward(cgB, {"out": True}, want_dx=True, want_dw=False)          # d fake_B
+
+        def d_a():
+            d_pair(DA, cdA, iA, r["fake_A"], real_A, S_DFA, S_DTA, S_PFA_D, S_PTA)
+            step_of(self.optimizer_D, DA, "netD_A")()
+            ops.pack_nchw(r["fake_A"], cgA.acts[0], 0)
+            ops.loss_lsgan(DA.forward(cgA)["out"], 1.0, 1.0, sc, S_GA, S_PFA, cgA.dyraw[iA], ws())
+            r["g10"] = DA.backward(cgA, {"out": True}, want_dx=True, want_dw=False)          # d fake_A
+
+        # ---- cycle forwards + backward (model.py:175-180): independent of the discriminators, so they follow the
+        # first forwards on lanes 0 / 1 while the D pass and the adversarial terms run beside them on lanes 3 / 4
+        def g_cyc_0():
             ops.pack_nchw(r["fake_B"], c13.acts[0], 0)          # rec_A = G_B_A(fake_B)
             r["rec_A"] = GBA.forward(c13)["out"]
             ops.loss_l1(r["rec_A"], real_A, o.lambda_A, True, sc, S_CYCA, -1, c13.dyraw[iGo], ws())
             r["g13"] = GBA.backward(c13, {"out": True}, want_dx=True)                        # d fake_B
-            r["g11"] = DB.backward(cgB, {"out": True}, want_dx=True, want_dw=False)          # d fake_B
 
-        def g_fwd_1():
-            ops.pack_nchw(r["fake_A"], cgA.acts[0], 0)
-            ops.loss_lsgan(DA.forward(cgA)["out"], 1.0, 1.0, sc, S_GA, S_PFA, cgA.dyraw[iA], ws())
+        def g_cyc_1():
             ops.pack_nchw(r["fake_A"], c15.acts[0], 0)          # rec_B = G_A_B(fake_A, z)
             c15.z.copy_(z)
             r["rec_B"] = GAB.forward(c15)["out"]
             ops.loss_l1(r["rec_B"], real_B, o.lambda_B, True, sc, S_CYCB, -1, c15.dyraw[iGAo], ws())
             r["g15"] = GAB.backward(c15, {"out": True}, want_dx=True)                        # d fake_A
-            r["g10"] = DA.backward(cgA, {"out": True}, want_dx=True, want_dw=False)          # d fake_A
 
-        # c13 runs G_B_A (lane 1 produced fake_A with it: read-only) on fake_B from lane 0, and vice versa
-        e_b0 = ln.run(0, g_fwd_0)
-        e_b1 = ln.run(1, g_fwd_1)
+        e_b0 = ln.run(0, g_cyc_0)
+        e_b1 = ln.run(1, g_cyc_1)
+        e_db = ln.run(3, d_b, after=(e_f1,))
+        e_da = ln.run(4, d_a, after=(e_f2,))
 
         def g_last_0():
             ops.grad_gather([r["g13"], r["g11"]], [0, 0], o.output_nc, out=c1.dyraw[iGAo], tanh_y=r["fake_B"])
@@ -859,8 +858,8 @@ class StochCycleGAN(_FusedCycleModel):
             GBA.backward(c2, {"out": True})
             r[GBA] = ar(GBA.arena)
 
-        ln.run(0, g_last_0, after=(e_b1,))      # e_b1: c15's backward wrote G_A_B's gradient arena
-        ln.run(1, g_last_1, after=(e_b0,))      # e_b0: c13's backward wrote G_B_A's gradient arena
+        ln.run(0, g_last_0, after=(e_db, e_b1))      # e_b1: c15's backward wrote G_A_B's gradient arena
+        ln.run(1, g_last_1, after=(e_da, e_b0))      # e_b0: c13's backward wrote G_B_A's gradient arena
         ln.run(0, step_of(self.optimizer_G, GAB, "netG_A_B"))
         ln.run(1, step_of(self.optimizer_G, GBA, "netG_B_A"))
         ln.end()

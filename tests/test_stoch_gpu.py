@@ -276,6 +276,6 @@ def test_checkpoint_reference_format_roundtrip(tmp_path):
     topt.load_state_dict(saved["optimizer_G_B"])
     assert topt.param_groups[0]["lr"] == pytest.approx(2e-4)
     some = topt.state[params[0]]
-    assert int(some["step"]) == 3 and some["exp_avg"].shape == params[0].shape
+    assert int(some["step"]) == 2 and some["exp_avg"].shape == params[0].shape
     for name in onets.NET_NAMES:
         assert set(state[name].keys()) <= set(saved[name].keys()), name
