@@ -37,7 +37,7 @@ class PackItem(C.Structure):
     _fields_ = [("src", C.c_void_p), ("dst", C.c_void_p), ("rows", C.c_int32), ("rows_p", C.c_int32),
                 ("cols", C.c_int32), ("cols_p", C.c_int32), ("taps", C.c_int32), ("srs", C.c_int32),
                 ("scs", C.c_int32), ("dtype", C.c_int32), ("fold_kw", C.c_int32), ("fold_flip", C.c_int32),
-                ("fold_fc", C.c_int32), ("reserved", C.c_int32)]
+                ("fold_fc", C.c_int32), ("s2d_k", C.c_int32)]
 
 
 _lib = None
@@ -60,6 +60,8 @@ _SIGS = {
     "dtg_cin_affine_bwd": (C.c_int, [_P, _P, _P, _P, _P, _P, C.c_int, C.c_int, C.c_int, _P, _P, _P, _P, _P, _P]),
     "dtg_pack_nchw": (C.c_int, [_P, _P, C.c_int, C.c_int, C.c_int, C.c_int, C.POINTER(Plane), C.c_int, C.c_int, _P]),
     "dtg_unpack_nchw": (C.c_int, [C.POINTER(Plane), C.c_int, C.c_int, _P, _P]),
+    "dtg_pack_nchw_s2d": (C.c_int, [_P, C.c_int, C.c_int, C.c_int, C.c_int, C.POINTER(Plane), C.c_int, C.c_int, _P]),
+    "dtg_s2d_unfold_add": (C.c_int, [_P, _P, C.c_int, C.c_int, C.c_int, C.c_int, _P]),
     "dtg_grad_gather": (C.c_int, [C.POINTER(C.POINTER(Plane)), C.POINTER(C.c_int), C.c_int, _P, _P, C.c_int,
                                   C.POINTER(Plane), _P, _P]),
     "dtg_channel_sum": (C.c_int, [C.POINTER(Plane), C.c_int, _P, _P, _P]),

@@ -35,7 +35,15 @@ __global__ void pack_weights_kernel(const dtg_pack_item* items) {
     const int r = (i / it.cols_p) % it.rows_p;
     const int t = i / (it.cols_p * it.rows_p);
     float v = 0.f;
-    if (it.fold_kw > 0) {
+    if (it.s2d_k > 0) {
+      // space-to-depth view of a stride-2, pad-1 KxK filter (K = 3 or 4) as a stride-1 3x3 filter over 2x2 pixel
+      // blocks: tap (DY, DX), column (dy*2 + dx) * cp + b  <-  w[r][b][kh = 2*DY + dy - 1][kw = 2*DX + dx - 1]
+      const int cp = it.fold_fc, K = it.s2d_k;
+      const int sub = c / cp, b = c % cp;
+      const int kh = 2 * (t / 3) + (sub >> 1) - 1, kw = 2 * (t % 3) + (sub & 1) - 1;
+      if (r < it.rows && b < it.cols && sub < 4 && kh >= 0 && kh < K && kw >= 0 && kw < K)
+        v = it.src[((static_cast<size_t>(r) * it.srs + static_cast<size_t>(b) * it.scs) * K + kh) * K + kw];
+    } else if (it.fold_kw > 0) {
       const int j = c / it.fold_fc, b = c % it.fold_fc;
       if (r < it.rows && j < it.fold_kw && b < it.cols) {
         const int kw = it.fold_flip ? it.fold_kw - 1 - j : j;
@@ -74,6 +82,39 @@ __global__ void pack_nchw_kernel(const float* __restrict__ src, const float* __r
           st_elem(dst.ptr, pix * dst.c + c_off + ch, dst.dtype, v);
         }
     }
+  }
+}
+
+// NCHW fp32 -> space-to-depth plane [n][h/2][w/2][4*cp]: pixel (y, x) channel ch lands in block (y/2, x/2), channel
+// ((y&1)*2 + (x&1)) * cp + c_off + ch.  One thread per (n, h, w).
+__global__ void pack_nchw_s2d_kernel(const float* __restrict__ src, int n, int c, int h, int w, dtg_plane dst, int cp, int c_off) {
+  pdl_enter();
+  const size_t total = static_cast<size_t>(n) * h * w;
+  for (size_t i = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; i < total;
+       i += static_cast<size_t>(gridDim.x) * blockDim.x) {
+    const int x = i % w;
+    const int y = (i / w) % h;
+    const int b = i / (static_cast<size_t>(w) * h);
+    const size_t pix = (static_cast<size_t>(b) * dst.h + (y >> 1)) * dst.w + (x >> 1);
+    const int sub = (y & 1) * 2 + (x & 1);
+    for (int ch = 0; ch < c; ++ch)
+      st_elem(dst.ptr, pix * dst.c + sub * cp + c_off + ch, dst.dtype, src[((static_cast<size_t>(b) * c + ch) * h + y) * w + x]);
+  }
+}
+
+// dw[co][b][kh][kw] += dw2[co][(dy*2+dx)*cp + b][DY][DX] for the space-to-depth filter view above; dw2 is cleared
+// (every element, also the structurally-zero ones) so that the next accumulation starts from zero.
+__global__ void s2d_unfold_add_kernel(float* __restrict__ dw2, float* __restrict__ dw, int cout, int cin, int K, int cp) {
+  pdl_enter();
+  const int total = cout * 4 * cp * 9;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
+    const int t = i % 9;
+    const int col = (i / 9) % (4 * cp);
+    const int co = i / (9 * 4 * cp);
+    const int sub = col / cp, b = col % cp;
+    const int kh = 2 * (t / 3) + (sub >> 1) - 1, kw = 2 * (t % 3) + (sub & 1) - 1;
+    if (b < cin && kh >= 0 && kh < K && kw >= 0 && kw < K) dw[((static_cast<size_t>(co) * cin + b) * K + kh) * K + kw] += dw2[i];
+    dw2[i] = 0.f;
   }
 }
 
@@ -222,6 +263,24 @@ extern "C" int dtg_pack_nchw(const float* src, const float* tanh_y, int n, int c
   DTG_REQUIRE(dst->n == n && dst->h == h && dst->w == w && c_off + c <= dst->c, "dtg_pack_nchw: shape mismatch");
   const size_t total = static_cast<size_t>(n) * h * w;
   DTG_CHECK_CUDA(launch_k(pack_nchw_kernel, grid_for(total, 256), 256, 0, static_cast<cudaStream_t>(stream), src, tanh_y, n, c, h, w, *dst, c_off, reflect));
+  return DTG_OK;
+}
+
+extern "C" int dtg_pack_nchw_s2d(const float* src, int n, int c, int h, int w, const dtg_plane* dst, int cp, int c_off,
+                                 void* stream) {
+  DTG_REQUIRE(src && dst && dst->ptr, "dtg_pack_nchw_s2d: null");
+  DTG_REQUIRE(h % 2 == 0 && w % 2 == 0 && dst->n == n && dst->h == h / 2 && dst->w == w / 2 && dst->halo == 0 &&
+                  dst->c == 4 * cp && c_off + c <= cp,
+              "dtg_pack_nchw_s2d: shape mismatch");
+  const size_t total = static_cast<size_t>(n) * h * w;
+  DTG_CHECK_CUDA(launch_k(pack_nchw_s2d_kernel, grid_for(total, 256), 256, 0, static_cast<cudaStream_t>(stream), src, n, c, h, w, *dst, cp, c_off));
+  return DTG_OK;
+}
+
+extern "C" int dtg_s2d_unfold_add(float* dw2, float* dw, int cout, int cin, int k, int cp, void* stream) {
+  DTG_REQUIRE(dw2 && dw && cout > 0 && cin > 0 && cin <= cp && (k == 3 || k == 4), "dtg_s2d_unfold_add: bad args");
+  const size_t total = static_cast<size_t>(cout) * 4 * cp * 9;
+  DTG_CHECK_CUDA(launch_k(s2d_unfold_add_kernel, grid_for(total, 256), 256, 0, static_cast<cudaStream_t>(stream), dw2, dw, cout, cin, k, cp));
   return DTG_OK;
 }
 

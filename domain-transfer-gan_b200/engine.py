@@ -6,12 +6,15 @@ A network (networks.py) is described as a chain of ``Layer`` specs (conv [+ norm
 arithmetic happens here.  Gradients are accumulated straight into the flat fp32 gradient arena in
 PyTorch parameter layout, so ``param.grad`` views and the fused clip+Adam kernel see them in place.
 """
+import os
+
 import torch
 
 from . import _lib as L
 from . import ops
 
 _PRECISION = {"dtype": torch.bfloat16}
+S2D = os.environ.get("DTG_NO_S2D") is None      # space-to-depth execution of the stride-2 input layers
 
 
 def set_precision(name):
@@ -123,6 +126,9 @@ class Layer:
         # fold_in : the INPUT is a 16-byte-per-pixel plane  -> forward conv and wgrad read it kw-folded
         # fold_out: the OUTPUT gradient is (head with <= fc channels) -> dgrad and wgrad read dy kw-folded
         self.fold_in = self.fold_out = False
+        # space-to-depth execution of a stride-2 first layer with a <= 64-byte input pixel (decided in
+        # NetExec.prepare): the input plane is stored as 2x2 pixel blocks, forward conv and wgrad run as stride-1 3x3
+        self.s2d = False
 
     def out_hw(self, h, w):
         if self.transposed:       # k3 s2 p1 op1 -> exactly 2x
@@ -162,14 +168,24 @@ class NetExec:
             self.dtype = dtype
             self.pack = ops.PackTable(self.arena.device)
             fc = ops.fold_channels(dtype)
+            cp = ops.cpad_small(self.in_channels, dtype)
+            first = [ly for ly in self.layers if ly.src == 0]
+            s2d_ok = (S2D and self.in_halo == 0 and 4 * cp * (2 if dtype == torch.bfloat16 else 4) <= 256 and
+                      all((not ly.transposed) and ly.stride == 2 and ly.pad == 1 and ly.k in (3, 4) and
+                          ly.conv.weight.dim() == 4 for ly in first))
+            self.s2d_cp = cp if (s2d_ok and first) else 0
             for ly in self.layers:
+                ly.s2d = bool(self.s2d_cp) and ly.src == 0
                 w = ly.conv.weight
                 w4 = w if w.dim() == 4 else w.view(w.shape[0], w.shape[1], 1, 1)
                 foldable = (not ly.transposed) and ly.stride == 1 and 3 < ly.k <= 8 and 2 * ly.pad == ly.k - 1
                 ly.fold_in = foldable and ly.src == 0 and ly.cin <= fc and self.in_channels <= fc and self.in_halo >= ly.pad
                 src_halo = self.in_halo if ly.src == 0 else self.layers[ly.src - 1].out_halo
                 ly.fold_out = foldable and ly.head and ly.cout <= fc and not ly.fold_in and src_halo == 0
-                if ly.fold_in:
+                if ly.s2d:
+                    ly.w_f = ops.add_packed(self.pack, w4, dtype, "fwd_s2d", s2d_cp=cp)
+                    ly.w_d = ops.add_packed(self.pack, w4, dtype, "dgrad")
+                elif ly.fold_in:
                     ly.w_f = ops.add_packed(self.pack, w4, dtype, "fwd_fold")
                     ly.w_d = ops.add_packed(self.pack, w4, dtype, "dgrad")
                 elif ly.fold_out:
@@ -196,7 +212,14 @@ class NetExec:
         dt, dev = self.dtype, self.arena.device
         c = Ctx()
         c.n = n
-        c.acts[0] = ops.PlaneT(n, h, w, ops.cpad_small(self.in_channels, dt), self.in_halo, dt, dev)
+        if self.s2d_cp:
+            if h % 2 or w % 2:
+                raise ValueError("dtg_b200: the stride-2 input layers need even image extents, got %dx%d" % (h, w))
+            c.acts[0] = ops.PlaneT(n, h // 2, w // 2, 4 * self.s2d_cp, 0, dt, dev, s2d=self.s2d_cp)
+            c.s2d_dw2 = {i: torch.zeros(ly.cout * 4 * self.s2d_cp * 9, dtype=torch.float32, device=dev)
+                         for i, ly in enumerate(self.layers) if ly.s2d}
+        else:
+            c.acts[0] = ops.PlaneT(n, h, w, ops.cpad_small(self.in_channels, dt), self.in_halo, dt, dev)
         dims = {0: (h, w)}
         for i, ly in enumerate(self.layers):
             ih, iw = dims[ly.src]
@@ -231,7 +254,11 @@ class NetExec:
         key = (idx, consumer)
         if key not in c.gact:
             a = c.acts[idx]
-            c.gact[key] = ops.PlaneT(a.n, a.h, a.w, a.c, a.halo, a.dtype, a.t.device)
+            if idx == 0 and self.s2d_cp:      # the input gradient keeps the ordinary pixel layout
+                h, w = c.dims[0]
+                c.gact[key] = ops.PlaneT(a.n, h, w, self.s2d_cp, 0, a.dtype, a.t.device)
+            else:
+                c.gact[key] = ops.PlaneT(a.n, a.h, a.w, a.c, a.halo, a.dtype, a.t.device)
         return c.gact[key]
 
     def _dres(self, c, idx):
@@ -250,6 +277,8 @@ class NetExec:
             mode = L.CONV_DGRAD if ly.transposed else L.CONV_FWD
             kw = dict(mode=mode, kh=ly.k, kw=ly.k, stride=ly.stride, pad=ly.pad, cout=ly.cout, out_h=oh, out_w=ow,
                       cin=ly.cin, fold_w=ly.fold_in)
+            if ly.s2d:      # stride-1 3x3 over 2x2 pixel blocks; cin keeps the algorithmic FLOP count of the KxK filter
+                kw.update(kh=3, kw=3, stride=1, pad=1, cin=ly.cin * ly.k * ly.k / 9.0)
             bias = ly.conv.bias if ly.use_bias else None
             if ly.head:
                 ops.conv(a_in, ly.w_f, bias, None, act=ly.act, out_nchw=c.heads[ly.name], **kw)
@@ -342,7 +371,7 @@ class NetExec:
                     pending[ly.residual] = (d_res, d1) if d0 is None else (d0, d_res)
             # weight gradient
             if want_dw:
-                ops.off_chain(self._wgrad_fn(ly, a_in, dyr, A.g(ly.conv.weight)))
+                ops.off_chain(self._wgrad_fn(ly, a_in, dyr, A.g(ly.conv.weight), c.s2d_dw2[i] if ly.s2d else None))
             # data gradient
             if ly.src > 0 or want_dx:
                 gin = self._gact(c, ly.src, i)
@@ -362,8 +391,13 @@ class NetExec:
         return pending.get(0, (None, None))[0] if want_dx else None
 
     @staticmethod
-    def _wgrad_fn(ly, a_in, dyr, dw):
+    def _wgrad_fn(ly, a_in, dyr, dw, dw2=None):
         """the weight gradient of one layer: off the norm-backward / dgrad chain (ops.off_chain)"""
+        if ly.s2d:
+            def f():
+                ops.conv_wgrad(dyr, a_in, dw2, kh=3, kw=3, stride=1, pad=1, pa=ly.cout, qb=a_in.c)
+                ops.s2d_unfold_add(dw2, dw, a_in.s2d)
+            return f
         if ly.transposed:
             return lambda: ops.conv_wgrad(a_in, dyr, dw, kh=ly.k, kw=ly.k, stride=ly.stride, pad=ly.pad, pa=ly.cin,
                                           qb=ly.cout)

@@ -151,10 +151,12 @@ def cpad_small(c, dtype):
 class PlaneT:
     """NHWC activation / gradient buffer with optional halo ring: tensor [n, h+2*halo, w+2*halo, c]."""
 
-    __slots__ = ("t", "n", "h", "w", "c", "halo", "dtype", "_s", "_buf")
+    __slots__ = ("t", "n", "h", "w", "c", "halo", "dtype", "_s", "_buf", "s2d")
 
-    def __init__(self, n, h, w, c, halo=0, dtype=torch.bfloat16, device="cuda"):
+    def __init__(self, n, h, w, c, halo=0, dtype=torch.bfloat16, device="cuda", s2d=0):
         self.n, self.h, self.w, self.c, self.halo, self.dtype = n, h, w, c, halo, dtype
+        # s2d = cp > 0: space-to-depth plane of a [n, 2h, 2w, cp] image (c == 4*cp); pack_nchw fills it accordingly
+        self.s2d = s2d
         # 256 bytes of zero slack behind the plane: kw-folded TMA views read one 128-byte row past the last pixel
         numel = n * (h + 2 * halo) * (w + 2 * halo) * c
         self._buf = torch.zeros(numel + 256 // torch.empty((), dtype=dtype).element_size(), dtype=dtype, device=device)
@@ -177,6 +179,7 @@ class PlaneT:
         v = PlaneT.__new__(PlaneT)
         v.n, v.h, v.w, v.c, v.halo, v.dtype = i1 - i0, self.h, self.w, self.c, self.halo, self.dtype
         v.t = self.t[i0:i1]
+        v.s2d = self.s2d
         v._buf = self._buf
         v._s = L.Plane(v.t.data_ptr(), v.n, v.h, v.w, v.c, v.halo, _DT[self.dtype])
         return v
@@ -197,8 +200,19 @@ def pack_nchw(src, dst, c_off=0, tanh_y=None, reflect=True):
     """reflect=False leaves dst's halo untouched (zero padding: planes are zero-initialised)"""
     n, c, h, w = src.shape
     assert src.dtype == torch.float32 and src.is_contiguous()
+    if getattr(dst, "s2d", 0):
+        assert tanh_y is None
+        L.check(L.lib().dtg_pack_nchw_s2d(_ptr(src), n, c, h, w, dst.s, dst.s2d, c_off, _stream()), "pack_nchw_s2d")
+        return
     L.check(L.lib().dtg_pack_nchw(_ptr(src), _ptr(tanh_y), n, c, h, w, dst.s, c_off, 1 if reflect else 0, _stream()),
             "pack_nchw")
+
+
+def s2d_unfold_add(dw2, dw, cp):
+    """dw [cout][cin][k][k] += the space-to-depth weight gradient dw2 [cout][4*cp][3][3]; clears dw2"""
+    cout, cin, k, _ = dw.shape
+    assert dw2.numel() == cout * 4 * cp * 9 and dw2.dtype == torch.float32 and dw.dtype == torch.float32
+    L.check(L.lib().dtg_s2d_unfold_add(_ptr(dw2), _ptr(dw), cout, cin, k, cp, _stream()), "s2d_unfold_add")
 
 
 def unpack_nchw(src, c, c_off=0, out=None):
@@ -218,7 +232,7 @@ class PackTable:
         self.max_elems = 0
         self.device = device
 
-    def add(self, src, rows, cols, taps, srs, scs, dtype, fold_kw=0, fold_flip=False):
+    def add(self, src, rows, cols, taps, srs, scs, dtype, fold_kw=0, fold_flip=False, s2d_k=0, s2d_cp=0):
         """src: fp32 tensor (PyTorch layout, contiguous).  Returns the packed destination tensor
         [taps, rows_p, cols_p] with dst[t][r][c] = src.flat[(r*srs + c*scs)*taps + t].
         fold_kw = KW > 0: kw-folded packing (taps = KH): dst[kh][r][j*fc + b] = src.flat[((r*srs + b*scs)*KH + kh)*KW + kw(j)],
@@ -227,9 +241,12 @@ class PackTable:
         q = 8 if dtype == torch.bfloat16 else 4
         cols_p = 8 * q if fold_kw else (cols + q - 1) // q * q
         assert not fold_kw or (cols <= q and fold_kw <= 8)
+        if s2d_k:       # dtg_pack_item.s2d_k: 9 taps, 4 * cp columns
+            assert taps == 9 and cols <= s2d_cp and not fold_kw
+            cols_p = 4 * s2d_cp
         dst = torch.zeros(taps, rows_p, cols_p, dtype=dtype, device=self.device)
         self.items.append(L.PackItem(src.data_ptr(), dst.data_ptr(), rows, rows_p, cols, cols_p, taps, srs, scs,
-                                     _DT[dtype], fold_kw, 1 if fold_flip else 0, q, 0))
+                                     _DT[dtype], fold_kw, 1 if fold_flip else 0, s2d_cp if s2d_k else q, s2d_k))
         self.keep.append((src, dst))
         self.max_elems = max(self.max_elems, dst.numel())
         self.dev = None
@@ -259,9 +276,11 @@ def pack_conv_weight(w, dtype, kind):
     return dst
 
 
-def add_packed(tab, w, dtype, kind):
+def add_packed(tab, w, dtype, kind, s2d_cp=0):
     d0, d1, kh, kw = w.shape
     taps = kh * kw
+    if kind == "fwd_s2d":              # stride-2 pad-1 first layer over a space-to-depth input plane
+        return tab.add(w, d0, d1, 9, d1, 1, dtype, s2d_k=kh, s2d_cp=s2d_cp)
     if kind in ("fwd", "tdgrad"):      # rows = dim0, cols = dim1
         return tab.add(w, d0, d1, taps, d1, 1, dtype)
     if kind in ("dgrad", "tfwd"):      # rows = dim1, cols = dim0

@@ -65,7 +65,13 @@ typedef struct dtg_pack_item {
   const float* src;
   void* dst;
   int32_t rows, rows_p, cols, cols_p, taps, srs, scs, dtype;
-  int32_t fold_kw, fold_flip, fold_fc, reserved;
+  int32_t fold_kw, fold_flip, fold_fc;
+  /* K > 0: space-to-depth packing of a stride-2, pad-1 KxK filter (K = 3 or 4) whose input has <= fold_fc channel
+   * slots per pixel (fold_fc = channels of the 16..64-byte pixel): taps = 9, dst[DY*3+DX][r][(dy*2+dx)*fold_fc + b] =
+   * w[r][b][2*DY+dy-1][2*DX+dx-1] (zero outside the filter).  With the input stored by dtg_pack_nchw_s2d the
+   * strided convolution becomes a stride-1 3x3 convolution over 2x2 pixel blocks (first layers of
+   * Discriminator / Discriminator_edges / LatentEncoder, networks.py:322,366,446). */
+  int32_t s2d_k;
 } dtg_pack_item;
 int dtg_pack_weights(const dtg_pack_item* items_dev, int nitems, int max_elems, void* stream);
 
@@ -196,6 +202,13 @@ int dtg_cin_affine_bwd(const float* z, const float* ws, const float* wb, const f
 int dtg_pack_nchw(const float* src, const float* tanh_y, int n, int c, int h, int w, const dtg_plane* dst, int c_off,
                   int reflect /* 1: mirror into dst.halo; 0: leave the halo untouched (zero padding) */, void* stream);
 int dtg_unpack_nchw(const dtg_plane* src, int c_off, int c, float* dst, void* stream);
+/* Space-to-depth variant for the 3/6-channel inputs of the stride-2 first layers (networks.py:322,366,446):
+ * dst is [n][h/2][w/2][4*cp] (halo 0); pixel (y,x) channel ch is stored in block (y/2, x/2) at channel
+ * ((y&1)*2 + (x&1))*cp + c_off + ch.  TMA then reads contiguous rows instead of gathering every other pixel. */
+int dtg_pack_nchw_s2d(const float* src, int n, int c, int h, int w, const dtg_plane* dst, int cp, int c_off, void* stream);
+/* Weight gradient of such a layer: dtg_conv_wgrad on the space-to-depth plane yields dw2 [cout][4*cp][3][3]; this
+ * adds its entries to the PyTorch-layout gradient dw [cout][cin][k][k] (k = 3 or 4) and clears dw2. */
+int dtg_s2d_unfold_add(float* dw2, float* dw, int cout, int cin, int k, int cp, void* stream);
 
 /* Sum of up to 3 gradient planes (each optionally with a halo to fold, channel offset c_off[i]),
  * optionally multiplied by tanh'(y) = 1 - y^2 (y dense NCHW fp32, the generator output), written to

@@ -18,16 +18,21 @@ CASES = {  # cin, cout, h, k, s, pad, halo, mode
     "db3": (256, 256, 15, 4, 1, 1, 0, "fwd"), "down": (64, 128, 64, 3, 2, 1, 0, "fwd"),
     "res_wgrad": (128, 128, 32, 3, 1, 1, 1, "wgrad"), "c7in_wgrad": (3, 32, 64, 7, 1, 3, 3, "wgrad"),
     "c3b_wgrad": (64, 32, 64, 3, 1, 1, 0, "wgrad"), "c7out_dgrad": (32, 3, 64, 7, 1, 3, 0, "dgrad"),
+    "db0": (3, 64, 64, 4, 2, 1, 0, "fwd", 160), "db0_wgrad": (3, 64, 64, 4, 2, 1, 0, "wgrad", 160),
+    "da0": (3, 32, 64, 3, 2, 1, 0, "fwd", 160), "db4": (256, 1, 14, 4, 1, 1, 0, "fwd", 160),
     "c7in_dgrad": (3, 32, 64, 7, 1, 3, 3, "dgrad"), "c7out_wgrad": (32, 3, 64, 7, 1, 3, 0, "wgrad"), "c3a_wgrad": (32, 64, 64, 3, 1, 1, 0, "wgrad"),
 }
-cin, cout, h, k, s, pad, halo, mode = CASES[case]
+cin, cout, h, k, s, pad, halo, mode = CASES[case][:8]
+N = CASES[case][8] if len(CASES[case]) > 8 else N
 oh = (h + 2 * pad - k) // s + 1
 x = ops.PlaneT(N, h, h, ops.cpad(cin, dt), halo, dt); x.t.normal_()
 w = (torch.randn(cout, cin, k, k, generator=g) * 0.05).cuda()
 if mode == "fwd":
     wp = ops.pack_conv_weight(w, dt, "fwd")
     out = ops.PlaneT(N, oh, oh, ops.cpad(cout, dt), 0, dt)
-    f = lambda: ops.conv(x, wp, None, out, kh=k, kw=k, stride=s, pad=pad, cout=cout, out_h=oh, out_w=oh)
+    bias = torch.zeros(cout, device="cuda") if os.environ.get("PROF_BIAS") else None
+    f = lambda: ops.conv(x, wp, bias, out, kh=k, kw=k, stride=s, pad=pad, cout=cout, out_h=oh, out_w=oh,
+                         act=int(os.environ.get("PROF_ACT", "0")))
 elif mode == "dgrad":
     wp = ops.pack_conv_weight(w, dt, "dgrad")
     dy = ops.PlaneT(N, oh, oh, ops.cpad(cout, dt), 0, dt); dy.t.normal_()
