@@ -221,6 +221,39 @@ static void choose_patch(int PW, int PH, int N, int* bw, int* bh, int* bn) {
 
 static int floordiv2(int e) { return (e - (e & 1)) / 2; }
 
+// Mirror the interior of a plane into its halo ring (nn.ReflectionPad2d of the NEXT conv's input).  One thread per
+// (image, ring pixel, 16-byte channel chunk); ring pixels are enumerated as top rows, bottom rows, left / right columns.
+__global__ void __launch_bounds__(256) reflect_halo_kernel(dtg_plane p, int vec_per_pix) {
+  pdl_enter();
+  const int hl = p.halo, Hb = p.h + 2 * hl, Wb = p.w + 2 * hl;
+  const int ring = 2 * hl * Wb + 2 * hl * p.h;
+  const size_t total = static_cast<size_t>(p.n) * ring * vec_per_pix;
+  uint4* base = reinterpret_cast<uint4*>(p.ptr);
+  for (size_t i = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; i < total;
+       i += static_cast<size_t>(gridDim.x) * blockDim.x) {
+    const int v = i % vec_per_pix;
+    const int r = (i / vec_per_pix) % ring;
+    const int n = i / (static_cast<size_t>(vec_per_pix) * ring);
+    int yb, xb;
+    if (r < 2 * hl * Wb) {          // top / bottom rows
+      const int row = r / Wb;
+      xb = r - row * Wb;
+      yb = row < hl ? row : p.h + row;          // rows [0, hl) and [h + hl, h + 2 hl)
+    } else {                        // left / right columns of the interior rows
+      const int q = r - 2 * hl * Wb;
+      const int row = q / (2 * hl), col = q - row * (2 * hl);
+      yb = row + hl;
+      xb = col < hl ? col : p.w + col;
+    }
+    int y = yb - hl, x = xb - hl;
+    y = y < 0 ? -y : (y >= p.h ? 2 * (p.h - 1) - y : y);
+    x = x < 0 ? -x : (x >= p.w ? 2 * (p.w - 1) - x : x);
+    const size_t img = static_cast<size_t>(n) * Hb * Wb;
+    base[(img + static_cast<size_t>(yb) * Wb + xb) * vec_per_pix + v] =
+        base[(img + static_cast<size_t>(y + hl) * Wb + (x + hl)) * vec_per_pix + v];
+  }
+}
+
 template <bool TF32>
 static int launch_igemm(const IgemmParams& p, cudaStream_t stream) {
   static int num_sms = 0;
@@ -253,6 +286,22 @@ using namespace dtg;
 extern "C" int dtg_conv(const dtg_conv_args* a, const dtg_plane* in, const void* w, int w_rows, int w_cols,
                         const float* bias, const dtg_plane* out, float* out_nchw, void* stream) {
   DTG_REQUIRE(a && in && w, "dtg_conv: null argument");
+  {
+    // out_reflect into a plane: the tiles leave through the TMA-store epilogue (which cannot mirror), then one small
+    // kernel fills the halo ring -- faster than the per-thread mirrored stores of the generic epilogue
+    static const bool fused_reflect = getenv("DTG_FUSED_REFLECT") != nullptr;
+    if (a->out_reflect && !a->out_nchw_f32 && !fused_reflect && out && out->ptr && out->halo > 0 &&
+        out->h >= out->halo + 1 && out->w >= out->halo + 1 && (out->c * elem_size(out->dtype)) % 16 == 0) {
+      dtg_conv_args a2 = *a;
+      a2.out_reflect = 0;
+      const int rc = dtg_conv(&a2, in, w, w_rows, w_cols, bias, out, out_nchw, stream);
+      if (rc != DTG_OK) return rc;
+      const int vec = out->c * elem_size(out->dtype) / 16;
+      const size_t total = static_cast<size_t>(out->n) * (2 * out->halo * (out->w + 2 * out->halo) + 2 * out->halo * out->h) * vec;
+      DTG_CHECK_CUDA(launch_k(reflect_halo_kernel, static_cast<int>(std::max<size_t>(1, std::min<size_t>((total + 255) / 256, 148 * 16))), 256, 0, static_cast<cudaStream_t>(stream), *out, vec));
+      return DTG_OK;
+    }
+  }
   DTG_REQUIRE(a->stride == 1 || a->stride == 2, "dtg_conv: stride %d unsupported", a->stride);
   DTG_REQUIRE(a->kh * a->kw <= kMaxTaps && a->kh >= 1 && a->kw >= 1, "dtg_conv: kernel %dx%d unsupported", a->kh, a->kw);
   DTG_REQUIRE(w_rows % 16 == 0 && w_rows >= 16 && w_rows <= 256, "dtg_conv: packed rows %d must be 16..256, multiple of 16", w_rows);
