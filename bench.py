@@ -112,12 +112,13 @@ class ClockSampler(threading.Thread):
 def _ncu_traffic():
     """DRAM bytes per launch (dram__bytes_read.sum + dram__bytes_write.sum) of the residual-stack conv, from the committed
     ncu --set full summary; None when the profile is not in the tree."""
-    try:
-        d = json.load(open(os.path.join(ROOT, "profiles", "r1_ncu_summary.json")))
-        k = d["igemm_kernel_res_conv"]
-        return k["dram_bytes_read"] + k["dram_bytes_write"]
-    except Exception:
-        return None
+    for fn, key in (("r1b_ncu_summary.json", "pconv2_kernel_res_conv"), ("r1_ncu_summary.json", "igemm_kernel_res_conv")):
+        try:
+            k = json.load(open(os.path.join(ROOT, "profiles", fn)))[key]
+            return k["dram_bytes_read"] + k["dram_bytes_write"]
+        except Exception:
+            continue
+    return None
 
 
 def run_reference(args):
@@ -370,7 +371,7 @@ def main():
             line["conv_roofline_frac_of_step"] = (tot_fl / 2) / (ms / K * 1e-3) / (peak * 1e12)
         dom = max(summ, key=lambda k: summ[k]["ms"])
         ach = summ[dom]["flops"] / (summ[dom]["ms"] * 1e-3) / 1e12
-        line["roofline"] = {"bound": "tensor", "kernel": dom + " (conv fwd/dgrad: igemm_kernel + pconv_kernel)" if dom == "igemm_kernel" else dom,
+        line["roofline"] = {"bound": "tensor", "kernel": dom + " (conv fwd/dgrad: igemm_kernel + pconv_kernel + pconv2_kernel)" if dom == "igemm_kernel" else dom,
                             "achieved": ach, "peak": peak, "unit": "TFLOP/s",
                             "frac": ach / peak, "traffic": _ncu_traffic(),
                             "peak_source": "MEASURED_PEAKS.json bf16_tflops_sustained" if peaks else "fallback 1.59 PF x 0.88",

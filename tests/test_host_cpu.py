@@ -89,6 +89,15 @@ def _dp_worker(rank, world, port, q):
     plan.allreduce_arena(arena)
     plan.wait()
     ok &= torch.equal(arena.grad[:6], torch.full((6,), 3.0)) and torch.equal(arena.grad[6:], torch.full((4,), float(rank + 1)))
+    # per-network handles: each optimizer step waits for ITS all-reduce only (the lanes of the fused step)
+    a1 = types.SimpleNamespace(grad=torch.full((4,), float(rank + 1)), active_count=4)
+    a2 = types.SimpleNamespace(grad=torch.full((4,), 10.0 * (rank + 1)), active_count=4)
+    h1, h2 = plan.allreduce_arena(a1), plan.allreduce_arena(a2)
+    ok &= h1 is not None and h2 is not None and len(plan._pending) == 2
+    plan.wait([h2])
+    ok &= torch.equal(a2.grad, torch.full((4,), 30.0)) and len(plan._pending) == 1
+    plan.wait([h1, None])
+    ok &= torch.equal(a1.grad, torch.full((4,), 3.0)) and len(plan._pending) == 0
     # mean of shard gradients = SUM * (1 / world_size), the grad_scale handed to the fused clip+Adam kernel
     ok &= abs(float(arena.grad[0]) / world - 1.5) < 1e-6
     # synchronised batch-norm: per-channel (sum, sumsq) all-reduced in place
