@@ -6,9 +6,9 @@ Host code is Python/PyTorch (device memory, streams, torch.distributed); all ari
 path runs in the hand-written CUDA kernels of ``csrc/`` behind the C ABI of ``include/dtg_b200.h``.
 There is no CPU / eager fallback: every op raises if the extension is missing.
 """
-from . import _lib, engine, model, modules, networks, ops, parallel  # noqa: F401
+from . import _lib, engine, model, modules, networks, ops, parallel, trainer  # noqa: F401
 from .engine import set_precision  # noqa: F401
 from .model import AugmentedCycleGAN, StochCycleGAN  # noqa: F401
 
-__all__ = ["_lib", "ops", "engine", "modules", "networks", "model", "parallel", "set_precision", "AugmentedCycleGAN",
+__all__ = ["_lib", "ops", "engine", "modules", "networks", "model", "parallel", "trainer", "set_precision", "AugmentedCycleGAN",
            "StochCycleGAN"]

@@ -1,0 +1,265 @@
+"""Training loop and input staging around the fused step: the loop semantics of the reference's
+``train_model`` hot loop (/root/reference/augmented_cyclegan/train.py:185-256, 307-313) and of its in-memory batch
+iterators (dataloader.py:60-149), in Python 3, with the three things a millisecond-scale step needs:
+
+  * ``StagedBatches``: pinned, double-buffered host staging; the host->device copies of batch k+1 run on a copy stream
+    while step k computes (the reference issues three synchronous pageable ``.cuda()`` copies per step, train.py:198-201);
+  * ``prior_z_B`` is drawn on the device (train.py:190 draws it on the host and copies it);
+  * the loss dictionaries are read back only when they are printed (``print_freq``): every other step runs with
+    ``report=False`` and costs no device->host synchronisation (the reference syncs >= 23 times per step, model.py:518-536).
+
+Visualisation (PNG dumps, train.py:47-94) and the per-epoch evaluation (evaluate.py) stay with the caller: ``train_epochs``
+takes them as hooks.  Nothing here touches the arithmetic of the step.
+"""
+import queue
+import threading
+import time
+
+import numpy as np
+import torch
+
+
+# ---- batch iterators (dataloader.py:60-149) ------------------------------------------------------------------------
+class AlignedIterator(object):
+    """Iterate two arrays IN THE SAME ORDER and return dicts of minibatches (dataloader.py:60-110)."""
+
+    def __init__(self, data_A, data_B, **kwargs):
+        assert data_A.shape[0] == data_B.shape[0], 'passed data differ in number!'
+        self.data_A, self.data_B = data_A, data_B
+        self.num_samples = data_A.shape[0]
+        self.batch_size = kwargs.get('batch_size', 100)
+        self.shuffle = kwargs.get('shuffle', False)
+        self.n_batches = self.num_samples // self.batch_size          # Python-2 integer division in the reference
+        if self.num_samples % self.batch_size != 0:
+            self.n_batches += 1
+        self.reset()
+
+    def __iter__(self):
+        return self
+
+    def reset(self):
+        if self.shuffle:
+            self.data_indices = np.random.permutation(self.num_samples)
+        else:
+            self.data_indices = np.arange(self.num_samples)
+        self.batch_idx = 0
+
+    def indices(self):
+        """index arrays of the next batch (what ``next`` gathers), or None at the end of the epoch"""
+        if self.batch_idx == self.n_batches:
+            self.reset()
+            return None
+        idx = self.batch_idx * self.batch_size
+        chosen = self.data_indices[idx:idx + self.batch_size]
+        self.batch_idx += 1
+        return chosen, chosen
+
+    def __next__(self):
+        ix = self.indices()
+        if ix is None:
+            raise StopIteration
+        return {'A': torch.from_numpy(self.data_A[ix[0]]), 'B': torch.from_numpy(self.data_B[ix[1]])}
+
+    next = __next__
+
+    def __len__(self):
+        return self.num_samples
+
+
+class UnalignedIterator(AlignedIterator):
+    """Iterate two arrays IN DIFFERENT ORDER (two independent permutations per epoch); the last batch of an epoch is
+    moved back so that it is full (dataloader.py:112-152)."""
+
+    def __init__(self, data_A, data_B, **kwargs):
+        kwargs = dict(kwargs)
+        kwargs.pop('shuffle', None)
+        super(UnalignedIterator, self).__init__(data_A, data_B, **kwargs)
+
+    def reset(self):
+        self.data_indices = [np.random.permutation(self.num_samples) for _ in range(2)]
+        self.batch_idx = 0
+
+    def indices(self):
+        if self.batch_idx == self.n_batches:
+            self.reset()
+            return None
+        idx = self.batch_idx * self.batch_size
+        if idx + self.batch_size >= len(self.data_indices[0]):
+            idx = len(self.data_indices[0]) - self.batch_size
+        a = self.data_indices[0][idx:idx + self.batch_size]
+        b = self.data_indices[1][idx:idx + self.batch_size]
+        self.batch_idx += 1
+        return a, b
+
+
+# ---- input staging ---------------------------------------------------------------------------------------------------
+class StagedBatches(object):
+    """Wrap a batch iterator (dicts with float32 'A' / 'B' host tensors).  A staging thread copies each batch into one
+    of `depth` pinned buffers and from there to the device on a copy stream, `depth - 1` batches ahead of the consumer,
+    so neither the pinned memcpy nor the host->device transfer sits between two steps.  Yields (real_A, real_B,
+    prior_z_B) CUDA tensors that are valid until the following ``next()``; ``prior_z_B`` ~ N(0, 1) [N, nlatent, 1, 1]
+    is drawn on the device from ``generator``."""
+
+    _END = object()
+
+    def __init__(self, it, nlatent, device=None, generator=None, depth=2):
+        if not torch.cuda.is_available():
+            raise RuntimeError("dtg_b200: StagedBatches needs a CUDA device; there is no CPU fallback")
+        self.it = iter(it)
+        self.nlatent = nlatent
+        self.device = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
+        self.gen = generator
+        self.copy_stream = torch.cuda.Stream(device=self.device)
+        self.h2d_bytes = 0
+        self._last = None
+        self._free = queue.Queue()
+        self._ready = queue.Queue()
+        for _ in range(max(2, depth)):
+            self._free.put(dict(pin_A=None, pin_B=None, dev_A=None, dev_B=None, ready=None, consumed=None))
+        self._thread = threading.Thread(target=self._stage, name="dtg-stage", daemon=True)
+        self._thread.start()
+
+    def _stage(self):
+        try:
+            torch.cuda.set_device(self.device)
+            while True:
+                s = self._free.get()
+                if s is None:                          # close()
+                    return
+                try:
+                    d = next(self.it)
+                except StopIteration:
+                    self._ready.put(self._END)
+                    return
+                a, b = d['A'].float(), d['B'].float()
+                if s["pin_A"] is None or s["pin_A"].shape != a.shape or s["pin_B"].shape != b.shape:
+                    s.update(pin_A=torch.empty(a.shape, dtype=torch.float32).pin_memory(),
+                             pin_B=torch.empty(b.shape, dtype=torch.float32).pin_memory(),
+                             dev_A=torch.empty(a.shape, dtype=torch.float32, device=self.device),
+                             dev_B=torch.empty(b.shape, dtype=torch.float32, device=self.device), ready=None)
+                if s["ready"] is not None:
+                    s["ready"].synchronize()           # the previous H2D out of this pinned buffer has completed
+                s["pin_A"].copy_(a)
+                s["pin_B"].copy_(b)
+                if s["consumed"] is not None:
+                    self.copy_stream.wait_event(s["consumed"])     # the step that read these device buffers is done
+                with torch.cuda.stream(self.copy_stream):
+                    s["dev_A"].copy_(s["pin_A"], non_blocking=True)
+                    s["dev_B"].copy_(s["pin_B"], non_blocking=True)
+                    s["ready"] = torch.cuda.Event()
+                    s["ready"].record(self.copy_stream)
+                self.h2d_bytes += (a.numel() + b.numel()) * 4
+                self._ready.put(s)
+        except BaseException as exc:                   # surface loader errors in the consumer
+            self._ready.put(exc)
+
+    def __iter__(self):
+        return self
+
+    def __next__(self):
+        cur = torch.cuda.current_stream()
+        if self._last is not None:
+            # everything the caller issued on the batch handed out last time precedes this point in stream order
+            self._last["consumed"] = torch.cuda.Event()
+            self._last["consumed"].record(cur)
+            self._free.put(self._last)
+            self._last = None
+        s = self._ready.get()
+        if s is self._END:
+            self._ready.put(self._END)
+            raise StopIteration
+        if isinstance(s, BaseException):
+            raise s
+        cur.wait_event(s["ready"])
+        z = torch.randn(s["dev_A"].shape[0], self.nlatent, 1, 1, device=self.device, dtype=torch.float32, generator=self.gen)
+        self._last = s
+        return s["dev_A"], s["dev_B"], z
+
+    next = __next__
+
+    def close(self):
+        self._free.put(None)
+
+
+# ---- logging (train.py:34-45) ------------------------------------------------------------------------------------------
+def print_log(out_f, message):
+    if out_f is not None:
+        out_f.write(message + "\n")
+        out_f.flush()
+    print(message)
+
+
+def format_log(epoch, i, errors, t, prefix=True):
+    message = '(epoch: %d, iters: %d, time: %.3f) ' % (epoch, i, t)
+    if not prefix:
+        message = ' ' * len(message)
+    for k, v in errors.items():
+        message += '%s: %.3f ' % (k, v)
+    return message
+
+
+# ---- the loop (train.py:185-256, 307-313) ------------------------------------------------------------------------------
+def train_epochs(model, opt, train_dataset, out_f=None, sup_train_dataset=None, use_graph=True, generator=None,
+                 on_display=None, on_epoch_end=None, log=print_log, stager=None):
+    """Runs epochs ``opt.epoch_count .. opt.niter + opt.niter_decay`` of ``model.train_instance`` over ``train_dataset``
+    (an iterator of {'A', 'B'} host batches that resets itself at StopIteration, like the reference's).  Returns
+    (total_steps, history) where history lists the printed (epoch, epoch_iter, losses[, sup_losses][, gnorms]) records.
+
+    Hooks: on_display(model, epoch, epoch_iter, real_A, visuals) at ``display_freq`` (train.py:218-241),
+    on_epoch_end(model, epoch, total_steps) after the checkpoint cadence (evaluation, train.py:259-305).
+    stager(iterator, nlatent, generator) -> iterator of (real_A, real_B, prior_z_B); default StagedBatches."""
+    if stager is None:
+        stager = lambda it, nz, gen: StagedBatches(it, nz, generator=gen)
+    total_steps = 0
+    history = []
+    print_start_time = time.time()
+    for epoch in range(opt.epoch_count, opt.niter + opt.niter_decay + 1):
+        epoch_start_time = time.time()
+        epoch_iter = 0
+        staged = stager(_same_size_only(train_dataset), opt.nlatent, generator)
+        sup_losses = None
+        for real_A, real_B, prior_z_B in staged:
+            total_steps += opt.batchSize                  # the reference counts batchSize even for a short batch
+            epoch_iter += opt.batchSize
+            show = total_steps % opt.display_freq == 0
+            say = total_steps % opt.print_freq == 0
+            out = model.train_instance(real_A, real_B, prior_z_B, use_graph=use_graph, report=say)
+            losses, visuals = out[0], out[1]
+            gnorms = out[2] if len(out) > 2 else None
+            if getattr(opt, "supervised", False):
+                sup = next(sup_train_dataset)
+                sup_losses = model.supervised_train_instance(sup['A'].float().to(real_A.device, non_blocking=True),
+                                                             sup['B'].float().to(real_A.device, non_blocking=True),
+                                                             prior_z_B)
+            if show and on_display is not None:
+                on_display(model, epoch, epoch_iter // opt.batchSize, real_A, visuals)
+            if say:
+                t = (time.time() - print_start_time) / opt.batchSize
+                log(out_f, format_log(epoch, epoch_iter, losses, t))
+                rec = [epoch, epoch_iter, losses]
+                if getattr(opt, "supervised", False):
+                    log(out_f, format_log(epoch, epoch_iter, sup_losses, t, prefix=False))
+                    rec.append(sup_losses)
+                if opt.monitor_gnorm:
+                    log(out_f, format_log(epoch, epoch_iter, gnorms, t, prefix=False) + "\n")
+                    rec.append(gnorms)
+                history.append(tuple(rec))
+                print_start_time = time.time()
+        if epoch % opt.save_epoch_freq == 0:
+            log(out_f, 'saving the model at the end of epoch %d, iters %d' % (epoch, total_steps))
+            model.save('latest')
+        if on_epoch_end is not None:
+            on_epoch_end(model, epoch, total_steps)
+        log(out_f, 'End of epoch %d / %d \t Time Taken: %d sec' % (epoch, opt.niter + opt.niter_decay,
+                                                                   time.time() - epoch_start_time))
+        if epoch > opt.niter:
+            model.update_learning_rate()
+    return total_steps, history
+
+
+def _same_size_only(it):
+    """train.py:188-189: batches whose A and B sizes differ are skipped (without counting a step)"""
+    for d in it:
+        if d['A'].size(0) != d['B'].size(0):
+            continue
+        yield d

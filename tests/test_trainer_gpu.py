@@ -1,0 +1,87 @@
+"""GPU tests of the input staging and the training loop around the fused step (dtg_b200.trainer)."""
+import argparse
+
+import numpy as np
+import pytest
+import torch
+
+import dtg  # noqa: F401
+from dtg_b200 import engine, model as dmodel, trainer
+from oracle import nets as onets, step as ostep
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda"
+
+
+def test_staged_batches_deliver_the_source_batches():
+    """double-buffered pinned staging: every batch arrives intact even when the consumer is slow (a long kernel is
+    queued behind each hand-out) and the device buffers are recycled two batches later"""
+    g = np.random.RandomState(0)
+    A = g.rand(37, 3, 16, 16).astype(np.float32)
+    B = g.rand(37, 3, 16, 16).astype(np.float32)
+    it = trainer.AlignedIterator(A, B, batch_size=5)
+    staged = trainer.StagedBatches(it, nlatent=16)
+    big = torch.randn(4096, 4096, device=DEV)
+    seen, zs = 0, []
+    for k, (a, b, z) in enumerate(staged):
+        keep_a, keep_b = a.clone(), b.clone()          # stream-ordered right after the hand-out
+        for _ in range(3):
+            big = big @ big * 1e-4                      # keeps the compute stream busy while the next batch is staged
+        late_a = a.clone()                              # still the same batch after the busy work (slot not recycled yet)
+        lo, hi = k * 5, min(37, k * 5 + 5)
+        assert torch.equal(keep_a.cpu(), torch.from_numpy(A[lo:hi])) and torch.equal(keep_b.cpu(), torch.from_numpy(B[lo:hi]))
+        assert torch.equal(late_a.cpu(), torch.from_numpy(A[lo:hi]))
+        assert z.shape == (hi - lo, 16, 1, 1) and z.is_cuda
+        zs.append(z.clone())
+        seen += hi - lo
+    assert seen == 37 and staged.h2d_bytes == 2 * 37 * 3 * 16 * 16 * 4
+    assert float(torch.cat(zs).std()) > 0.5            # N(0, 1) draws, not a constant
+
+
+def test_train_epochs_equals_manual_steps(tmp_path):
+    """the loop adds nothing to the arithmetic: losses printed by train_epochs (graph replay, staged inputs, lazily
+    synced reports) equal those of the same steps issued by hand"""
+    engine.set_precision("bf16")
+    opt = argparse.Namespace(**vars(ostep.default_opt()), expr_dir=str(tmp_path), niter_decay=1, niter=1, epoch_count=1,
+                             batchSize=4, print_freq=8, display_freq=16, save_epoch_freq=1, supervised=False)
+    state = onets.init_model_state(seed=5, perturb=0.02)
+    a, b, _ = ostep.synthetic_batch(12, seed=3)
+    A, B = a.numpy(), b.numpy()
+
+    def build():
+        m = dmodel.AugmentedCycleGAN(opt, testing=True)
+        for name, net in m._nets().items():
+            net.load_state_dict({k: v.clone() for k, v in state[name].items()}, strict=False)
+        m.prepare()
+        for net in m._nets().values():
+            net._ex.repack()
+        return m
+
+    np.random.seed(11)
+    it = trainer.UnalignedIterator(A, B, batch_size=4)
+    gen = torch.Generator(device=DEV).manual_seed(99)
+    m1 = build()
+    logs = []
+    total, hist = trainer.train_epochs(m1, opt, it, use_graph=True, generator=gen, log=lambda f, s: logs.append(s))
+    assert total == 2 * 3 * 4 and len(hist) == 3            # 6 steps, printed every second one
+    assert sum(1 for s in logs if s.startswith("saving the model")) == 2
+    # by hand: same permutations, same z stream
+    np.random.seed(11)
+    it = trainer.UnalignedIterator(A, B, batch_size=4)
+    gen = torch.Generator(device=DEV).manual_seed(99)
+    m2 = build()
+    k, printed = 0, []
+    for epoch in (1, 2):
+        for d in it:
+            z = torch.randn(4, 16, 1, 1, device=DEV, generator=gen)
+            losses, _, gn = m2.train_instance(d['A'].to(DEV), d['B'].to(DEV), z, use_graph=True)
+            k += 1
+            if (k * 4) % 8 == 0:
+                printed.append((losses, gn))
+        if epoch > opt.niter:
+            m2.update_learning_rate()
+    for (e, i, l1, g1), (l2, g2) in zip(hist, printed):
+        assert dict(l1) == dict(l2) and dict(g1) == dict(g2)
+    assert m1.old_lr == m2.old_lr
+    for (n1, p1), (n2, p2) in zip(m1.netG_A_B.named_parameters(), m2.netG_A_B.named_parameters()):
+        assert torch.equal(p1, p2), n1
