@@ -1,0 +1,108 @@
+"""Evaluation inner loops of the reference, Python 3, running on the drop-in models:
+``eval_mse_A`` (/root/reference/augmented_cyclegan/evaluate.py:10-19) and ``variational_ubo`` / ``eval_ubo_B``
+(evaluate.py:21-148) -- per batch, `steps` iterations of: G_A_B forward on (real_A, z_B ~ q), Laplace log-likelihood of
+real_B, KL to the prior, backward to (mu, logvar), RMSprop.  The network passes run through the fused plans
+(model.predict_B stays differentiable with respect to z_B, networks._NetFn); the variational objective around them
+(elementwise on [N,3,64,64] and [N,nlatent]) is plain PyTorch host code here -- it is NOT yet fused into kernels, and the
+generator backward also produces the (unused) weight gradients exactly as the reference's autograd does.
+Visualisation (evaluate.py:79-86, 136-147) is left to the caller.  Like the reference, 64x64x3 is hard-coded in the
+bits-per-pixel constant.
+"""
+import math
+
+import numpy as np
+import torch
+import torch.nn.functional as F
+
+
+def gauss_reparametrize(mu, logvar, n_sample=1):
+    """model.py:15-22 (clamped to +-4)"""
+    std = logvar.mul(0.5).exp()
+    size = std.size()
+    eps = std.detach().new_empty(size[0], n_sample, size[1]).normal_()
+    z = eps.mul(std[:, None, :]).add(mu[:, None, :])
+    z = torch.clamp(z, -4., 4.)
+    return z.view(z.size(0) * z.size(1), z.size(2), 1, 1)
+
+
+def log_prob_laplace(z, mu, log_var):
+    """model.py:24-28"""
+    sd = torch.exp(0.5 * log_var)
+    return -0.5 * log_var - (torch.abs(z - mu) / sd) - float(np.log(2))
+
+
+def kld_std_guss(mu, log_var):
+    """model.py:45-53"""
+    return -0.5 * torch.sum(log_var + 1. - mu ** 2 - torch.exp(log_var), dim=1)
+
+
+def eval_mse_A(dataset, model, device="cuda"):
+    """evaluate.py:10-19"""
+    mse_A = []
+    for batch in dataset:
+        real_A, real_B = batch['A'].float().to(device), batch['B'].float().to(device)
+        with torch.no_grad():
+            pred_A = model.predict_A(real_B)
+        mse_A.append(float(F.mse_loss(pred_A, real_A)))
+    return np.mean(mse_A)
+
+
+def variational_ubo(model, real_A, real_B, steps, logvar_B=None, compute_l1=False, verbose=False):
+    """evaluate.py:39-148 without the PNG dumps.  real_A / real_B live on the model's device.  Returns
+    (ubo, kld, bpp) of the LAST evaluated iterate, like the reference."""
+    dev = real_A.device
+    nz = model.opt.nlatent
+    dequant = torch.zeros(*real_B.size()).uniform_(0, 1. / 127.5).to(dev)                 # :43
+    size = real_A.size()
+    mu = torch.zeros(size[0], nz, device=dev, requires_grad=True)                         # :48-50
+    logvar = torch.zeros(size[0], nz).fill_(math.log(0.01)).to(dev).requires_grad_(True)
+    if logvar_B is None:
+        logvar_B = torch.zeros(1, 3, 64, 64).fill_(math.log(0.01)).to(dev)                # :52
+    if hasattr(model, 'netE_B'):                                                          # :56-62
+        params = model.predict_enc_params(real_A, real_B)
+        mu = params[0].detach().clone().requires_grad_(True)
+        if len(params) == 2:
+            logvar = params[1].detach().clone().requires_grad_(True)
+    iterative_opt = torch.optim.RMSprop([mu, logvar], lr=1e-2)                            # :65
+    real_B = real_B + dequant                                                             # :67
+    z_B = gauss_reparametrize(mu, logvar)                                                 # :70-71
+    fake_B = model.predict_B(real_A, z_B)
+    rec_B = None
+    if compute_l1:                                                                        # :73-78
+        with torch.no_grad():
+            rec_B = fake_B.detach() if model.opt.stoch_enc else model.predict_B(real_A, mu.detach().view(size[0], nz, 1, 1))
+    ubo_val = kld_val = bpp = None
+    for i in range(steps):                                                                # :89
+        log_prob = log_prob_laplace(real_B, fake_B, logvar_B).view(size[0], -1).sum(1)    # :93-94
+        kld = kld_std_guss(mu, logvar)                                                    # :101
+        ubo = (-log_prob + kld) + (64 * 64 * 3) * math.log(127.5)                         # :103
+        ubo_val = float(ubo.detach().mean(0))
+        kld_val = float(kld.detach().mean(0))
+        bpp = ubo_val / (64 * 64 * 3 * math.log(2.))                                      # :106
+        if verbose:
+            msg = '[%d] UBO: %.4f, KLD: %.4f, BPP: %.4f' % (i, ubo_val, kld_val, bpp)
+            if compute_l1:
+                msg = '%s, L1: %.4f' % (msg, float(F.l1_loss(real_B, rec_B)))
+            print(msg)
+        loss = ubo.mean(0)                                                                # :118-121
+        iterative_opt.zero_grad()
+        loss.backward()
+        iterative_opt.step()
+        z_B = gauss_reparametrize(mu, logvar)                                             # :123-124
+        fake_B = model.predict_B(real_A, z_B)
+        if compute_l1:
+            with torch.no_grad():
+                rec_B = fake_B.detach() if model.opt.stoch_enc else model.predict_B(real_A, mu.detach().view(size[0], nz, 1, 1))
+    return ubo_val, kld_val, bpp
+
+
+def eval_ubo_B(dataset, model, steps=500, logvar_B=None, compute_l1=False, verbose=False, device="cuda"):
+    """evaluate.py:21-37"""
+    ubo_B, bpp_B, kld_B = [], [], []
+    for batch in dataset:
+        real_A, real_B = batch['A'].float().to(device), batch['B'].float().to(device)
+        ubo, kld, bpp = variational_ubo(model, real_A, real_B, steps, logvar_B, compute_l1, verbose)
+        ubo_B.append(ubo)
+        bpp_B.append(bpp)
+        kld_B.append(kld)
+    return np.mean(ubo_B), np.mean(bpp_B), np.mean(kld_B)

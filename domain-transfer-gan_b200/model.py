@@ -307,7 +307,10 @@ class _FusedCycleModel(object):
 
     # ---- forward-only helpers shared by both models ------------------------------------------------
     def _fwd(self, net, heads, *inputs, z=None):
-        with torch.no_grad():
+        """forward-only unless an input asks for a gradient: evaluate.py:70-123 (variational_ubo) differentiates
+        predict_B(real_A, z_B) with respect to z_B, so that call stays on the autograd path of networks._NetFn"""
+        need = torch.is_grad_enabled() and any(t is not None and t.requires_grad for t in inputs + (z,))
+        with torch.set_grad_enabled(need):
             return net._call(heads, inputs[0], z, *inputs[1:])
 
     def _z(self, z_B):

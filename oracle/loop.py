@@ -65,3 +65,23 @@ def train_loop(model, opt, train_dataset, draw_z, log, sup_train_dataset=None):
         if epoch > opt.niter:                                                        # :312-313
             model.update_learning_rate()
     return total_steps
+
+
+def reference_evaluate():
+    """The reference's evaluate.py executed live (build container only) with text shims: Python-2 ``print res_str`` ->
+    ``print(res_str)``, ``.data[0]`` -> ``.item()`` (0-dim indexing), ``.cuda()`` removed (CPU run), and the model import
+    redirected to the live reference model module.  Returns the module namespace (eval_mse_A, variational_ubo, ...)."""
+    import os
+    import types
+    import sys
+    from . import live_reference as lr
+    _, _, M = lr.load()
+    src = open(os.path.join(lr.REF_DIR, "evaluate.py")).read()
+    src = src.replace("print res_str", "print(res_str)").replace(".data[0]", ".item()").replace(".cuda()", "")
+    src = src.replace("from model import gauss_reparametrize, log_prob_laplace, log_prob_gaussian, kld_std_guss", "")
+    mod = types.ModuleType("ref_evaluate")
+    for k in ("gauss_reparametrize", "log_prob_laplace", "log_prob_gaussian", "kld_std_guss"):
+        setattr(mod, k, getattr(M, k))
+    sys.dont_write_bytecode = True
+    exec(compile(src, os.path.join(lr.REF_DIR, "evaluate.py"), "exec"), mod.__dict__)
+    return mod

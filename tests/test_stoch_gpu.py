@@ -279,3 +279,31 @@ def test_checkpoint_reference_format_roundtrip(tmp_path):
     assert int(some["step"]) == 2 and some["exp_avg"].shape == params[0].shape
     for name in onets.NET_NAMES:
         assert set(state[name].keys()) <= set(saved[name].keys()), name
+
+
+def test_predict_B_is_differentiable_in_z():
+    """evaluate.py:70-123 (variational_ubo) optimises q(z) by back-propagating through model.predict_B(real_A, z_B):
+    the drop-in keeps that call differentiable with respect to z_B (and forward-only otherwise)."""
+    engine.set_precision("tf32")
+    state = onets.init_model_state(seed=21, perturb=0.05)
+    a, b, z = [t.to(DEV) for t in ostep.synthetic_batch(3, seed=2)]
+    ours = _load(dmodel.AugmentedCycleGAN(_opt(), testing=True), state)
+    om = ostep.OracleModel(ostep.default_opt(), state, device=DEV)
+    wgt = torch.linspace(-1, 1, b.numel(), device=DEV).view_as(b)
+    mu = z.reshape(3, 16).clone().requires_grad_(True)
+    logvar = torch.full((3, 16), -4.6, device=DEV, requires_grad=True)
+    eps = torch.randn(3, 16, device=DEV)
+
+    def objective(predict):
+        zz = (mu + eps * torch.exp(0.5 * logvar)).reshape(3, 16, 1, 1)          # gauss_reparametrize, model.py:15-22
+        out = predict(a, zz)
+        return (((out - b) ** 2) * wgt).sum()      # smooth: a tf32 sign flip of |.|' would dominate the comparison
+
+    objective(ours.predict_B).backward()
+    g_mu, g_lv = mu.grad.clone(), logvar.grad.clone()
+    mu.grad = None; logvar.grad = None
+    objective(lambda x, zz: om.G_A_B(x, zz)).backward()
+    assert _rel(g_mu, mu.grad) < 2e-2 and _rel(g_lv, logvar.grad) < 2e-2, (_rel(g_mu, mu.grad), _rel(g_lv, logvar.grad))
+    with torch.no_grad():
+        y = ours.predict_B(a, z)
+    assert not y.requires_grad and not ours.predict_B(a, z).requires_grad

@@ -137,3 +137,32 @@ def test_format_log_matches_reference_format():
     assert msg == "(epoch: 3, iters: 40, time: 0.012) D_A: 0.123 G_A: 1.000 "        # train.py:39-45
     cont = trainer.format_log(3, 40, OrderedDict([("x", 2.0)]), 0.0123, prefix=False)
     assert cont == " " * len("(epoch: 3, iters: 40, time: 0.012) ") + "x: 2.000 "
+
+
+@pytest.mark.skipif(not lr.available(), reason="/root/reference not present (GPU box)")
+def test_evaluate_port_matches_live_reference():
+    """dtg_b200.evaluate (eval_mse_A, variational_ubo) against the reference's own evaluate.py (text shims only, see
+    oracle.loop.reference_evaluate), both driving the LIVE reference model on CPU with the same RNG stream."""
+    import copy
+    import warnings
+    from dtg_b200 import evaluate as ev
+    from oracle import nets, step
+    warnings.simplefilter("ignore")
+    ref_ev = oloop.reference_evaluate()
+    opt = step.default_opt()
+    state = nets.init_model_state(seed=5, perturb=0.03)
+    a, b, _ = step.synthetic_batch(3, seed=9)
+
+    def fresh():
+        m = lr.build_reference_model(copy.deepcopy(opt), state)
+        m.eval()          # BatchNorm running statistics: predict_enc_params must not move them between the two runs
+        return m
+
+    torch.manual_seed(77)
+    r_ubo, r_kld, r_bpp = ref_ev.variational_ubo(fresh(), a, b, 4, use_gpu=False)
+    torch.manual_seed(77)
+    o_ubo, o_kld, o_bpp = ev.variational_ubo(fresh(), a, b, 4)
+    assert abs(o_ubo - r_ubo) <= 1e-4 * abs(r_ubo) and abs(o_kld - r_kld) <= 1e-4 * abs(r_kld) + 1e-6
+    assert abs(o_bpp - r_bpp) <= 1e-4 * abs(r_bpp)
+    data = [{'A': a, 'B': b}, {'A': a.flip(0), 'B': b.flip(0)}]
+    assert abs(ev.eval_mse_A(data, fresh(), device="cpu") - ref_ev.eval_mse_A(data, fresh(), use_gpu=False)) < 1e-6

@@ -85,3 +85,45 @@ def test_train_epochs_equals_manual_steps(tmp_path):
     assert m1.old_lr == m2.old_lr
     for (n1, p1), (n2, p2) in zip(m1.netG_A_B.named_parameters(), m2.netG_A_B.named_parameters()):
         assert torch.equal(p1, p2), n1
+
+
+def test_variational_ubo_on_the_fused_model_matches_oracle():
+    """evaluate.py:39-148 through dtg_b200.evaluate: the fused model (G_A_B forward + backward to z through the C ABI)
+    against the same loop driving the oracle networks with cuDNN; same RNG stream, 3 RMSprop steps."""
+    from dtg_b200 import evaluate as ev
+    engine.set_precision("tf32")
+    torch.backends.cudnn.allow_tf32 = False
+    torch.backends.cuda.matmul.allow_tf32 = False
+    opt = argparse.Namespace(**vars(ostep.default_opt()), expr_dir="/tmp", niter_decay=25)
+    state = onets.init_model_state(seed=5, perturb=0.03)
+    a, b, _ = [t.to(DEV) for t in ostep.synthetic_batch(4, seed=9)]
+    ours = dmodel.AugmentedCycleGAN(opt, testing=True)
+    for name, net in ours._nets().items():
+        net.load_state_dict({k: v.clone() for k, v in state[name].items()}, strict=False)
+    ours.prepare()
+    for net in ours._nets().values():
+        net._ex.repack()
+    om = ostep.OracleModel(ostep.default_opt(), state, device=DEV)
+
+    class Adapter(object):      # the oracle networks behind the model interface evaluate.py uses
+        opt = om.opt
+        netE_B = True
+
+        def predict_B(self, x, z):
+            return om.G_A_B(x, z)
+
+        def predict_enc_params(self, x, y):
+            with torch.no_grad():
+                mu, _ = om.E_B(torch.cat((x, y), 1))
+            return (mu.reshape(mu.shape[0], -1),)
+
+    torch.manual_seed(3)
+    r = ev.variational_ubo(Adapter(), a, b, 3)
+    torch.manual_seed(3)
+    o = ev.variational_ubo(ours, a, b, 3)
+    for x, y, name in zip(o, r, ("ubo", "kld", "bpp")):
+        assert abs(x - y) <= 5e-3 * abs(y) + 1e-3, (name, x, y)
+    data = [{'A': a.cpu(), 'B': b.cpu()}]
+    with torch.no_grad():
+        ref_mse = float(torch.nn.functional.mse_loss(om.G_B_A(b), a))
+    assert abs(ev.eval_mse_A(data, ours) - ref_mse) <= 5e-3 * ref_mse
