@@ -240,8 +240,13 @@ def main():
         raise SystemExit("bench.py: no CUDA device (there is no CPU fallback for the product path)")
     torch.cuda.set_device(local)
     import torch.distributed as dist
+    json_out = sys.stdout
     if world > 1:
-        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")    # keep stdout to the one JSON line (NCCL's version banner)
+        # keep stdout to the ONE JSON line: NCCL prints its version banner to fd 1 when the communicator is created, so
+        # fd 1 points at stderr for the whole run and the JSON line goes to a private duplicate of the real stdout
+        sys.stdout.flush()
+        json_out = os.fdopen(os.dup(1), "w")
+        os.dup2(2, 1)
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     say("process group up")
 
@@ -394,7 +399,8 @@ def main():
             except Exception as e:
                 line["torch_gpu_baseline"] = {"error": str(e).splitlines()[0][:200]}
             line["cpu_baseline"] = cpu_baseline(wl)
-        print(json.dumps(line))
+        json_out.write(json.dumps(line) + "\n")
+        json_out.flush()
     if world > 1:
         # release the captured graph (it holds NCCL kernels) before tearing the communicator down; the teardown of a
         # communicator that was used under graph capture can block for minutes, so leave without it
