@@ -195,27 +195,6 @@ class _FusedCycleModel(object):
         ar = dp.allreduce_arena if dp is not None else (lambda arena: None)   # async, overlaps later backward
         return dp, sync_bn, gs, ar
 
-    def _d_pair(self, ex, fake, real, n, h, w, s_fake, s_true, s_pf, s_pt):
-        """discriminate() (model.py:327-334) for an instance-norm discriminator: fake.detach() and real as ONE
-        batch of 2N (instance statistics are per sample, so this is exact); fills the seed gradients."""
-        sc, ws = self.scalars, self.red_ws[0]
-        c = ex.new_ctx(2 * n, h, w, "d")
-        ops.pack_nchw(fake, c.acts[0].batch_slice(0, n), 0)
-        ops.pack_nchw(real, c.acts[0].batch_slice(n, 2 * n), 0)
-        p = ex.forward(c)["out"]
-        i = self._head_idx(ex, "out")
-        ops.loss_lsgan(p[:n], 0.0, 0.5, sc, s_fake, s_pf, c.dyraw[i].batch_slice(0, n), ws)
-        ops.loss_lsgan(p[n:], 1.0, 0.5, sc, s_true, s_pt, c.dyraw[i].batch_slice(n, 2 * n), ws)
-        return c
-
-    def _g_adv(self, ex, fake, n, h, w, s_loss, s_pf):
-        """generator-side adversarial term: criterionGAN(D(fake), True) with the updated discriminator"""
-        c = ex.new_ctx(n, h, w, "g")
-        ops.pack_nchw(fake, c.acts[0], 0)
-        i = self._head_idx(ex, "out")
-        ops.loss_lsgan(ex.forward(c)["out"], 1.0, 1.0, self.scalars, s_loss, s_pf, c.dyraw[i], self._rws())
-        return c
-
     def _rws(self):
         return self.red_ws[ops.lane()]
 

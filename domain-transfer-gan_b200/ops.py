@@ -4,6 +4,7 @@ Everything here only marshals pointers; all arithmetic happens in libdtg_b200.so
 CUDA stream.  Nothing falls back to torch ops.
 """
 import ctypes as C
+import os
 
 import torch
 
@@ -28,16 +29,16 @@ def lane():
 class Lanes(object):
     """Fork / join of independent branches of one step onto lane CUDA streams.  begin() forks the lanes off the
     caller's current stream (under torch.cuda.graph: the capturing stream, so the lanes join the capture through the
-    fork event and the branches become parallel paths of the SAME CUDA graph); end() joins them back.  Tasks on one lane run in issue order;
-    cross-lane dependencies are the events returned by run().  With enabled=False every task runs on lane 0 in
+    fork event and the branches become parallel paths of the SAME CUDA graph); end() joins them back.  Tasks on one
+    lane run in issue order; cross-lane dependencies are the events returned by run().  With enabled=False every task runs on lane 0 in
     issue order (the issue order must therefore be a valid serial schedule)."""
 
     def __init__(self, n_lanes, device, chain_priority=0, comp_priority=0):
-        import os
+        # DTG_LANE_PRIO="chain,companion" overrides the stream priorities (measured on B200: equal priorities are best;
+        # favouring the chains pushes the weight gradients into a tail, favouring the companions delays the chains)
         if os.environ.get("DTG_LANE_PRIO"):
             chain_priority, comp_priority = [int(v) for v in os.environ["DTG_LANE_PRIO"].split(",")]
-        # the lanes carry dependency chains (forward / norm-backward / dgrad): high priority, so that a chain kernel
-        # is dispatched ahead of the queued off-chain work (weight gradients on the companion streams, priority 0)
+        # lanes carry the dependency chains (forward / norm-backward / dgrad), companions the off-chain work
         self.lane_streams = [torch.cuda.Stream(device=device, priority=chain_priority) for _ in range(n_lanes)]
         self.comp = [torch.cuda.Stream(device=device, priority=comp_priority) for _ in range(n_lanes)]   # companion of each lane
         self.enabled = True
