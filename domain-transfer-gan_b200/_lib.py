@@ -51,6 +51,10 @@ _SIGS = {
     "dtg_conv": (C.c_int, [C.POINTER(ConvArgs), C.POINTER(Plane), _P, C.c_int, C.c_int, _P, C.POINTER(Plane), _P, _P]),
     "dtg_conv_wgrad_workspace_bytes": (C.c_size_t, [C.POINTER(WgradArgs), C.POINTER(Plane), C.POINTER(Plane)]),
     "dtg_conv_wgrad": (C.c_int, [C.POINTER(WgradArgs), C.POINTER(Plane), C.POINTER(Plane), _P, _P, C.c_size_t, _P]),
+    "dtg_head1_fwd": (C.c_int, [C.POINTER(Plane), _P, _P, C.c_int, C.c_int, C.c_int, C.c_int, _P, C.c_int, C.c_int, _P]),
+    "dtg_head1_dgrad": (C.c_int, [C.POINTER(Plane), _P, C.c_int, C.c_int, C.c_int, C.c_int, C.POINTER(Plane), _P]),
+    "dtg_head1_wgrad_workspace_bytes": (C.c_size_t, [C.c_int, C.c_int, C.c_int]),
+    "dtg_head1_wgrad": (C.c_int, [C.POINTER(Plane), C.POINTER(Plane), _P, C.c_int, C.c_int, C.c_int, C.c_int, _P, C.c_size_t, _P]),
     "dtg_norm_workspace_bytes": (C.c_size_t, [C.POINTER(Plane)]),
     "dtg_norm_fwd": (C.c_int, [C.POINTER(NormArgs), C.POINTER(Plane), C.POINTER(Plane), _P, _P, _P, _P, _P, _P,
                                C.POINTER(Plane), _P]),

@@ -15,6 +15,10 @@ from . import ops
 
 _PRECISION = {"dtype": torch.bfloat16}
 S2D = os.environ.get("DTG_NO_S2D") is None      # space-to-depth execution of the stride-2 input layers
+# matrix-vector kernels (dtg_head1_*) for the single-output-channel PatchGAN heads: measured equal to the N-padded
+# tensor-core path (fwd 52 vs 44 us, dgrad 49 vs 55 us, wgrad 68 vs 59 us at batch 160; step time unchanged), so the
+# tensor-core path stays the default and this is opt-in
+HEAD1 = os.environ.get("DTG_HEAD1") is not None
 
 
 def set_precision(name):
@@ -129,6 +133,8 @@ class Layer:
         # space-to-depth execution of a stride-2 first layer with a <= 64-byte input pixel (decided in
         # NetExec.prepare): the input plane is stored as 2x2 pixel blocks, forward conv and wgrad run as stride-1 3x3
         self.s2d = False
+        # single-output-channel head (PatchGAN last layer): matrix-vector shaped, runs on the dtg_head1_* kernels
+        self.head1 = False
 
     def out_hw(self, h, w):
         if self.transposed:       # k3 s2 p1 op1 -> exactly 2x
@@ -182,6 +188,12 @@ class NetExec:
                 ly.fold_in = foldable and ly.src == 0 and ly.cin <= fc and self.in_channels <= fc and self.in_halo >= ly.pad
                 src_halo = self.in_halo if ly.src == 0 else self.layers[ly.src - 1].out_halo
                 ly.fold_out = foldable and ly.head and ly.cout <= fc and not ly.fold_in and src_halo == 0
+                ly.head1 = (HEAD1 and ly.head and ly.cout == 1 and not ly.transposed and ly.stride == 1 and w.dim() == 4 and
+                            ly.k * ly.k <= 16 and ly.act == L.ACT_NONE and src_halo == 0 and ly.src > 0 and
+                            ly.cin % 8 == 0 and ly.cin <= 512)
+                if ly.head1:
+                    ly.fold_in = ly.fold_out = False
+                    continue            # no packed operand: the kernels read the fp32 master weight
                 if ly.s2d:
                     ly.w_f = ops.add_packed(self.pack, w4, dtype, "fwd_s2d", s2d_cp=cp)
                     ly.w_d = ops.add_packed(self.pack, w4, dtype, "dgrad")
@@ -280,6 +292,9 @@ class NetExec:
             if ly.s2d:      # stride-1 3x3 over 2x2 pixel blocks; cin keeps the algorithmic FLOP count of the KxK filter
                 kw.update(kh=3, kw=3, stride=1, pad=1, cin=ly.cin * ly.k * ly.k / 9.0)
             bias = ly.conv.bias if ly.use_bias else None
+            if ly.head1:
+                ops.head1_fwd(a_in, ly.conv.weight, bias, c.heads[ly.name], ly.pad)
+                continue
             if ly.head:
                 ops.conv(a_in, ly.w_f, bias, None, act=ly.act, out_nchw=c.heads[ly.name], **kw)
                 continue
@@ -376,7 +391,9 @@ class NetExec:
             if ly.src > 0 or want_dx:
                 gin = self._gact(c, ly.src, i)
                 ih, iw = c.dims[ly.src]
-                if ly.transposed:
+                if ly.head1:
+                    ops.head1_dgrad(dyr, ly.conv.weight, gin, ly.pad)
+                elif ly.transposed:
                     ops.conv(dyr, ly.w_d, None, gin, mode=L.CONV_FWD, kh=ly.k, kw=ly.k, stride=ly.stride, pad=ly.pad,
                              cout=ly.cin, out_h=ih, out_w=iw, cin=ly.cout)
                 else:
@@ -393,6 +410,8 @@ class NetExec:
     @staticmethod
     def _wgrad_fn(ly, a_in, dyr, dw, dw2=None):
         """the weight gradient of one layer: off the norm-backward / dgrad chain (ops.off_chain)"""
+        if ly.head1:
+            return lambda: ops.head1_wgrad(dyr, a_in, dw, ly.pad)
         if ly.s2d:
             def f():
                 ops.conv_wgrad(dyr, a_in, dw2, kh=3, kw=3, stride=1, pad=1, pa=ly.cout, qb=a_in.c)

@@ -369,6 +369,25 @@ def conv_wgrad(p, q, dw, *, kh, kw, stride=1, pad=0, pa, qb, ws=None, fold=0):
         PROFILE.end("wgrad_kernel", 2.0 * p.n * p.h * p.w * pa * qb * kh * kw, e0)
 
 
+def head1_fwd(x, w, bias, out_nchw, pad):
+    """cout == 1 head conv (dtg_head1_fwd): w is the fp32 master weight [1, cin, kh, kw]"""
+    _, cin, kh, kw = w.shape
+    n, _, oh, ow = out_nchw.shape
+    L.check(L.lib().dtg_head1_fwd(x.s, _ptr(w), _ptr(bias), cin, kh, kw, pad, _ptr(out_nchw), oh, ow, _stream()), "head1_fwd")
+
+
+def head1_dgrad(dy, w, dx, pad):
+    _, cin, kh, kw = w.shape
+    L.check(L.lib().dtg_head1_dgrad(dy.s, _ptr(w), cin, kh, kw, pad, dx.s, _stream()), "head1_dgrad")
+
+
+def head1_wgrad(dy, x, dw, pad):
+    _, cin, kh, kw = dw.shape
+    need = L.lib().dtg_head1_wgrad_workspace_bytes(cin, kh, kw)
+    ws = workspace(need, dw.device, "head1_wgrad")
+    L.check(L.lib().dtg_head1_wgrad(dy.s, x.s, _ptr(dw), cin, kh, kw, pad, _ptr(ws), ws.numel(), _stream()), "head1_wgrad")
+
+
 def norm_workspace_floats(x):
     return L.lib().dtg_norm_workspace_bytes(x.s) // 4
 

@@ -136,6 +136,22 @@ int dtg_conv_wgrad(const dtg_wgrad_args* a, const dtg_plane* p, const dtg_plane*
                    void* workspace, size_t workspace_bytes, void* stream);
 
 /* ---------------------------------------------------------------------------------------------
+ * Single-output-channel head convolutions, stride 1 (the last layers of the PatchGAN discriminators,
+ * networks.py:337 Conv2d(256,1,4,padding=1) and networks.py:381 Conv2d(128,1,4)) and their gradients: matrix-vector
+ * shaped and HBM bound, so they run as coalesced CUDA-core reductions instead of N-padded tensor-core tiles.
+ *   w  : the fp32 master weight [1][cin][kh][kw] (PyTorch layout; no packed operand)
+ *   fwd: out_nchw [n][1][oh][ow] fp32 = conv(in, w) + bias (zero padding `pad`)
+ *   dgrad: dx [n][h][w][>= cin] from channel 0 of the seed-gradient plane dy
+ *   wgrad: dw += the weight gradient; per-block partials in `workspace`, summed in a fixed order
+ * ------------------------------------------------------------------------------------------- */
+int dtg_head1_fwd(const dtg_plane* in, const float* w, const float* bias, int cin, int kh, int kw, int pad,
+                  float* out_nchw, int oh, int ow, void* stream);
+int dtg_head1_dgrad(const dtg_plane* dy, const float* w, int cin, int kh, int kw, int pad, const dtg_plane* dx, void* stream);
+size_t dtg_head1_wgrad_workspace_bytes(int cin, int kh, int kw);
+int dtg_head1_wgrad(const dtg_plane* dy, const dtg_plane* in, float* dw, int cin, int kh, int kw, int pad,
+                    void* workspace, size_t workspace_bytes, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
  * Fused normalisation + affine + activation (+ residual add) forward.  Replaces the ~9-12 ATen
  * kernels per layer of InstanceNorm.forward (modules.py:83-97), CondInstanceNorm.forward
  * (modules.py:120-132), nn.BatchNorm{1,2}d, the following ReLU / LeakyReLU(0.2), the residual
