@@ -18,8 +18,7 @@ from collections import OrderedDict
 
 import torch
 
-from . import _lib as L
-from . import engine, networks, ops
+from . import networks, ops
 
 # slots of the packed reporting vector (device fp32[32])
 S_DFA, S_DTA, S_DFB, S_DTB, S_DPZ, S_DQZ = 0, 1, 2, 3, 4, 5

@@ -16,7 +16,7 @@ import torch
 import torch.nn as nn
 
 from . import _lib as L
-from . import engine, ops
+from . import ops
 from .engine import Layer, NetExec, ParamArena
 from .modules import (CINResnetBlock, CondInstanceNorm, InstanceNorm, InstanceNorm2d, ResnetBlock,  # noqa: F401
                       TwoInputSequential)

@@ -11,7 +11,6 @@ BatchNorm in E_B / D_z_B couples samples: with ``sync_bn=True`` (de
 one GPU x N samples; ``sync_bn=False`` reproduces the per-replica statistics of the reference's own
 data_parallel.
 """
-import torch
 import torch.distributed as dist
 
 
