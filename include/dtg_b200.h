@@ -28,7 +28,7 @@
 extern "C" {
 #endif
 
-#define DTG_VERSION 100
+#define DTG_VERSION 110 /* 110: dtg_pack_item.s2d_k, dtg_pack_nchw_s2d, dtg_s2d_unfold_add, dtg_head1_* */
 
 enum { DTG_OK = 0, DTG_ERR_INVALID = -1, DTG_ERR_CUDA = -2, DTG_ERR_UNSUPPORTED = -3 };
 enum { DTG_BF16 = 0, DTG_F32 = 1 };
