@@ -125,7 +125,7 @@ class Layer:
         # 0).  Batch norm keeps it in the forward because running_mean must include it.
         self.use_bias = use_bias and norm == L.NORM_NONE and conv.bias is not None
         self.fwd_bias = self.use_bias or (norm == L.NORM_BATCH and conv.bias is not None)
-        self.w_f = self.w_d = None
+        self.w_f = self.w_d = self.w_f_s2d = None
         # kw-folded execution of the small-channel 7x7 layers (decided in NetExec.prepare for the plane dtype):
         # fold_in : the INPUT is a 16-byte-per-pixel plane  -> forward conv and wgrad read it kw-folded
         # fold_out: the OUTPUT gradient is (head with <= fc channels) -> dgrad and wgrad read dy kw-folded
@@ -194,8 +194,9 @@ class NetExec:
                 if ly.head1:
                     ly.fold_in = ly.fold_out = False
                     continue            # no packed operand: the kernels read the fp32 master weight
-                if ly.s2d:
-                    ly.w_f = ops.add_packed(self.pack, w4, dtype, "fwd_s2d", s2d_cp=cp)
+                if ly.s2d:      # both forms: the block form needs even image extents (decided per context)
+                    ly.w_f_s2d = ops.add_packed(self.pack, w4, dtype, "fwd_s2d", s2d_cp=cp)
+                    ly.w_f = ops.add_packed(self.pack, w4, dtype, "fwd")
                     ly.w_d = ops.add_packed(self.pack, w4, dtype, "dgrad")
                 elif ly.fold_in:
                     ly.w_f = ops.add_packed(self.pack, w4, dtype, "fwd_fold")
@@ -224,9 +225,8 @@ class NetExec:
         dt, dev = self.dtype, self.arena.device
         c = Ctx()
         c.n = n
-        if self.s2d_cp:
-            if h % 2 or w % 2:
-                raise ValueError("dtg_b200: the stride-2 input layers need even image extents, got %dx%d" % (h, w))
+        c.s2d_cp = self.s2d_cp if (h % 2 == 0 and w % 2 == 0) else 0      # odd extents: ordinary strided path
+        if c.s2d_cp:
             c.acts[0] = ops.PlaneT(n, h // 2, w // 2, 4 * self.s2d_cp, 0, dt, dev, s2d=self.s2d_cp)
             c.s2d_dw2 = {i: torch.zeros(ly.cout * 4 * self.s2d_cp * 9, dtype=torch.float32, device=dev)
                          for i, ly in enumerate(self.layers) if ly.s2d}
@@ -266,7 +266,7 @@ class NetExec:
         key = (idx, consumer)
         if key not in c.gact:
             a = c.acts[idx]
-            if idx == 0 and self.s2d_cp:      # the input gradient keeps the ordinary pixel layout
+            if idx == 0 and c.s2d_cp:         # the input gradient keeps the ordinary pixel layout
                 h, w = c.dims[0]
                 c.gact[key] = ops.PlaneT(a.n, h, w, self.s2d_cp, 0, a.dtype, a.t.device)
             else:
@@ -289,20 +289,22 @@ class NetExec:
             mode = L.CONV_DGRAD if ly.transposed else L.CONV_FWD
             kw = dict(mode=mode, kh=ly.k, kw=ly.k, stride=ly.stride, pad=ly.pad, cout=ly.cout, out_h=oh, out_w=ow,
                       cin=ly.cin, fold_w=ly.fold_in)
-            if ly.s2d:      # stride-1 3x3 over 2x2 pixel blocks; cin keeps the algorithmic FLOP count of the KxK filter
+            w_f = ly.w_f
+            if ly.s2d and c.s2d_cp:      # stride-1 3x3 over 2x2 pixel blocks; cin keeps the algorithmic FLOP count of the KxK filter
                 kw.update(kh=3, kw=3, stride=1, pad=1, cin=ly.cin * ly.k * ly.k / 9.0)
+                w_f = ly.w_f_s2d
             bias = ly.conv.bias if ly.use_bias else None
             if ly.head1:
                 ops.head1_fwd(a_in, ly.conv.weight, bias, c.heads[ly.name], ly.pad)
                 continue
             if ly.head:
-                ops.conv(a_in, ly.w_f, bias, None, act=ly.act, out_nchw=c.heads[ly.name], **kw)
+                ops.conv(a_in, w_f, bias, None, act=ly.act, out_nchw=c.heads[ly.name], **kw)
                 continue
             out = c.acts[i + 1]
             if ly.norm == L.NORM_NONE:
-                ops.conv(a_in, ly.w_f, bias, out, act=ly.act, out_reflect=ly.out_halo > 0, **kw)
+                ops.conv(a_in, w_f, bias, out, act=ly.act, out_reflect=ly.out_halo > 0, **kw)
                 continue
-            ops.conv(a_in, ly.w_f, ly.conv.bias if ly.fwd_bias else None, c.yraw[i], **kw)
+            ops.conv(a_in, w_f, ly.conv.bias if ly.fwd_bias else None, c.yraw[i], **kw)
             nm = ly.norm_mod
             res = c.acts[ly.residual] if ly.residual is not None else None
             if ly.norm == L.NORM_COND_INSTANCE:
@@ -386,7 +388,7 @@ class NetExec:
                     pending[ly.residual] = (d_res, d1) if d0 is None else (d0, d_res)
             # weight gradient
             if want_dw:
-                ops.off_chain(self._wgrad_fn(ly, a_in, dyr, A.g(ly.conv.weight), c.s2d_dw2[i] if ly.s2d else None))
+                ops.off_chain(self._wgrad_fn(ly, a_in, dyr, A.g(ly.conv.weight), c.s2d_dw2[i] if (ly.s2d and c.s2d_cp) else None))
             # data gradient
             if ly.src > 0 or want_dx:
                 gin = self._gact(c, ly.src, i)
@@ -412,7 +414,7 @@ class NetExec:
         """the weight gradient of one layer: off the norm-backward / dgrad chain (ops.off_chain)"""
         if ly.head1:
             return lambda: ops.head1_wgrad(dyr, a_in, dw, ly.pad)
-        if ly.s2d:
+        if dw2 is not None:
             def f():
                 ops.conv_wgrad(dyr, a_in, dw2, kh=3, kw=3, stride=1, pad=1, pa=ly.cout, qb=a_in.c)
                 ops.s2d_unfold_add(dw2, dw, a_in.s2d)

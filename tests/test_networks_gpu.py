@@ -138,15 +138,16 @@ def test_resnet_generator(prec):
 
 
 @pytest.mark.parametrize("prec", ["tf32", "bf16"])
-@pytest.mark.parametrize("which", ["netD_A", "netD_B"])
-def test_discriminators(which, prec):
+@pytest.mark.parametrize("which,size", [("netD_A", 64), ("netD_B", 64), ("netD_B", 67)])
+def test_discriminators(which, prec, size):
+    """size 67: odd extents take the ordinary strided first layer instead of the space-to-depth one"""
     engine.set_precision(prec)
     sd = STATE[which]
     net = (networks.Discriminator_edges(3, 32, norm_layer=networks.get_norm_layer("instance")) if which == "netD_A"
            else networks.Discriminator(3, 64, norm_layer=networks.get_norm_layer("instance"))).to(DEV)
     _load(net, sd)
     g = torch.Generator().manual_seed(2)
-    x = (torch.rand(4, 3, 64, 64, generator=g) * 2 - 1).to(DEV).requires_grad_(True)
+    x = (torch.rand(4, 3, size, size, generator=g) * 2 - 1).to(DEV).requires_grad_(True)
     y = net(x)
     wgt = torch.randn(y.shape, generator=g).to(DEV)
     (y * wgt).sum().backward()
