@@ -131,6 +131,17 @@ class FusedAdam(object):
         self.sync_hyper()
 
 
+class PendingReport(object):
+    """losses / gnorms of one step whose device->host copy is still in flight (train_instance(report="defer"))"""
+
+    def __init__(self, model, host, event):
+        self.model, self.host, self.event = model, host, event
+
+    def get(self):
+        self.event.synchronize()
+        return self.model._dicts(self.host.tolist())
+
+
 class _FusedCycleModel(object):
     """What AugmentedCycleGAN and StochCycleGAN share: device buffers, the eager / CUDA-graph step drivers,
     forward-only helpers and bookkeeping.  Subclasses define NET_NAMES, OPT_NAMES, _step_device, _report."""
@@ -203,6 +214,21 @@ class _FusedCycleModel(object):
         torch.cuda.current_stream().synchronize()
         return self.scalars_host.tolist()
 
+    def _report(self):
+        return self._dicts(self._read_scalars())
+
+    def _report_deferred(self):
+        """enqueue the packed device->host copy behind the step and return a handle; PendingReport.get() waits for
+        THAT copy only, so the caller can issue the next step first and read this one's losses while it runs"""
+        k = self._defer_k = (getattr(self, "_defer_k", -1) + 1) % 4
+        if not hasattr(self, "_defer_host"):
+            self._defer_host = [torch.zeros(N_SCALARS, dtype=torch.float32).pin_memory() for _ in range(4)]
+        host = self._defer_host[k]
+        host.copy_(self.scalars, non_blocking=True)
+        ev = torch.cuda.Event()
+        ev.record(torch.cuda.current_stream())
+        return PendingReport(self, host, ev)
+
     def _check_common(self, real_A, real_B, prior_z_B):
         for t in (real_A, real_B, prior_z_B):
             if not (t.is_cuda and t.dtype == torch.float32):
@@ -225,13 +251,17 @@ class _FusedCycleModel(object):
     def train_instance(self, real_A, real_B, prior_z_B, use_graph=False, report=True):
         """model.py:402-539 / :126-208.  use_graph=True replays a CUDA graph of the whole step (captured on
         first use for this batch shape; inputs are copied into static buffers).  report=False skips the
-        device->host read and returns (None, visuals, None)."""
+        device->host read and returns (None, visuals, None); report="defer" returns (PendingReport, visuals, None):
+        the read is enqueued behind the step and resolved by PendingReport.get() -> (losses, gnorms), at most four
+        steps later."""
         ins = self._check_inputs(real_A, real_B, prior_z_B)
         visuals = self._run("train", self._step_device, ins, use_graph)
         visuals = OrderedDict(visuals)
         visuals['real_A'], visuals['real_B'] = ins[0], ins[1]
         if not report:
             return None, visuals, None
+        if report == "defer":
+            return self._report_deferred(), visuals, None
         losses, gnorms = self._report()
         if self.opt.monitor_gnorm:
             return losses, visuals, gnorms
@@ -567,9 +597,8 @@ class AugmentedCycleGAN(_FusedCycleModel):
                              "(LatentEncoder yields [N, nlatent] only at 64x64); StochCycleGAN takes any size")
         return ins
 
-    def _report(self):
-        """the reference's OrderedDicts (model.py:518-537) from one packed read"""
-        s = self._read_scalars()
+    def _dicts(self, s):
+        """the reference's OrderedDicts (model.py:518-537) from the packed reporting vector"""
         losses = OrderedDict([('D_A', 0.5 * (s[S_DFA] + s[S_DTA])), ('G_A', s[S_GA]), ('Cyc_A', s[S_CYCA]),
                               ('Cyc_z_B', s[S_CYCZ]), ('KLD_z_B', s[S_KLD]),
                               ('D_B', 0.5 * (s[S_DFB] + s[S_DTB])), ('G_B', s[S_GB]), ('Cyc_B', s[S_CYCB]),
@@ -847,9 +876,8 @@ class StochCycleGAN(_FusedCycleModel):
         return OrderedDict([('real_A', real_A), ('fake_B', r["fake_B"]), ('rec_A', r["rec_A"]),
                             ('real_B', real_B), ('fake_A', r["fake_A"]), ('rec_B', r["rec_B"])])
 
-    def _report(self):
+    def _dicts(self, s):
         """model.py:193-206"""
-        s = self._read_scalars()
         losses = OrderedDict([('D_A', 0.5 * (s[S_DFA] + s[S_DTA])), ('G_A', s[S_GA]), ('Cyc_A', s[S_CYCA]),
                               ('D_B', 0.5 * (s[S_DFB] + s[S_DTB])), ('G_B', s[S_GB]), ('Cyc_B', s[S_CYCB]),
                               ('P_t_A', s[S_PTA]), ('P_f_A', s[S_PFA]), ('P_t_B', s[S_PTB]), ('P_f_B', s[S_PFB])])

@@ -127,3 +127,28 @@ def test_variational_ubo_on_the_fused_model_matches_oracle():
     with torch.no_grad():
         ref_mse = float(torch.nn.functional.mse_loss(om.G_B_A(b), a))
     assert abs(ev.eval_mse_A(data, ours) - ref_mse) <= 5e-3 * ref_mse
+
+
+def test_deferred_report_equals_immediate_report():
+    """train_instance(report="defer"): the losses resolved later (after the next step has been issued) are those of
+    their own step"""
+    engine.set_precision("bf16")
+    opt = argparse.Namespace(**vars(ostep.default_opt()), expr_dir="/tmp", niter_decay=25)
+    state = onets.init_model_state(seed=5, perturb=0.02)
+    a, b, z = [t.to(DEV) for t in ostep.synthetic_batch(4, seed=3)]
+
+    def build():
+        m = dmodel.AugmentedCycleGAN(opt, testing=True)
+        for name, net in m._nets().items():
+            net.load_state_dict({k: v.clone() for k, v in state[name].items()}, strict=False)
+        m.prepare()
+        for net in m._nets().values():
+            net._ex.repack()
+        return m
+
+    m1, m2 = build(), build()
+    now = [m1.train_instance(a, b, z, use_graph=True) for _ in range(4)]
+    handles = [m2.train_instance(a, b, z, use_graph=True, report="defer")[0] for _ in range(4)]      # all four in flight
+    for (l1, _, g1), h in zip(now, handles):
+        l2, g2 = h.get()
+        assert dict(l1) == dict(l2) and dict(g1) == dict(g2)
