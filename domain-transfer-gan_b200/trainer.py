@@ -92,6 +92,61 @@ class UnalignedIterator(AlignedIterator):
         return a, b
 
 
+# ---- .npz ingestion (dataloader.py:13-59) ------------------------------------------------------------------------------
+DEV_SIZE = 200
+
+
+def _py2_shuffle(x, rng):
+    """random.shuffle as Python 2.7 implements it (``j = int(random() * (i + 1))``); Python 3 draws the indices
+    differently, so the reference's seeded train / dev split (dataloader.py:44-51) is only reproduced this way"""
+    for i in reversed(range(1, len(x))):
+        j = int(rng.random() * (i + 1))
+        x[i], x[j] = x[j], x[i]
+
+
+def preprocess_fields(arr, grid_size=None):
+    """dataloader.py:17-34 for one array [b, h, w(, c)]: first three channels, NaN -> 0, per-sample / per-channel
+    min-max scaling to [-1, 1] (constant fields -> 0), optional resize to grid_size x grid_size, NHWC -> NCHW float32.
+    The reference resizes with skimage.transform.resize (not available here, and its defaults changed between
+    versions); this uses bilinear interpolation with anti-aliasing when shrinking -- the one documented deviation."""
+    arr = np.asarray(arr)[..., :3]
+    arr = np.nan_to_num(arr)
+    if arr.ndim == 3:
+        arr = np.expand_dims(arr, axis=2)
+    lo = arr.min((1, 2))[:, np.newaxis, np.newaxis]
+    hi = arr.max((1, 2))[:, np.newaxis, np.newaxis]
+    with np.errstate(divide="ignore", invalid="ignore"):
+        arr = -1 + 2 * (arr - lo) / (hi - lo)
+    arr = np.nan_to_num(arr, nan=0.0, posinf=0.0, neginf=0.0)
+    if grid_size is not None and (arr.shape[1] != grid_size or arr.shape[2] != grid_size):
+        t = torch.from_numpy(np.ascontiguousarray(arr.transpose(0, 3, 1, 2))).double()
+        shrink = grid_size < min(arr.shape[1], arr.shape[2])
+        t = torch.nn.functional.interpolate(t, size=(grid_size, grid_size), mode="bilinear", align_corners=False,
+                                            antialias=bool(shrink))
+        return t.float().numpy()
+    return np.ascontiguousarray(arr.transpose(0, 3, 1, 2)).astype('float32')
+
+
+def load_numpy_data(root, shuffle=True, grid_size=None):
+    """dataloader.py:13-59: {train,test}{A,B}.npz (key 'data') -> (trainA, trainB, devA, devB, testA, testB); the first
+    DEV_SIZE shuffled training samples become the dev split.  Note the reference quirk kept here: a 3-D array
+    [b, h, w] gets its channel axis inserted at position 2 (dataloader.py:20-21), i.e. it is read as [b, h, 1, w]."""
+    import os
+    import random
+
+    def _load(fname):
+        return preprocess_fields(np.load(os.path.join(root, fname))['data'], grid_size)
+
+    trainA, trainB = _load("trainA.npz"), _load("trainB.npz")
+    testA, testB = _load("testA.npz"), _load("testB.npz")
+    if shuffle:
+        indx = list(range(len(trainA)))
+        _py2_shuffle(indx, random.Random(123))          # random.seed(123); random.shuffle(indx) under Python 2
+        trainA, trainB = trainA[indx], trainB[indx]
+    devA, devB = trainA[:DEV_SIZE], trainB[:DEV_SIZE]
+    return trainA[DEV_SIZE:], trainB[DEV_SIZE:], devA, devB, testA, testB
+
+
 # ---- input staging ---------------------------------------------------------------------------------------------------
 class StagedBatches(object):
     """Wrap a batch iterator (dicts with float32 'A' / 'B' host tensors).  A staging thread copies each batch into one

@@ -166,3 +166,45 @@ def test_evaluate_port_matches_live_reference():
     assert abs(o_bpp - r_bpp) <= 1e-4 * abs(r_bpp)
     data = [{'A': a, 'B': b}, {'A': a.flip(0), 'B': b.flip(0)}]
     assert abs(ev.eval_mse_A(data, fresh(), device="cpu") - ref_ev.eval_mse_A(data, fresh(), use_gpu=False)) < 1e-6
+
+
+def test_preprocess_fields_follows_the_loader_arithmetic():
+    """dataloader.py:17-34 restated with plain loops on a small field stack with NaNs (ocean cells), a constant
+    channel and a fourth channel that must be dropped"""
+    g = np.random.RandomState(1)
+    arr = g.randn(5, 6, 7, 4).astype(np.float64) * 3 + 2
+    arr[0, 1:3, 2:5, 0] = np.nan
+    arr[2, :, :, 1] = 4.25                       # constant field: (x - min) / 0 -> NaN -> 0
+    out = trainer.preprocess_fields(arr)
+    assert out.shape == (5, 3, 6, 7) and out.dtype == np.float32
+    for b in range(5):
+        for c in range(3):
+            f = np.nan_to_num(arr[b, :, :, c])
+            lo, hi = f.min(), f.max()
+            exp = np.zeros_like(f) if hi == lo else -1 + 2 * (f - lo) / (hi - lo)
+            assert np.allclose(out[b, c], exp, atol=1e-6), (b, c)
+    assert out.min() >= -1 - 1e-6 and out.max() <= 1 + 1e-6 and np.all(out[2, 1] == 0)
+    small = trainer.preprocess_fields(arr, grid_size=4)
+    assert small.shape == (5, 3, 4, 4) and np.isfinite(small).all() and abs(small).max() <= 1 + 1e-5
+    same = trainer.preprocess_fields(arr[:, :6, :6], grid_size=6)          # already at grid_size: no resampling
+    assert np.array_equal(same, trainer.preprocess_fields(arr[:, :6, :6]))
+
+
+def test_load_numpy_data_split_and_python2_shuffle(tmp_path):
+    n = 230
+    base = np.arange(n, dtype=np.float64)[:, None, None, None] + np.linspace(0, 1, 4 * 4 * 3).reshape(1, 4, 4, 3)
+    for name, off in (("trainA", 0.0), ("trainB", 1000.0), ("testA", 0.0), ("testB", 0.0)):
+        np.savez(str(tmp_path / (name + ".npz")), data=(base + off) if name.startswith("train") else base[:7])
+    trA, trB, dvA, dvB, teA, teB = trainer.load_numpy_data(str(tmp_path))
+    assert trA.shape == (30, 3, 4, 4) and dvA.shape == (200, 3, 4, 4) and teA.shape == (7, 3, 4, 4) and trB.shape == trA.shape
+    # the permutation is Python 2.7's random.shuffle under seed 123: j = int(random() * (i + 1)) on the MT19937 stream
+    import random
+    rng = random.Random(123)
+    idx = list(range(n))
+    for i in reversed(range(1, n)):
+        j = int(rng.random() * (i + 1))
+        idx[i], idx[j] = idx[j], idx[i]
+    plain = trainer.load_numpy_data(str(tmp_path), shuffle=False)
+    allA = np.concatenate([plain[2], plain[0]])                 # unshuffled order: dev (first 200) then train
+    assert np.array_equal(np.concatenate([dvA, trA]), allA[idx])
+    assert np.array_equal(np.concatenate([dvB, trB]), np.concatenate([plain[3], plain[1]])[idx])   # A and B stay paired
