@@ -50,6 +50,7 @@ struct WgradParams {
   int a_load_blocks;                 // p channel blocks actually loaded; the others read a shared all-zero block
   int zero_off;                      // byte offset of the zero block from the smem base
   float* ws;
+  int dbg;                           // DTG_WGRAD_DBG experiments: 1 = no MMAs, 2 = no TMA loads, 4 = no epilogue stores
 };
 
 template <bool TF32>
@@ -118,6 +119,15 @@ __global__ void __launch_bounds__(kWThreads, 1) wgrad_kernel(const __grid_consta
         const int a0 = th * p.bh, b0 = tw * p.bw, n0 = tn * p.bn;
         mbar_wait(&bar_empty[stage], phase ^ 1);
         uint8_t* s = smem + stage * stage_bytes;
+        if (p.dbg & 2) {
+          if (elect_one()) mbar_arrive(&bar_full[stage]);
+          __syncwarp();
+          if (++stage == S) {
+            stage = 0;
+            phase ^= 1;
+          }
+          continue;
+        }
         if (elect_one()) mbar_expect_tx(&bar_full[stage], tx_bytes);
         __syncwarp();
         for (int blk = 0; blk < p.a_load_blocks; ++blk)
@@ -155,7 +165,7 @@ __global__ void __launch_bounds__(kWThreads, 1) wgrad_kernel(const __grid_consta
         // second p channel block: either loaded right behind the first or the shared zero block (LBO reaches it)
         const uint32_t a_lbo = p.a_load_blocks < p.nblkA ? smem_u32(smem + p.zero_off) - sa : static_cast<uint32_t>(p.blk_bytes);
         const uint64_t ad0 = umma_desc_sw128(sa, a_lbo, TF32 ? 512 : 1024, TF32 ? 1 : 2);
-        const int nk = p.kp / UK;
+        const int nk = (p.dbg & 1) ? 0 : p.kp / UK;
         if (p.patch) {
           const uint64_t bq0 = umma_desc_sw128(sa + a_bytes, p.q_blk_bytes, TF32 ? 512 : 1024, TF32 ? 1 : 2);
           if (elect_one()) {
@@ -211,7 +221,7 @@ __global__ void __launch_bounds__(kWThreads, 1) wgrad_kernel(const __grid_consta
           float4 o = any ? make_float4(__uint_as_float(v[4 * q]), __uint_as_float(v[4 * q + 1]),
                                        __uint_as_float(v[4 * q + 2]), __uint_as_float(v[4 * q + 3]))
                          : make_float4(0.f, 0.f, 0.f, 0.f);
-          dst[static_cast<size_t>(c0 / 4 + q) * p.mtot] = o;
+          if (!(p.dbg & 4)) dst[static_cast<size_t>(c0 / 4 + q) * p.mtot] = o;
         }
       }
     }
@@ -228,66 +238,72 @@ __global__ void __launch_bounds__(kWThreads, 1) wgrad_kernel(const __grid_consta
 // dw[(a*qb + b)*ntaps + t] += sum_s ws[(((s*ntaps + t)*(n_umma/4) + b/4)*mtot + a)*4 + b%4]
 // fold = 1: accumulator column b' = j*fc + b holds filter column kw = j          (t = kh, KW real columns)
 // fold = 2: accumulator row    a' = j*fc + a holds filter column kw = KW - 1 - j
-__global__ void __launch_bounds__(256) wgrad_reduce_kernel(const float* __restrict__ ws, float* __restrict__ dw, int splits,
+// One thread per float4 of accumulator columns: consecutive threads take consecutive rows (= consecutive float4 of the
+// workspace: every warp load is 512 contiguous bytes), all split loads of a thread are independent (16 in flight) and
+// summed in split order (deterministic, no atomics, no shared memory, no barrier).
+__global__ void __launch_bounds__(256) wgrad_reduce_kernel(const float4* __restrict__ ws, float* __restrict__ dw, int splits,
                                                            int ntaps, int mtot, int n_umma, int pa, int qb, int fold, int KW,
-                                                           int fc) {
+                                                           int fc, int rows, int total) {
   pdl_enter();
-  // block = 32 float4 columns x 8 split lanes: lane l sums splits l, l+8, ... (independent loads), then the 8 lane
-  // partials are added in a fixed order (deterministic); one thread per float4 writes.
-  __shared__ float4 sh[8][32];
+  const int i = blockIdx.x * 256 + threadIdx.x;
+  if (i >= total) return;
   const int ncol4 = n_umma / 4;
-  const int rows = fold == 2 ? KW * fc : pa;          // accumulator rows that hold data
-  const int total = ntaps * rows * ncol4;
-  const size_t sstride = static_cast<size_t>(ntaps) * mtot * n_umma;
-  const int cl = threadIdx.x & 31, sl = threadIdx.x >> 5;
-  for (int i0 = blockIdx.x * 32; i0 < total; i0 += gridDim.x * 32) {
-    const int i = i0 + cl;
-    const bool ok = i < total;
-    const int row = ok ? i % rows : 0;
-    const int c4 = ok ? (i / rows) % ncol4 : 0;
-    const int t = ok ? i / (ncol4 * rows) : 0;
-    const float* src = ws + ((static_cast<size_t>(t) * ncol4 + c4) * mtot + row) * 4;
-    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
-    if (ok) {
-#pragma unroll 4
-      for (int s = sl; s < splits; s += 8) {
-        const float4 v = *reinterpret_cast<const float4*>(src + s * sstride);
-        acc.x += v.x;
-        acc.y += v.y;
-        acc.z += v.z;
-        acc.w += v.w;
-      }
-    }
-    __syncthreads();
-    sh[sl][cl] = acc;
-    __syncthreads();
-    if (sl != 0 || !ok) continue;
+  const int row = i % rows;
+  const int c4 = (i / rows) % ncol4;
+  const int t = i / (ncol4 * rows);
+  const float4* src = ws + (static_cast<size_t>(t) * ncol4 + c4) * mtot + row;
+  const size_t sstride = static_cast<size_t>(ntaps) * mtot * ncol4;
+  float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+  int s = 0;
+  for (; s + 16 <= splits; s += 16) {
+    float4 v[16];
 #pragma unroll
-    for (int l = 1; l < 8; ++l) {
-      acc.x += sh[l][cl].x;
-      acc.y += sh[l][cl].y;
-      acc.z += sh[l][cl].z;
-      acc.w += sh[l][cl].w;
-    }
-    const float av[4] = {acc.x, acc.y, acc.z, acc.w};
+    for (int u = 0; u < 16; ++u) v[u] = __ldcg(src + (s + u) * sstride);
 #pragma unroll
-    for (int e = 0; e < 4; ++e) {
-      const int col = c4 * 4 + e;
-      int a = row, b = col, j = 0;
-      if (fold == 1) {
-        j = col / fc;
-        b = col % fc;
-      } else if (fold == 2) {
-        j = row / fc;
-        a = row % fc;
-      }
-      if (a >= pa || b >= qb || j >= KW) continue;
-      if (fold) {
-        const int kw = fold == 2 ? KW - 1 - j : j;
-        dw[((static_cast<size_t>(a) * qb + b) * ntaps + t) * KW + kw] += av[e];
-      } else {
-        dw[(static_cast<size_t>(a) * qb + b) * ntaps + t] += av[e];
-      }
+    for (int u = 0; u < 16; ++u) {
+      acc.x += v[u].x;
+      acc.y += v[u].y;
+      acc.z += v[u].z;
+      acc.w += v[u].w;
+    }
+  }
+  for (; s + 4 <= splits; s += 4) {
+    float4 v[4];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) v[u] = __ldcg(src + (s + u) * sstride);
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      acc.x += v[u].x;
+      acc.y += v[u].y;
+      acc.z += v[u].z;
+      acc.w += v[u].w;
+    }
+  }
+  for (; s < splits; ++s) {
+    const float4 v = __ldcg(src + s * sstride);
+    acc.x += v.x;
+    acc.y += v.y;
+    acc.z += v.z;
+    acc.w += v.w;
+  }
+  const float av[4] = {acc.x, acc.y, acc.z, acc.w};
+#pragma unroll
+  for (int e = 0; e < 4; ++e) {
+    const int col = c4 * 4 + e;
+    int a = row, b = col, j = 0;
+    if (fold == 1) {
+      j = col / fc;
+      b = col % fc;
+    } else if (fold == 2) {
+      j = row / fc;
+      a = row % fc;
+    }
+    if (a >= pa || b >= qb || j >= KW) continue;
+    if (fold) {
+      const int kw = fold == 2 ? KW - 1 - j : j;
+      dw[((static_cast<size_t>(a) * qb + b) * ntaps + t) * KW + kw] += av[e];
+    } else {
+      dw[(static_cast<size_t>(a) * qb + b) * ntaps + t] += av[e];
     }
   }
 }
@@ -440,6 +456,10 @@ extern "C" int dtg_conv_wgrad(const dtg_wgrad_args* a, const dtg_plane* pp, cons
   p.a_load_blocks = pl.a_load_blocks;
   p.zero_off = pl.stages * pl.stage_bytes + 1024;      // behind the stages and the barrier block
   p.ws = reinterpret_cast<float*>(workspace);
+  {
+    static const int dbgv = getenv("DTG_WGRAD_DBG") ? atoi(getenv("DTG_WGRAD_DBG")) : 0;
+    p.dbg = dbgv;
+  }
 
   const int s = a->stride, hl = q->halo;
   const int fold = a->fold;
@@ -535,9 +555,9 @@ extern "C" int dtg_conv_wgrad(const dtg_wgrad_args* a, const dtg_plane* pp, cons
     DTG_CHECK_CUDA(launch_k(wgrad_kernel<true>, grid, kWThreads, smem, stream, p));
   else
     DTG_CHECK_CUDA(launch_k(wgrad_kernel<false>, grid, kWThreads, smem, stream, p));
-  const int total = pl.ntaps * (fold == 2 ? a->kw * (16 / es) : a->pa) * (pl.n_umma / 4);
-  const int rgrid = std::max(1, std::min((total + 31) / 32, 148 * 16));
-  DTG_CHECK_CUDA(launch_k(wgrad_reduce_kernel, rgrid, 256, 0, stream, p.ws, dw, pl.splits, pl.ntaps, p.mtot, pl.n_umma, a->pa, a->qb, fold, a->kw,
-                                                 16 / es));
+  const int rrows = fold == 2 ? a->kw * (16 / es) : a->pa;
+  const int total = pl.ntaps * rrows * (pl.n_umma / 4);
+  DTG_CHECK_CUDA(launch_k(wgrad_reduce_kernel, (total + 255) / 256, 256, 0, stream, reinterpret_cast<const float4*>(p.ws), dw, pl.splits,
+                          pl.ntaps, p.mtot, pl.n_umma, a->pa, a->qb, fold, a->kw, 16 / es, rrows, total));
   return DTG_OK;
 }

@@ -94,4 +94,11 @@ int try_norm_bwd_fused(const dtg_norm_args* a, const dtg_plane* dy, const dtg_pl
                        const dtg_plane* x, const float* stats, const float* gamma, float* sums, const dtg_plane* dx,
                        const dtg_plane* d_res, cudaStream_t stream);
 
+// TMA-staged persistent-cluster forward / backward (norm_tma.cu); same return convention
+int try_norm_fwd_tma(const dtg_norm_args* a, const dtg_plane* x, const dtg_plane* residual, const float* gamma,
+                     const float* beta, float* stats, const dtg_plane* out, cudaStream_t stream);
+int try_norm_bwd_tma(const dtg_norm_args* a, const dtg_plane* dy, const dtg_plane* dy2, const dtg_plane* y,
+                     const dtg_plane* x, const float* stats, const float* gamma, float* sums, const dtg_plane* dx,
+                     const dtg_plane* d_res, cudaStream_t stream);
+
 }  // namespace dtg
