@@ -60,6 +60,21 @@ def _oracle_for(wl, device="cpu"):
     return om, mk
 
 
+def _reference_for(wl, device="cpu"):
+    """(model, kind): the UNMODIFIED reference model.py (staged under baseline/_ref/ by oracle/stage_ref.py, or
+    /root/reference in the build container; `.data[0]` -> `.item()` reporting shim only) -> kind "reference"; the oracle
+    port when the sources are not available -> kind "port"."""
+    import copy
+    from oracle import live_reference as lr, nets as onets, step as ostep
+    if not lr.available():
+        return _oracle_for(wl, device)[0], "port"
+    opt = ostep.default_opt(output_nc=wl["output_nc"])
+    opt.gpu_ids = [torch.cuda.current_device()] if device != "cpu" else []
+    opt.expr_dir = "/tmp"
+    state = onets.init_model_state(seed=1234, output_nc=wl["output_nc"])
+    return lr.build_reference_model(copy.deepcopy(opt), state, stoch=wl["model"] != "aug"), "reference"
+
+
 def _peaks():
     try:
         return json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
@@ -109,16 +124,87 @@ class ClockSampler(threading.Thread):
         return out
 
 
-def _ncu_traffic():
-    """DRAM bytes per launch (dram__bytes_read.sum + dram__bytes_write.sum) of the residual-stack conv, from the committed
-    ncu --set full summary; None when the profile is not in the tree."""
-    for fn, key in (("r1b_ncu_summary.json", "pconv2_kernel_res_conv"), ("r1_ncu_summary.json", "igemm_kernel_res_conv")):
+def _ncu_traffic(workload, kernel):
+    """DRAM bytes per launch (dram__bytes_read.sum + dram__bytes_write.sum) of the dominant kernel from the committed
+    `ncu --set full` summaries (profiles/*ncu_summary.json: {capture: {kernel, workload, dram_bytes_read, ...}}); None
+    when no capture of THIS workload and kernel is in the tree."""
+    import glob
+    best = None
+    for fn in sorted(glob.glob(os.path.join(ROOT, "profiles", "*ncu_summary.json"))):
         try:
-            k = json.load(open(os.path.join(ROOT, "profiles", fn)))[key]
-            return k["dram_bytes_read"] + k["dram_bytes_write"]
+            for key, k in json.load(open(fn)).items():
+                if k.get("workload", "aug64") == workload and str(k.get("kernel", key)).split("<")[0].split("::")[-1] in kernel:
+                    best = k["dram_bytes_read"] + k["dram_bytes_write"]
         except Exception:
             continue
-    return None
+    return best
+
+
+def kernel_profile(m, dev, _lib, ops, replays=3):
+    """per-kernel device time of ONE serial step (see the call site); returns {"serial_us", "kernels": {name: {n, us,
+    flops, bytes}}, "ops": {op: {n, us}}} (per step)"""
+    from torch.profiler import ProfilerActivity, profile
+    snap = m._snapshot()
+    prev = _lib.set_option("pdl", 0)
+    m.lanes.enabled = False
+    try:
+        for _ in range(2):
+            m._step_device(*dev)
+        torch.cuda.synchronize()
+        ops.PROFILE = ops.OpLog()
+        g = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(g):
+            m._step_device(*dev)
+        log = list(ops.PROFILE.records)
+        ops.PROFILE = None
+        g.replay()
+        torch.cuda.synchronize()
+        with profile(activities=[ProfilerActivity.CUDA]) as prof:
+            for _ in range(replays):
+                g.replay()
+            torch.cuda.synchronize()
+        del g
+    finally:
+        ops.PROFILE = None
+        _lib.set_option("pdl", prev)
+        m.lanes.enabled = True
+        m._restore(snap)
+    ev = []
+    for k in prof.profiler.kineto_results.events():
+        if "CUDA" in str(k.device_type()) and k.duration_ns() > 0:
+            ev.append((k.start_ns(), k.duration_ns(), k.name()))
+    ev.sort()
+    span_us = (max(a + d for a, d, _ in ev) - ev[0][0]) / 1e3 / replays
+    own = [(d, n) for a, d, n in ev if "dtg::" in n]
+    per_step = sum(r[1] for r in log)
+    if per_step == 0 or len(own) != per_step * replays:
+        raise RuntimeError("kernel records (%d) do not match the op log (%d launches x %d replays)" % (len(own), per_step, replays))
+    kernels, opsum = {}, {}
+    for r in range(replays):
+        i = r * per_step
+        for name, nl, fl, by in log:
+            recs = own[i:i + nl]
+            i += nl
+            us = sum(d for d, _ in recs) / 1e3
+            o = opsum.setdefault(name, {"n": 0, "us": 0.0})
+            o["n"] += 1
+            o["us"] += us
+            # the op's algorithmic work belongs to its heaviest kernel (conv: the tcgen05 kernel; wgrad: wgrad_kernel,
+            # its split-K reduction is listed separately with no FLOPs of its own)
+            heavy = max(range(len(recs)), key=lambda j: recs[j][0]) if recs else -1
+            for j, (d, n) in enumerate(recs):
+                kn = n.split("(")[0].replace("void ", "").replace("dtg::", "")
+                kk = kernels.setdefault(kn, {"n": 0, "us": 0.0, "flops": 0.0, "bytes": 0.0})
+                kk["n"] += 1
+                kk["us"] += d / 1e3
+                if j == heavy:
+                    kk["flops"] += fl
+                    kk["bytes"] += by
+    for d in list(kernels.values()) + list(opsum.values()):
+        for f in d:
+            d[f] = d[f] / replays
+        d["n"] = int(round(d["n"]))
+    return {"serial_us": span_us, "kernels": kernels, "ops": opsum}
 
 
 def run_reference(args):
@@ -131,7 +217,8 @@ def run_reference(args):
     cores = os.cpu_count() or 1
     torch.set_num_threads(cores)
     sample_n = 8 if wl["size"] == 64 else 2
-    om, mk = _oracle_for(wl)
+    mk = _oracle_for(wl)[1]
+    om, kind = _reference_for(wl)
     a, b, z = mk(sample_n)
     for _ in range(max(1, min(args.warmup, 2))):
         om.train_instance(a, b, z)
@@ -145,9 +232,10 @@ def run_reference(args):
             "warmup": max(1, min(args.warmup, 2)), "ms_per_step": 1e3 * dt / steps, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": {"workload": _desc(wl, args), "sample": "batch %d of the batch-%d workload per step" % (sample_n, args.batch or wl["batch"])},
-            "cpu_baseline": {"value": v, "unit": UNIT, "cores": cores, "kind": "port",
-                             "sample": "%d train_instance steps at batch %d, torch %s CPU fp32, %d threads"
-                                       % (steps, sample_n, torch.__version__, cores)},
+            "cpu_baseline": {"value": v, "unit": UNIT, "cores": cores, "kind": kind,
+                             "sample": "%d train_instance steps at batch %d, %s, torch %s CPU fp32, %d threads"
+                                       % (steps, sample_n, "unmodified reference model.py" if kind == "reference" else "oracle port",
+                                          torch.__version__, cores)},
             "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     print(json.dumps(line))
 
@@ -161,7 +249,8 @@ def cpu_baseline(wl):
     cores = os.cpu_count() or 1
     torch.set_num_threads(cores)
     n = 8 if wl["size"] == 64 else 2
-    om, mk = _oracle_for(wl)
+    mk = _oracle_for(wl)[1]
+    om, kind = _reference_for(wl)
     a, b, z = mk(n)
     om.train_instance(a, b, z)
     steps, t0 = 0, time.perf_counter()
@@ -169,40 +258,63 @@ def cpu_baseline(wl):
         om.train_instance(a, b, z)
         steps += 1
     dt = time.perf_counter() - t0
-    return {"value": n * steps / dt, "unit": UNIT, "cores": cores, "kind": "port",
-            "sample": "%d train_instance steps at batch %d%s, torch %s CPU fp32, %d threads"
+    return {"value": n * steps / dt, "unit": UNIT, "cores": cores, "kind": kind,
+            "sample": "%d train_instance steps at batch %d%s, %s, torch %s CPU fp32, %d threads"
                       % (steps, n, " (config 1)" if wl["model"] == "aug" else " at %dx%d" % (wl["size"], wl["size"]),
-                         torch.__version__, cores)}
+                         "unmodified reference model.py" if kind == "reference" else "oracle port", torch.__version__, cores)}
 
 
 def torch_gpu_baseline(n, wl):
-    """The reference's PyTorch path on this B200 (oracle port = same torch ops / cuDNN kernels), as the
-    denominator of north_star's >=15x target: best of fp32(TF32 conv) and bf16 autocast."""
+    """The reference's own PyTorch path on this B200 -- the denominator of north_star's >= 15x target (BASELINE.md 3,
+    B2): the unmodified model.py (kind "reference"; the oracle port if the staged sources are missing) with fp32 / TF32
+    convolutions and under torch.autocast(bf16), each in NCHW and channels_last; `best` is the fastest of the four."""
     res = {}
     a, b, z = [t.cuda() for t in _oracle_for(wl)[1](n)]
-    for name in ("tf32", "bf16_autocast"):
+    kind = "port"
+    for name in ("tf32", "bf16_autocast", "tf32_channels_last", "bf16_autocast_channels_last"):
         torch.backends.cudnn.allow_tf32 = True
         torch.backends.cuda.matmul.allow_tf32 = True
         torch.backends.cudnn.benchmark = True
-        om = _oracle_for(wl, "cuda")[0]
+        try:
+            om, kind = _reference_for(wl, "cuda")
+            xa, xb = a, b
+            if name.endswith("channels_last"):
+                if kind != "reference":
+                    continue
+                for k in ("netG_A_B", "netG_B_A", "netE_B", "netD_A", "netD_B", "netD_z_B"):
+                    if hasattr(om, k):
+                        getattr(om, k).to(memory_format=torch.channels_last)
+                xa, xb = a.contiguous(memory_format=torch.channels_last), b.contiguous(memory_format=torch.channels_last)
 
-        def one():
-            if name == "tf32":
-                om.train_instance(a, b, z)
-            else:
-                with torch.autocast("cuda", dtype=torch.bfloat16):
-                    om.train_instance(a, b, z)
-        for _ in range(3):
-            one()
-        torch.cuda.synchronize()
-        t0 = time.perf_counter()
-        k = 8
-        for _ in range(k):
-            one()
-        torch.cuda.synchronize()
-        res[name] = n * k / (time.perf_counter() - t0)
+            def one():
+                if name.startswith("tf32"):
+                    om.train_instance(xa, xb, z)
+                else:
+                    with torch.autocast("cuda", dtype=torch.bfloat16):
+                        om.train_instance(xa, xb, z)
+            import warnings
+            with warnings.catch_warnings():
+                warnings.simplefilter("ignore")
+                for _ in range(3):
+                    one()
+                torch.cuda.synchronize()
+                t0 = time.perf_counter()
+                k = 8
+                for _ in range(k):
+                    one()
+                torch.cuda.synchronize()
+            res[name] = n * k / (time.perf_counter() - t0)
+        except Exception as e:
+            res[name + "_error"] = str(e).splitlines()[0][:160]
+        finally:
+            torch.backends.cudnn.allow_tf32 = False
+            torch.backends.cuda.matmul.allow_tf32 = False
+    vals = [v for k, v in res.items() if not k.endswith("_error")]
+    res["best"] = max(vals) if vals else None
     res["unit"] = UNIT
-    res["note"] = "oracle port of the reference step on cuda (cuDNN/ATen), batch %d, includes its 23 host syncs" % n
+    res["kind"] = kind
+    res["note"] = ("%s step on cuda (cuDNN / ATen), batch %d, includes its >= 23 host syncs per step"
+                   % ("unmodified reference model.py" if kind == "reference" else "oracle port of the reference", n))
     return res
 
 
@@ -368,38 +480,53 @@ def main():
             "clocks": clocks,
             "conv_roofline_frac_of_step": value / world * FLOP_PER_IMAGE / ((_peaks() or {}).get("bf16_tflops_sustained", 1418.6) * 1e12)}
 
-    # ---- roofline of the dominant (tensor-core) kernels: instrumented eager pass.  EVERY rank runs the two steps
-    # (they contain the gradient / batch-norm collectives); rank 0 reports its own timings.
-    snap = m._snapshot()
-    ops.PROFILE = ops.KernelProfile()
-    m.lanes.enabled = False           # one stream: every kernel is timed alone, not against a concurrent branch
-    for _ in range(2):
-        m._step_device(*dev)
-    torch.cuda.synchronize()
-    m.lanes.enabled = True
-    summ = ops.PROFILE.summary()
-    ops.PROFILE = None
-    m._restore(snap)
+    # ---- per-kernel roofline: ONE serial step (single stream, programmatic dependent launch off) is captured in a CUDA
+    # graph and replayed under CUPTI (torch.profiler); every dtg:: kernel record is attributed to the ops.* call whose
+    # launch range covers it, which gives exact device durations per kernel (no host launch gaps, no time spent waiting
+    # on a predecessor) next to the algorithmic FLOPs / bytes of the call.  Numbers taken under the profiler explain the
+    # step; `value` / `e2e` above are never taken under it.  EVERY rank runs the pass (it contains the gradient and
+    # batch-norm collectives); rank 0 reports its own records.
+    kp = None
+    try:
+        kp = kernel_profile(m, dev, _lib, ops)
+    except Exception as e:      # CUPTI unavailable etc.: the line still carries value / e2e
+        sys.stderr.write("bench: kernel profile unavailable (%s)\n" % str(e).splitlines()[0][:200])
     say("instrumented pass done")
     if rank == 0:
         peaks = _peaks()
         peak = (peaks or {}).get("bf16_tflops_sustained", 1590.0 * 0.88)
+        hbm = (peaks or {}).get("hbm_gbs", 6650.0)
         if args.precision == "tf32":
             peak = peak / 2.0
-        tot_ms = sum(v["ms"] for v in summ.values())
-        tot_fl = sum(v["flops"] for v in summ.values())
-        if wl["model"] != "aug":     # algorithmic conv FLOPs of this workload = what the step's launches add up to
-            line["conv_roofline_frac_of_step"] = (tot_fl / 2) / (ms / K * 1e-3) / (peak * 1e12)
-        dom = max(summ, key=lambda k: summ[k]["ms"])
-        ach = summ[dom]["flops"] / (summ[dom]["ms"] * 1e-3) / 1e12
-        line["roofline"] = {"bound": "tensor", "kernel": dom + " (conv fwd/dgrad: igemm_kernel + pconv_kernel + pconv2_kernel)" if dom == "igemm_kernel" else dom,
-                            "achieved": ach, "peak": peak, "unit": "TFLOP/s",
-                            "frac": ach / peak, "traffic": _ncu_traffic(),
-                            "peak_source": "MEASURED_PEAKS.json bf16_tflops_sustained" if peaks else "fallback 1.59 PF x 0.88",
-                            "per_kernel": {k: {"tflops": v["flops"] / (v["ms"] * 1e-3) / 1e12, "ms_per_step": v["ms"] / 2,
-                                               "launches_per_step": v["launches"] // 2} for k, v in summ.items()},
-                            "tensor_kernels_share_of_step": (tot_ms / 2) / (ms / K),
-                            "all_tensor_kernels_tflops": tot_fl / (tot_ms * 1e-3) / 1e12}
+        if kp is not None:
+            tens = {k: v for k, v in kp["kernels"].items() if v["flops"] > 0}
+            tot_us = sum(v["us"] for v in tens.values())
+            tot_fl = sum(v["flops"] for v in tens.values())
+            if wl["model"] != "aug":     # algorithmic conv FLOPs of this workload = what the step's launches add up to
+                line["conv_roofline_frac_of_step"] = tot_fl / (ms / K * 1e-3) / (peak * 1e12)
+            dom = max(tens, key=lambda k: tens[k]["us"])
+            ach = tens[dom]["flops"] / (tens[dom]["us"] * 1e-6) / 1e12
+            per_kernel = {}
+            for k, v in sorted(kp["kernels"].items(), key=lambda kv: -kv[1]["us"]):
+                d = {"launches_per_step": v["n"], "us_per_step": round(v["us"], 1)}
+                if v["flops"] > 0:
+                    d["tflops"] = v["flops"] / (v["us"] * 1e-6) / 1e12
+                    d["frac_of_peak"] = d["tflops"] / peak
+                if v["bytes"] > 0:
+                    d["gbs"] = v["bytes"] / (v["us"] * 1e-6) / 1e9
+                    d["frac_of_hbm"] = d["gbs"] / hbm
+                per_kernel[k] = d
+            line["roofline"] = {"bound": "tensor", "kernel": dom, "achieved": ach, "peak": peak, "unit": "TFLOP/s",
+                                "frac": ach / peak, "traffic": _ncu_traffic(args.workload, dom),
+                                "peak_source": "MEASURED_PEAKS.json bf16_tflops_sustained" if peaks else "fallback 1.59 PF x 0.88",
+                                "hbm_peak_gbs": hbm,
+                                "how": "serial CUDA graph of one step, PDL off, CUPTI kernel durations (3 replays, mean)",
+                                "per_kernel": per_kernel,
+                                "serial_step_us": round(kp["serial_us"], 1),
+                                "tensor_kernels_us_per_step": round(tot_us, 1),
+                                "tensor_kernels_share_of_serial_step": tot_us / kp["serial_us"],
+                                "tensor_kernels_time_over_step_time": tot_us * 1e-3 / (ms / K),
+                                "all_tensor_kernels_tflops": tot_fl / (tot_us * 1e-6) / 1e12}
         if world == 1 and not args.no_baselines:
             try:
                 line["torch_gpu_baseline"] = torch_gpu_baseline(n, wl)

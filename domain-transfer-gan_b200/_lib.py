@@ -47,6 +47,7 @@ _SIGS = {
     "dtg_version": (C.c_int, []),
     "dtg_launch_count": (C.c_ulonglong, []),
     "dtg_last_error": (C.c_int, [C.c_char_p, C.c_size_t]),
+    "dtg_set_option": (C.c_int, [C.c_char_p, C.c_int]),
     "dtg_pack_weights": (C.c_int, [_P, C.c_int, C.c_int, _P]),
     "dtg_conv": (C.c_int, [C.POINTER(ConvArgs), C.POINTER(Plane), _P, C.c_int, C.c_int, _P, C.POINTER(Plane), _P, _P]),
     "dtg_conv_wgrad_workspace_bytes": (C.c_size_t, [C.POINTER(WgradArgs), C.POINTER(Plane), C.POINTER(Plane)]),
@@ -99,6 +100,14 @@ def lib():
             fn.argtypes = args
         _lib = l
     return _lib
+
+
+def set_option(key, value):
+    """dtg_set_option: returns the previous value"""
+    prev = lib().dtg_set_option(key.encode(), int(value))
+    if prev < 0:
+        raise RuntimeError("dtg_b200 set_option(%r) failed: %s" % (key, last_error()))
+    return prev
 
 
 def last_error():

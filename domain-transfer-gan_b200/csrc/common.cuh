@@ -37,6 +37,8 @@ void count_launch();
 // its prologue while this one drains; every kernel calls pdl_enter() (trigger + wait) before touching global memory,
 // so data dependencies (RAW and WAR) are still honoured.  DTG_NO_PDL=1 disables the attribute.
 bool pdl_enabled();
+bool tma_norm_enabled();       // dtg_set_option("tma_norm")
+bool wgrad_atomic_enabled();   // dtg_set_option("wgrad_atomic")
 #ifdef __CUDACC__
 template <typename... KArgs, typename... Args>
 inline cudaError_t launch_k(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t stream, Args&&... args) {
@@ -71,6 +73,12 @@ int encode_tiled(CUtensorMap* map, int dtype, int rank, void* base, const uint64
                  int swizzle /* 0 none, 1 = 128B (16-byte atoms), 2 = 128B with 32-byte atoms, 3 = 64B, 4 = 32B */);
 
 static inline int elem_size(int dtype) { return dtype == DTG_BF16 ? 2 : 4; }
+
+// Shared-memory budget (bytes) of ONE tensor-core CTA.  The tcgen05 kernels are persistent, one CTA per SM; what they
+// leave free decides whether a bandwidth-bound kernel of another stream (normalisation, losses, optimizer: ~22 KB of
+// static shared memory per CTA) can be co-resident on the same SM and stream from HBM while the tensor pipe works.
+// dtg_set_option("smem_cap_kb") / DTG_SMEM_CAP_KB.
+int tensor_smem_budget();
 
 // ------------------------------------------------------------------------------------------
 // device helpers

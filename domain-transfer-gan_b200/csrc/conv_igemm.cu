@@ -464,7 +464,7 @@ extern "C" int dtg_conv(const dtg_conv_args* a, const dtg_plane* in, const void*
   }
 
   const int stage_bytes = kATileBytes + p.n_umma * kRowBytes;
-  p.stages = std::max(2, std::min(8, (196 * 1024) / stage_bytes));
+  p.stages = std::max(2, std::min(8, (tensor_smem_budget() - 31 * 1024) / stage_bytes));    // + barriers, epilogue staging, alignment
   int cols = 32;
   while (cols < 2 * p.n_umma) cols <<= 1;
   p.tmem_cols = cols;

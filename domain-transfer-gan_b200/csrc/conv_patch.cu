@@ -269,7 +269,7 @@ int try_launch_pconv(const IgemmParams& g, const dtg_plane* in, const void* w, i
   if (PW > 256 || PH > 256) return 1;
   const int a_stage_bytes = (PW * PH * rb + 1023) & ~1023;
   const int fixed = 1024 + ((b_bytes + 1023) & ~1023) + 1024 + 4 * std::max(kEpiWarpBytes, kEpiTmaWarpBytes);
-  const int budget = 227 * 1024 - fixed;
+  const int budget = tensor_smem_budget() - fixed;
   if (b_bytes > 120 * 1024 || budget < 2 * a_stage_bytes) return 1;
   const int OHp = g.ph_OH[0], OWp = g.ph_OW[0];
   if (OWp < kPW || OHp < 4) return 1;      // tiny images: the batch-tiled per-tap kernel wastes less

@@ -273,7 +273,7 @@ int try_launch_pconv2(const IgemmParams& g, const dtg_plane* in, const void* w, 
   if (OWp < kP2W || OHp < 8 || PW > 256 || PH > 256) return 1;
   if (OWp % kP2W != 0 || OHp % kP2H != 0) return 1;     // ragged 8x16 tilings (e.g. 34x34 ring outputs) waste > 40 % of the MMAs
   const int epi = 4 * std::max(kEpiWarpBytes, kEpiTmaWarpBytes);
-  const int budget = 227 * 1024 - 1024 - 1024 - epi;
+  const int budget = tensor_smem_budget() - 1024 - 1024 - epi;
   // ring sizes: at least the 2*kchunks patch units of one item plus one to prefetch; 3-4 weight stages
   // the weight ring must cover the L2 round trip (a stage is consumed in 8 MMAs = 512 clk): as many stages as fit
   // next to the 2*kchunks patch units of one item

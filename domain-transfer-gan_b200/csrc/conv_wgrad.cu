@@ -50,6 +50,7 @@ struct WgradParams {
   int a_load_blocks;                 // p channel blocks actually loaded; the others read a shared all-zero block
   int zero_off;                      // byte offset of the zero block from the smem base
   float* ws;
+  int rows_valid, cols_valid;        // accumulator rows / columns that hold data (the rest is zero padding: never stored)
   int dbg;                           // DTG_WGRAD_DBG experiments: 1 = no MMAs, 2 = no TMA loads, 4 = no epilogue stores
 };
 
@@ -207,12 +208,13 @@ __global__ void __launch_bounds__(kWThreads, 1) wgrad_kernel(const __grid_consta
     const bool any = t_end > t_begin;
     // workspace layout [split][tap][column / 4][row][4]: the 32 lanes of a warp hold 32 consecutive rows, so every
     // float4 store instruction writes 512 contiguous bytes
-    for (int tl = 0; tl < ntl; ++tl) {
+    const bool rows_live = mblock * 128 + quad * 32 < p.rows_valid;      // warp-uniform
+    for (int tl = 0; tl < (rows_live ? ntl : 0); ++tl) {
       const int t = tap0 + tl;
       float4* dst = reinterpret_cast<float4*>(p.ws) + (static_cast<size_t>(split) * p.ntaps + t) * (p.n_umma / 4) * p.mtot +
                     mblock * 128 + row;
       const uint32_t taddr = tmem_base + (static_cast<uint32_t>(quad * 32) << 16) + tl * p.n_umma;
-      for (int c0 = 0; c0 < p.n_umma; c0 += 16) {
+      for (int c0 = 0; c0 < p.cols_valid; c0 += 16) {
         uint32_t v[16];
         tmem_ld16(taddr + c0, v);
         tmem_ld_wait();
@@ -243,14 +245,14 @@ __global__ void __launch_bounds__(kWThreads, 1) wgrad_kernel(const __grid_consta
 // summed in split order (deterministic, no atomics, no shared memory, no barrier).
 __global__ void __launch_bounds__(256) wgrad_reduce_kernel(const float4* __restrict__ ws, float* __restrict__ dw, int splits,
                                                            int ntaps, int mtot, int n_umma, int pa, int qb, int fold, int KW,
-                                                           int fc, int rows, int total) {
+                                                           int fc, int rows, int ncv4, int total) {
   pdl_enter();
   const int i = blockIdx.x * 256 + threadIdx.x;
   if (i >= total) return;
   const int ncol4 = n_umma / 4;
   const int row = i % rows;
-  const int c4 = (i / rows) % ncol4;
-  const int t = i / (ncol4 * rows);
+  const int c4 = (i / rows) % ncv4;
+  const int t = i / (ncv4 * rows);
   const float4* src = ws + (static_cast<size_t>(t) * ncol4 + c4) * mtot + row;
   const size_t sstride = static_cast<size_t>(ntaps) * mtot * ncol4;
   float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -403,7 +405,7 @@ static int make_plan(const dtg_wgrad_args* a, const dtg_plane* pp, const dtg_pla
   pl->T = pl->tiles_w * pl->tiles_h * pl->tiles_n;
   stage_bytes = (stage_bytes + 1023) & ~1023;
   pl->stage_bytes = stage_bytes;
-  pl->stages = std::max(2, std::min(6, (180 * 1024) / stage_bytes));
+  pl->stages = std::max(2, std::min(6, std::min(180 * 1024, tensor_smem_budget() - 12 * 1024) / stage_bytes));
   int cols = 32;
   while (cols < pl->tpg * pl->n_umma) cols <<= 1;
   pl->tmem_cols = cols;
@@ -456,6 +458,8 @@ extern "C" int dtg_conv_wgrad(const dtg_wgrad_args* a, const dtg_plane* pp, cons
   p.a_load_blocks = pl.a_load_blocks;
   p.zero_off = pl.stages * pl.stage_bytes + 1024;      // behind the stages and the barrier block
   p.ws = reinterpret_cast<float*>(workspace);
+  p.rows_valid = a->fold == 2 ? a->kw * (16 / es) : a->pa;
+  p.cols_valid = std::min(pl.n_umma, ((a->fold == 1 ? a->kw * (16 / es) : a->qb) + 15) / 16 * 16);
   {
     static const int dbgv = getenv("DTG_WGRAD_DBG") ? atoi(getenv("DTG_WGRAD_DBG")) : 0;
     p.dbg = dbgv;
@@ -555,9 +559,10 @@ extern "C" int dtg_conv_wgrad(const dtg_wgrad_args* a, const dtg_plane* pp, cons
     DTG_CHECK_CUDA(launch_k(wgrad_kernel<true>, grid, kWThreads, smem, stream, p));
   else
     DTG_CHECK_CUDA(launch_k(wgrad_kernel<false>, grid, kWThreads, smem, stream, p));
-  const int rrows = fold == 2 ? a->kw * (16 / es) : a->pa;
-  const int total = pl.ntaps * rrows * (pl.n_umma / 4);
+  const int rrows = p.rows_valid;
+  const int ncv4 = (p.cols_valid + 3) / 4;
+  const int total = pl.ntaps * rrows * ncv4;
   DTG_CHECK_CUDA(launch_k(wgrad_reduce_kernel, (total + 255) / 256, 256, 0, stream, reinterpret_cast<const float4*>(p.ws), dw, pl.splits,
-                          pl.ntaps, p.mtot, pl.n_umma, a->pa, a->qb, fold, a->kw, 16 / es, rrows, total));
+                          pl.ntaps, p.mtot, pl.n_umma, a->pa, a->qb, fold, a->kw, 16 / es, rrows, ncv4, total));
   return DTG_OK;
 }

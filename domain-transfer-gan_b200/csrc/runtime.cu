@@ -15,9 +15,43 @@ static std::atomic<unsigned long long> g_launches{0};
 
 void count_launch() { g_launches.fetch_add(1, std::memory_order_relaxed); }
 
-bool pdl_enabled() {
-  static const bool on = getenv("DTG_NO_PDL") == nullptr;
-  return on;
+// ---- runtime options: -1 = not yet initialised from the environment -----------------------------------------------
+struct Option {
+  const char* key;
+  const char* env;
+  int env_value;      // value when the environment variable is set (integer variables: parsed instead)
+  int dflt;
+  bool env_is_int;
+  std::atomic<int> v{-1};
+};
+static Option g_opts[] = {
+    {"pdl", "DTG_NO_PDL", 0, 1, false},
+    {"tma_norm", "DTG_TMA_NORM", 1, 0, false},
+    {"smem_cap_kb", "DTG_SMEM_CAP_KB", 0, 227, true},
+    {"wgrad_atomic", "DTG_WGRAD_ATOMIC", 1, 0, false},
+};
+
+static int opt_get(int i) {
+  Option& o = g_opts[i];
+  int v = o.v.load(std::memory_order_relaxed);
+  if (v < 0) {
+    const char* e = getenv(o.env);
+    v = e ? (o.env_is_int ? atoi(e) : o.env_value) : o.dflt;
+    if (v < 0) v = o.dflt;
+    o.v.store(v, std::memory_order_relaxed);
+  }
+  return v;
+}
+
+bool pdl_enabled() { return opt_get(0) != 0; }
+bool tma_norm_enabled() { return opt_get(1) != 0; }
+bool wgrad_atomic_enabled() { return opt_get(3) != 0; }
+
+int tensor_smem_budget() {
+  int kb = opt_get(2);
+  if (kb < 96) kb = 96;
+  if (kb > 227) kb = 227;
+  return kb * 1024;
 }
 
 void set_error(const char* fmt, ...) {
@@ -90,6 +124,18 @@ int encode_tiled(CUtensorMap* map, int dtype, int rank, void* base, const uint64
 }  // namespace dtg
 
 extern "C" int dtg_version(void) { return DTG_VERSION; }
+
+extern "C" int dtg_set_option(const char* key, int value) {
+  if (key != nullptr && value >= 0)
+    for (size_t i = 0; i < sizeof(dtg::g_opts) / sizeof(dtg::g_opts[0]); ++i)
+      if (strcmp(key, dtg::g_opts[i].key) == 0) {
+        const int prev = dtg::opt_get(static_cast<int>(i));
+        dtg::g_opts[i].v.store(value, std::memory_order_relaxed);
+        return prev;
+      }
+  dtg::set_error("dtg_set_option: unknown key or negative value");
+  return DTG_ERR_INVALID;
+}
 
 extern "C" unsigned long long dtg_launch_count(void) { return dtg::g_launches.load(std::memory_order_relaxed); }
 

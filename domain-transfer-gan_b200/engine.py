@@ -111,6 +111,29 @@ class ParamArena:
         raise KeyError("parameter not in arena")
 
 
+class LooseArena:
+    """Arena facade for a module that runs a fused plan on its own but does NOT own its parameters' storage (a
+    CINResnetBlock / ResnetBlock called standalone may live inside a generator whose ParamArena holds the weights):
+    nothing is re-pointed; gradients accumulate straight into each parameter's ``.grad`` (allocated on demand)."""
+
+    def __init__(self, module):
+        self.module = module
+        self.device = next(module.parameters()).device
+        self._ptrs = None
+
+    def ensure(self):
+        self.device = next(self.module.parameters()).device
+        ptrs = tuple(p.data_ptr() for p in self.module.parameters())
+        changed = ptrs != self._ptrs          # weights moved (an outer arena re-flattened them, .cuda(), ...): repack
+        self._ptrs = ptrs
+        return changed
+
+    def g(self, param):
+        if param.grad is None or not param.grad.is_contiguous() or param.grad.dtype != torch.float32:
+            param.grad = torch.zeros_like(param, dtype=torch.float32, memory_format=torch.contiguous_format)
+        return param.grad
+
+
 class Layer:
     """conv (+ norm + act (+ residual)) -> activation plane, or a head conv -> dense NCHW fp32."""
 
@@ -331,12 +354,16 @@ class NetExec:
         return c.heads
 
     # ---- backward ----------------------------------------------------------------------------
-    def backward(self, c, seeds, want_dx=False, want_dw=True, want_dz=False, sync_bn=None):
+    def backward(self, c, seeds, want_dx=False, want_dw=True, want_dz=False, sync_bn=None, top_grad=None):
         """seeds: {head layer name: True} -- the seed gradient planes c.dyraw[idx] of those heads have been
         filled by the caller (loss kernels / pack_nchw).  Parameter gradients accumulate into the arena.
-        Returns the input-gradient plane (ring = input halo) if want_dx."""
+        top_grad: gradient plane w.r.t. the LAST activation (plans without a head: the standalone residual blocks).
+        Returns the input-gradient plane (ring = input halo) if want_dx; want_dx="pair" returns both contributions of
+        the input (dgrad of the first layer, residual branch) for the caller to sum."""
         A = self.arena
         pending = {}      # act index -> (dy plane, dy2 plane)
+        if top_grad is not None:
+            pending[len(self.layers)] = (top_grad, None)
         if want_dz and c.dz is not None:
             c.dz.zero_()
         for i in range(len(self.layers) - 1, -1, -1):
@@ -407,6 +434,8 @@ class NetExec:
                 pending[ly.src] = (gin, d1) if d0 is None else (gin, d0)
         if want_dw:
             ops.off_chain_join()        # the arena is complete when backward() returns (in stream order)
+        if want_dx == "pair":
+            return pending.get(0, (None, None))
         return pending.get(0, (None, None))[0] if want_dx else None
 
     @staticmethod

@@ -88,8 +88,11 @@ def variational_ubo(model, real_A, real_B, steps, logvar_B=None, compute_l1=Fals
         iterative_opt.zero_grad()
         loss.backward()
         iterative_opt.step()
-        z_B = gauss_reparametrize(mu, logvar)                                             # :123-124
-        fake_B = model.predict_B(real_A, z_B)
+        # :123-124; the iterate after the last RMSprop step is never scored nor back-propagated (the reference computes
+        # and drops it), so it is not built as a differentiable forward
+        with torch.set_grad_enabled(i + 1 < steps):
+            z_B = gauss_reparametrize(mu, logvar)
+            fake_B = model.predict_B(real_A, z_B)
         if compute_l1:
             with torch.no_grad():
                 rec_B = fake_B.detach() if model.opt.stoch_enc else model.predict_B(real_A, mu.detach().view(size[0], nz, 1, 1))

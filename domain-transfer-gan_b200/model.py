@@ -229,15 +229,18 @@ class _FusedCycleModel(object):
         ev.record(torch.cuda.current_stream())
         return PendingReport(self, host, ev)
 
-    def _check_common(self, real_A, real_B, prior_z_B):
+    def _check_common(self, real_A, real_B, prior_z_B, free_prior=False):
+        """free_prior: prior_z_B may have its own batch size (the supervised step only feeds it to D_z_B, and the
+        reference's trainer passes the unsupervised batch's prior next to a shorter supervised batch, train.py:211-216)"""
         for t in (real_A, real_B, prior_z_B):
             if not (t.is_cuda and t.dtype == torch.float32):
                 raise ValueError("dtg_b200: train_instance expects float32 CUDA tensors (like the reference after .cuda())")
         o = self.opt
         n = real_A.shape[0]
         if (real_A.dim() != 4 or real_B.dim() != 4 or real_A.shape[1] != o.input_nc or real_B.shape[1] != o.output_nc
-                or real_B.shape[0] != n or real_A.shape[2:] != real_B.shape[2:] or prior_z_B.shape[0] != n
-                or prior_z_B.numel() != n * o.nlatent):
+                or real_B.shape[0] != n or real_A.shape[2:] != real_B.shape[2:]
+                or (prior_z_B.shape[0] != n and not free_prior)
+                or prior_z_B.numel() != prior_z_B.shape[0] * o.nlatent):
             raise ValueError("dtg_b200: expected real_A [N,%d,H,W], real_B [N,%d,H,W], prior_z_B [N,%d,1,1]"
                              % (o.input_nc, o.output_nc, o.nlatent))
         return real_A.contiguous(), real_B.contiguous(), prior_z_B.contiguous()
@@ -561,7 +564,9 @@ class AugmentedCycleGAN(_FusedCycleModel):
         def e_first():
             # d mu_z_realB = D_z dgrad + dz of F15's CIN projections -> seed of F3's mu head
             ops.grad_gather([r["g12"]], [0], nz, out=c3.dyraw[i_mu], add_nchw=c15.dz)
-            r["g3"] = E.backward(c3, {"mu": True}, want_dx=True, sync_bn=sync_bn)            # channels 0..2: d fake_A
+            # with enc_A_B the encoder saw cat(fake_A, real_B): channels 0..2 of its input gradient are d fake_A;
+            # without it the encoder saw real_B only and fake_A receives nothing from this path (model.py:409-413)
+            r["g3"] = E.backward(c3, {"mu": True}, want_dx=bool(o.enc_A_B), sync_bn=sync_bn)
             r[E] = ar(E.arena)
 
         e_db = ln.run(3, d_b, after=(e_f1,))
@@ -577,7 +582,8 @@ class AugmentedCycleGAN(_FusedCycleModel):
             r[GAB] = ar(GAB.arena)
 
         def g_last_1():
-            ops.grad_gather([r["g15"], r["g10"], r["g3"]], [0, 0, 0], o.input_nc, out=c2.dyraw[iGo], tanh_y=r["fake_A"])
+            srcs = [r["g15"], r["g10"]] + ([r["g3"]] if o.enc_A_B else [])
+            ops.grad_gather(srcs, [0] * len(srcs), o.input_nc, out=c2.dyraw[iGo], tanh_y=r["fake_A"])
             GBA.backward(c2, {"out": True})
             r[GBA] = ar(GBA.arena)
 
@@ -590,8 +596,8 @@ class AugmentedCycleGAN(_FusedCycleModel):
         return OrderedDict([('real_A', real_A), ('fake_B', r["fake_B"]), ('rec_A', r["rec_A"]),
                             ('real_B', real_B), ('fake_A', r["fake_A"]), ('rec_B', r["rec_B"])])
 
-    def _check_inputs(self, real_A, real_B, prior_z_B):
-        ins = self._check_common(real_A, real_B, prior_z_B)
+    def _check_inputs(self, real_A, real_B, prior_z_B, free_prior=False):
+        ins = self._check_common(real_A, real_B, prior_z_B, free_prior)
         if real_A.shape[2] != 64 or real_A.shape[3] != 64:
             raise ValueError("dtg_b200: AugmentedCycleGAN needs 64x64 inputs, exactly like the reference "
                              "(LatentEncoder yields [N, nlatent] only at 64x64); StochCycleGAN takes any size")
@@ -635,8 +641,9 @@ class AugmentedCycleGAN(_FusedCycleModel):
         cz1 = DZ.new_ctx(n, 1, 1, "d1")
         ops.pack_nchw(mu, cz1.acts[0], 0)
         ops.loss_lsgan(DZ.forward(cz1, sync_bn)["out"], 0.0, 0.5, sc, S_DPZ, -1, cz1.dyraw[iZ], ws)
-        cz2 = DZ.new_ctx(n, 1, 1, "d2")
-        ops.pack_nchw(prior_z_B.reshape(n, nz, 1, 1), cz2.acts[0], 0)
+        nq = prior_z_B.shape[0]            # its own batch size: discriminate() runs the two forwards separately (:327-334)
+        cz2 = DZ.new_ctx(nq, 1, 1, "d2")
+        ops.pack_nchw(prior_z_B.reshape(nq, nz, 1, 1), cz2.acts[0], 0)
         ops.loss_lsgan(DZ.forward(cz2, sync_bn)["out"], 1.0, 0.5, sc, S_DQZ, -1, cz2.dyraw[iZ], ws)
         self.optimizer_D_B.zero_grad()
         DZ.backward(cz1, {"out": True}, sync_bn=sync_bn)
@@ -676,7 +683,7 @@ class AugmentedCycleGAN(_FusedCycleModel):
 
     def supervised_train_instance(self, real_A, real_B, prior_z_B, use_graph=False):
         """model.py:541-604; returns the reference's loss dict (:593-602)."""
-        ins = self._check_inputs(real_A, real_B, prior_z_B)
+        ins = self._check_inputs(real_A, real_B, prior_z_B, free_prior=True)
         self._run("sup", self._sup_device, ins, use_graph)
         s = self._read_scalars()
         gn = lambda k: s[S_SQ[k]] ** 0.5

@@ -4,8 +4,11 @@
 Inside the networks these modules are PARAMETER HOLDERS: the network-level engine (engine.py) reads
 their parameters and runs fused sm_100a kernels; it never calls their ``forward``.  Called on their own,
 ``InstanceNorm`` / ``CondInstanceNorm`` run the same fused norm kernels through an autograd Function
-(fp32 NCHW in / out, like the reference), so they remain drop-in usable as standalone layers.
+(fp32 NCHW in / out, like the reference), and ``CINResnetBlock`` / ``ResnetBlock`` run a two-layer fused plan
+(reflect-padded 3x3 tcgen05 convs + fused norms + residual), so they remain drop-in usable as standalone layers.
 """
+import weakref
+
 import torch
 import torch.nn as nn
 from torch.nn.parameter import Parameter
@@ -149,6 +152,70 @@ class CondInstanceNorm(TwoInputModule):
         return _NormFn.apply(input, gam, bet, L.NORM_COND_INSTANCE, self.eps)
 
 
+def _release_ctx(c):
+    c.busy = False
+
+
+class _BlockFn(torch.autograd.Function):
+    """Standalone residual block (modules.py:185-188, 232-235): out = relu(x + conv_block(x[, z])) as a two-layer
+    engine plan on a private context; differentiable in x, z and the block's parameters (gradients accumulate into
+    ``.grad``)."""
+
+    @staticmethod
+    def forward(ctx, block, x, z):
+        ex = block._exec()
+        n, cch, h, w = x.shape
+        ctx.set_materialize_grads(False)
+        ex.repack()
+        slot = 0
+        while getattr(ex.new_ctx(n, h, w, tag=("autograd", slot)), "busy", False):
+            slot += 1
+        c = ex.new_ctx(n, h, w, tag=("autograd", slot))
+        c.busy = torch.is_grad_enabled()
+        if c.busy:
+            weakref.finalize(ctx, _release_ctx, c)
+        ops.pack_nchw(x.detach().contiguous().float(), c.acts[0], 0)        # mirrors into the halo: ReflectionPad2d(1)
+        if z is not None:
+            c.z.copy_(z.detach().reshape(n, -1))
+        ex.forward(c)
+        ctx.block, ctx.c, ctx.cch = block, c, cch
+        ctx.zshape = z.shape if z is not None else None
+        return ops.unpack_nchw(c.acts[len(ex.layers)], cch)
+
+    @staticmethod
+    def backward(ctx, dy):
+        if dy is None:
+            return None, None, None
+        block, c = ctx.block, ctx.c
+        ex = block._exec()
+        c.busy = False
+        top = c.acts[len(ex.layers)]
+        if not hasattr(c, "top_grad"):
+            c.top_grad = ops.PlaneT(top.n, top.h, top.w, top.c, 0, top.dtype, top.t.device)
+        ops.pack_nchw(dy.contiguous().float(), c.top_grad, 0, reflect=False)
+        gin, dres = ex.backward(c, {}, want_dx="pair", want_dw=True, want_dz=ctx.zshape is not None, top_grad=c.top_grad)
+        dx = torch.empty(c.n, ctx.cch, gin.h, gin.w, device=gin.t.device)
+        ops.grad_gather([gin, dres], [0, 0], ctx.cch, out=None, out_nchw=dx)     # dgrad of conv 1 (ring folded) + identity branch
+        dz = c.dz.reshape(ctx.zshape).clone() if ctx.zshape is not None else None
+        return None, dx, dz
+
+
+class _FusedBlock(object):
+    """lazy two-layer plan of a standalone residual block (engine.LooseArena: the block does not own its weights)"""
+
+    def _exec(self):
+        from . import engine
+        dev = next(self.parameters()).device
+        if dev.type != "cuda":
+            raise RuntimeError("dtg_b200 modules run only on CUDA (sm_100a); there is no CPU fallback")
+        ex = getattr(self, "_ex", None)
+        if ex is None or ex.arena.device != dev:
+            ex = self._build_exec(engine)
+            object.__setattr__(self, "_ex", ex)
+        ex.prepare()
+        return ex
+
+
 def _pad_layers(padding_type):
     if padding_type == 'reflect':
         return [nn.ReflectionPad2d(1)], 0
@@ -159,11 +226,16 @@ def _pad_layers(padding_type):
     raise NotImplementedError('padding [%s] is not implemented' % padding_type)
 
 
-class CINResnetBlock(TwoInputModule):
-    """modules.py:139-188 (parameter holder; same child indices and the `str(idx)` aliases of :145-146)."""
+class CINResnetBlock(TwoInputModule, _FusedBlock):
+    """modules.py:139-188 (same child indices and the `str(idx)` aliases of :145-146).  Inside CINResnetGenerator the
+    block is a parameter holder of the generator's plan; called on its own it runs the two-layer plan below."""
 
     def __init__(self, x_dim, z_dim, padding_type, norm_layer, use_dropout, use_bias):
         super().__init__()
+        if use_dropout or padding_type != 'reflect':
+            raise NotImplementedError("dtg_b200: residual blocks implement reflect padding without dropout "
+                                      "(the reference's configuration, networks.py:173-175)")
+        self.x_dim, self.z_dim = x_dim, z_dim
         self.padding_type = padding_type
         self.conv_block = self.build_conv_block(x_dim, z_dim, padding_type, norm_layer, use_dropout, use_bias)
         self.relu = nn.ReLU(True)
@@ -184,16 +256,28 @@ class CINResnetBlock(TwoInputModule):
                        InstanceNorm2d(x_dim, affine=True)]
         return TwoInputSequential(*conv_block)
 
+    def _build_exec(self, engine):
+        cb, d = self.conv_block, self.x_dim
+        conv1, n1 = cb[1].module1, cb[1].module2
+        kind = L.NORM_COND_INSTANCE if isinstance(n1, CondInstanceNorm) else L.NORM_INSTANCE
+        ls = [engine.Layer("a", 0, conv1, d, d, 3, 1, 1, norm=kind, act=L.ACT_RELU, norm_mod=n1, out_halo=1),
+              engine.Layer("b", 1, cb[4], d, d, 3, 1, 1, norm=L.NORM_INSTANCE, act=L.ACT_RELU, norm_mod=cb[5], residual=0)]
+        return engine.NetExec(self, ls, d, 1, engine.LooseArena(self), nz=self.z_dim)
+
     def forward(self, x, noise):
-        raise RuntimeError("dtg_b200: CINResnetBlock runs inside CINResnetGenerator's fused plan; "
-                           "standalone block execution is not part of the hot path")
+        """modules.py:185-188: relu(x + conv_block(x, noise))"""
+        return _BlockFn.apply(self, x, noise)
 
 
-class ResnetBlock(nn.Module):
-    """modules.py:193-235 (parameter holder)."""
+class ResnetBlock(nn.Module, _FusedBlock):
+    """modules.py:193-235.  Inside ResnetGenerator a parameter holder; standalone it runs the two-layer plan below."""
 
     def __init__(self, dim, padding_type, norm_layer, use_dropout, use_bias):
         super().__init__()
+        if use_dropout or padding_type != 'reflect':
+            raise NotImplementedError("dtg_b200: residual blocks implement reflect padding without dropout "
+                                      "(the reference's configuration, networks.py:225-227)")
+        self.dim = dim
         self.padding_type = padding_type
         self.conv_block = self.build_conv_block(dim, padding_type, norm_layer, use_dropout, use_bias)
         self.relu = nn.ReLU(True)
@@ -210,6 +294,14 @@ class ResnetBlock(nn.Module):
         conv_block += [nn.Conv2d(dim, dim, kernel_size=3, padding=p, bias=use_bias), norm_layer(dim)]
         return nn.Sequential(*conv_block)
 
+    def _build_exec(self, engine):
+        cb, d = self.conv_block, self.dim
+        if not isinstance(cb[5], InstanceNorm):
+            raise NotImplementedError("dtg_b200: standalone ResnetBlock implements the reference's InstanceNorm2d")
+        ls = [engine.Layer("a", 0, cb[1], d, d, 3, 1, 1, norm=L.NORM_NONE, act=L.ACT_RELU, out_halo=1),
+              engine.Layer("b", 1, cb[4], d, d, 3, 1, 1, norm=L.NORM_INSTANCE, act=L.ACT_RELU, norm_mod=cb[5], residual=0)]
+        return engine.NetExec(self, ls, d, 1, engine.LooseArena(self))
+
     def forward(self, x):
-        raise RuntimeError("dtg_b200: ResnetBlock runs inside ResnetGenerator's fused plan; "
-                           "standalone block execution is not part of the hot path")
+        """modules.py:232-235: relu(x + conv_block(x))"""
+        return _BlockFn.apply(self, x, None)

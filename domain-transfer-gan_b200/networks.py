@@ -11,6 +11,7 @@ training step (model.py) drives the same plans directly.
 not ``nn.parallel.data_parallel``.
 """
 import functools
+import weakref
 
 import torch
 import torch.nn as nn
@@ -53,6 +54,10 @@ def _norm_kind(m):
     raise NotImplementedError("dtg_b200: unsupported norm layer %s" % type(m).__name__)
 
 
+def _release_ctx(c):
+    c.busy = False
+
+
 class _NetFn(torch.autograd.Function):
     """Differentiable network call: forward / backward run the fused plan on a private context."""
 
@@ -66,7 +71,11 @@ class _NetFn(torch.autograd.Function):
         while getattr(ex.new_ctx(n, h, w, tag=("autograd", slot)), "busy", False):
             slot += 1
         c = ex.new_ctx(n, h, w, tag=("autograd", slot))
+        # the activation context stays reserved until backward() has consumed it -- or until the autograd node dies
+        # without ever being back-propagated (a grad-enabled forward whose output is dropped), else it would leak
         c.busy = torch.is_grad_enabled()
+        if c.busy:
+            weakref.finalize(ctx, _release_ctx, c)
         srcs = (x,) + tuple(extra)
         off = 0
         for s in srcs:

@@ -293,34 +293,17 @@ def add_packed(tab, w, dtype, kind, s2d_cp=0):
     raise ValueError(kind)
 
 
-class KernelProfile:
-    """Optional per-call CUDA-event timing of the tensor-core kernels (bench.py roofline accounting).
-    Records (kind, algorithmic FLOPs, start event, end event) per call on the launching stream."""
+class OpLog:
+    """Optional log of every ops.* call in issue order: (name, kernels launched, algorithmic FLOPs, algorithmic bytes).
+    bench.py captures one serial step with it and lines the records up with the CUPTI kernel records of the replayed
+    graph (the k-th dtg:: kernel on the stream belongs to the op whose launch range covers k), which gives exact
+    per-op / per-kernel device times without host launch gaps."""
 
     def __init__(self):
         self.records = []
 
-    def begin(self):
-        e = torch.cuda.Event(enable_timing=True)
-        e.record(torch.cuda.current_stream())
-        return e
 
-    def end(self, kind, flops, e0):
-        e1 = torch.cuda.Event(enable_timing=True)
-        e1.record(torch.cuda.current_stream())
-        self.records.append((kind, flops, e0, e1))
-
-    def summary(self):
-        out = {}
-        for kind, flops, e0, e1 in self.records:
-            d = out.setdefault(kind, {"flops": 0.0, "ms": 0.0, "launches": 0})
-            d["flops"] += flops
-            d["ms"] += e0.elapsed_time(e1)
-            d["launches"] += 1
-        return out
-
-
-PROFILE = None    # set to a KernelProfile to time conv / wgrad calls
+PROFILE = None    # set to an OpLog to record the calls
 
 
 def conv(x, wp, bias, out, *, mode=L.CONV_FWD, kh, kw, stride=1, pad=0, ring=0, act=L.ACT_NONE, cout,
@@ -330,14 +313,9 @@ def conv(x, wp, bias, out, *, mode=L.CONV_FWD, kh, kw, stride=1, pad=0, ring=0, 
     a = L.ConvArgs(mode, kh, kw, stride, pad, ring, act, cout, 1 if out_nchw is not None else 0,
                    1 if out_reflect else 0, out_h, out_w, 1 if fold_w else 0)
     assert wp.shape[0] == (kh if fold_w else kh * kw)
-    e0 = PROFILE.begin() if PROFILE is not None else None
     rc = L.lib().dtg_conv(C.byref(a), x.s, _ptr(wp), wp.shape[1], wp.shape[2], _ptr(bias),
                           out.s if out is not None else NULL_PLANE, _ptr(out_nchw), _stream())
     L.check(rc, "conv")
-    if e0 is not None:
-        # algorithmic MACs = (pixels of the low-resolution side) * cin * cout * taps, for fwd and dgrad alike
-        pix = x.n * (out_h * out_w if mode == L.CONV_FWD else x.h * x.w)
-        PROFILE.end("igemm_kernel", 2.0 * pix * (cin or wp.shape[2]) * cout * kh * kw, e0)
 
 
 _ws_cache = {}
@@ -363,10 +341,7 @@ def conv_wgrad(p, q, dw, *, kh, kw, stride=1, pad=0, pa, qb, ws=None, fold=0):
     if ws is None:
         ws = workspace(need, dw.device, "wgrad")
     assert dw.dtype == torch.float32 and dw.is_contiguous() and dw.numel() == pa * qb * kh * kw
-    e0 = PROFILE.begin() if PROFILE is not None else None
     L.check(L.lib().dtg_conv_wgrad(C.byref(a), p.s, q.s, _ptr(dw), _ptr(ws), ws.numel(), _stream()), "conv_wgrad")
-    if e0 is not None:
-        PROFILE.end("wgrad_kernel", 2.0 * p.n * p.h * p.w * pa * qb * kh * kw, e0)
 
 
 def head1_fwd(x, w, bias, out_nchw, pad):
@@ -483,3 +458,52 @@ def adam_clip(p, g, m, v, hyper, sumsq, step_dev, grad_scale=1.0):
 
 def step_increment(step_dev):
     L.check(L.lib().dtg_step_increment(_ptr(step_dev), _stream()), "step_increment")
+
+
+# ---- op log (see OpLog): algorithmic work of the heavy ops, launch ranges of all of them ------------------------------
+def _conv_work(x, wp, bias, out, *, mode=L.CONV_FWD, kh, kw, cout, out_h, out_w, cin=None, **_):
+    # algorithmic MACs = (pixels of the low-resolution side) * cin * cout * taps, for fwd and dgrad alike
+    pix = x.n * (out_h * out_w if mode == L.CONV_FWD else x.h * x.w)
+    return 2.0 * pix * (cin or wp.shape[2]) * cout * kh * kw, 0.0
+
+
+def _wgrad_work(p, q, dw, *, kh, kw, pa, qb, **_):
+    return 2.0 * p.n * p.h * p.w * pa * qb * kh * kw, 0.0
+
+
+def _plane_bytes(p):
+    return float(p.n * p.h * p.w * p.c * p.t.element_size())
+
+
+def _norm_fwd_work(x, out, st, *, residual=None, **_):
+    # read x (+ residual), write y
+    return 0.0, _plane_bytes(x) * (2 + (1 if residual is not None else 0))
+
+
+def _norm_bwd_work(dy, dx, st, *, mode, act, y=None, x=None, dy2=None, d_res=None, **_):
+    # read dy (+ dy2, + y for the activation mask, + x for the statistics), write dx (+ residual-branch gradient)
+    passes = 2 + (1 if dy2 is not None else 0) + (1 if act != L.ACT_NONE else 0) + (1 if mode != L.NORM_NONE else 0) + \
+        (1 if d_res is not None else 0)
+    return 0.0, _plane_bytes(dx) * passes
+
+
+def _logged(name, fn, work=None):
+    def w(*a, **k):
+        if PROFILE is None:
+            return fn(*a, **k)
+        lc0 = L.lib().dtg_launch_count()
+        r = fn(*a, **k)
+        fl, by = work(*a, **k) if work is not None else (0.0, 0.0)
+        PROFILE.records.append((name, int(L.lib().dtg_launch_count() - lc0), fl, by))
+        return r
+    w.__name__, w.__doc__ = fn.__name__, fn.__doc__
+    return w
+
+
+for _n, _w in (("conv", _conv_work), ("conv_wgrad", _wgrad_work), ("norm_fwd", _norm_fwd_work), ("norm_bwd", _norm_bwd_work),
+               ("pack_nchw", None), ("unpack_nchw", None), ("s2d_unfold_add", None), ("head1_fwd", None), ("head1_dgrad", None),
+               ("head1_wgrad", None), ("cin_affine_fwd", None), ("cin_affine_bwd", None), ("grad_gather", None),
+               ("channel_sum", None), ("loss_lsgan", None), ("loss_l1", None), ("grad_sumsq", None), ("adam_clip", None),
+               ("step_increment", None)):
+    globals()[_n] = _logged(_n, globals()[_n], _w)
+PackTable.run = _logged("pack_weights", PackTable.run)

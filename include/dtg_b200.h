@@ -28,7 +28,7 @@
 extern "C" {
 #endif
 
-#define DTG_VERSION 110 /* 110: dtg_pack_item.s2d_k, dtg_pack_nchw_s2d, dtg_s2d_unfold_add, dtg_head1_* */
+#define DTG_VERSION 120 /* 120: dtg_set_option; TMA-staged instance-norm kernels behind dtg_norm_fwd / dtg_norm_bwd */
 
 enum { DTG_OK = 0, DTG_ERR_INVALID = -1, DTG_ERR_CUDA = -2, DTG_ERR_UNSUPPORTED = -3 };
 enum { DTG_BF16 = 0, DTG_F32 = 1 };
@@ -51,6 +51,20 @@ int dtg_version(void);
 unsigned long long dtg_launch_count(void);
 /* copies the calling thread's last error message (NUL terminated) into buf; returns its length */
 int dtg_last_error(char* buf, size_t cap);
+/* Runtime options (process-wide; each also has an environment default read at first use).  Returns the previous value,
+ * or DTG_ERR_INVALID for an unknown key.
+ *   "pdl"         1 (default; env DTG_NO_PDL=1 -> 0): kernels are launched with the programmatic-dependent-launch
+ *                 attribute and start with griddepcontrol.launch_dependents / .wait, so a prologue overlaps the previous
+ *                 kernel's tail.  0 = plain stream-ordered launches: per-kernel device durations (CUPTI, ncu) then do not
+ *                 include time spent waiting for a predecessor (bench.py's per-kernel roofline pass).
+ *   "tma_norm"    0 (default; env DTG_TMA_NORM=1 -> 1): dtg_norm_fwd / dtg_norm_bwd use the TMA-staged cluster kernels
+ *                 (norm_tma.cu) instead of the register-resident ones (norm_fused.cu) where the geometry allows.
+ *   "smem_cap_kb" 227 (env DTG_SMEM_CAP_KB): shared-memory budget of one tensor-core CTA; what it leaves free decides
+ *                 whether bandwidth-bound kernels of other streams can be co-resident on the same SM.
+ *   "wgrad_atomic" 0 (env DTG_WGRAD_ATOMIC=1 -> 1): the weight-gradient split-K partials are accumulated with
+ *                 red.global.add.f32 (order not fixed: results differ in the last bits from run to run) instead of the
+ *                 deterministic workspace + fixed-order reduction. */
+int dtg_set_option(const char* key, int value);
 
 /* ---------------------------------------------------------------------------------------------
  * Weight packing.  Replaces cuDNN's internal filter transforms for nn.Conv2d / nn.ConvTranspose2d /

@@ -1,16 +1,28 @@
-"""Import the UNMODIFIED reference live from /root/reference (build container only).
+"""Import the UNMODIFIED reference live: from /root/reference in the build container, from the byte-for-byte staged copy
+under baseline/_ref/ (oracle/stage_ref.py; git-ignored) on the GPU box.
 
 Test infrastructure.  Nothing is copied into the repo: ``modules.py`` / ``networks.py`` are
 imported by path; ``model.py`` is read as text and exec'd with the single reporting shim
 ``.data[0] -> .item()`` because 0-dim indexing raises on torch>=0.5.
-The GPU box has no /root/reference: ``available()`` is False there and callers must skip.
+``available()`` is False when neither exists and callers must skip.
 """
 import os
 import sys
 import types
 import warnings
 
-REF_DIR = os.environ.get("DTG_REFERENCE_DIR", "/root/reference/augmented_cyclegan")
+_ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _resolve():
+    for d in (os.environ.get("DTG_REFERENCE_DIR"), "/root/reference/augmented_cyclegan",
+              os.path.join(_ROOT, "baseline", "_ref", "augmented_cyclegan")):
+        if d and os.path.isfile(os.path.join(d, "model.py")):
+            return d
+    return "/root/reference/augmented_cyclegan"
+
+
+REF_DIR = _resolve()
 
 
 def available():

@@ -79,6 +79,24 @@ def resnet_generator(p, x, capture=None):
     return torch.tanh(cap("model.19", h))
 
 
+def cin_resnet_block(p, x, z):
+    """modules.py:139-188 standalone: relu(x + IN(conv(rpad(relu(CIN(conv(rpad(x)), z)))))); keys of the block's own
+    state_dict (conv_block.1.module1.*, conv_block.1.module2.*, conv_block.4.*, conv_block.5.*)"""
+    b = "conv_block"
+    t = F.conv2d(_rpad(x, 1), p[b + ".1.module1.weight"], p[b + ".1.module1.bias"])
+    t = F.relu(_cin(p, b + ".1.module2", t, z))
+    t = F.conv2d(_rpad(t, 1), p[b + ".4.weight"], p[b + ".4.bias"])
+    return F.relu(x + _in(p, b + ".5", t))
+
+
+def resnet_block(p, x):
+    """modules.py:193-235 standalone: relu(x + IN(conv(rpad(relu(conv(rpad(x)))))))"""
+    b = "conv_block"
+    t = F.relu(F.conv2d(_rpad(x, 1), p[b + ".1.weight"], p[b + ".1.bias"]))
+    t = F.conv2d(_rpad(t, 1), p[b + ".4.weight"], p[b + ".4.bias"])
+    return F.relu(x + _in(p, b + ".5", t))
+
+
 def discriminator(p, x, capture=None):
     """networks.py:308-349 PatchGAN, 4x4 kernels, strides 2,2,1,1,1, pad 1."""
     h = F.leaky_relu(F.conv2d(x, p["model.0.weight"], p["model.0.bias"], stride=2, padding=1), 0.2)

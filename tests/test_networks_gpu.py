@@ -6,7 +6,7 @@ Tolerances.  Single layers meet north_star's 1e-3 bound (test_conv_gpu / test_wg
 Through a whole network the reference's OWN reduced-precision paths are far from 1e-3 on gradients
 (measured on B200, CIN generator at init, vs fp64: cuDNN TF32 dx 4.0e-2 / dW 5.8e-2; bf16 autocast
 dx 0.19 / dW 0.32 -- InstanceNorm.scale ~ N(0,.02) makes activations tiny), so the bound is
-stated the way SURVEY 9.3 recommends: our error against the fp32 oracle must be <= 2.5x the worst error of the
+stated the way SURVEY 9.3 recommends: our error against the fp32 oracle must be <= 1.5x the worst error of the
 reference's own path at the same precision (cuDNN TF32 for tf32 mode, torch.autocast(bf16) for bf16
 mode), computed in the same test on the same inputs; forward outputs additionally <= 2e-3 (tf32) /
 3e-2 (bf16) rel-L2."""
@@ -17,6 +17,7 @@ import torch
 import dtg  # noqa: F401
 from dtg_b200 import engine, networks
 from oracle import nets as onets
+from tolerances import GRAD_FACTOR, record
 
 pytestmark = pytest.mark.gpu
 DEV = "cuda"
@@ -92,7 +93,9 @@ def _compare(name, prec, net, ours_outs, ours_ingrads, ref, low):
         assert _rel(o, r) < OUT_TOL[prec], (name, "out", _rel(o, r))
     real = [k for k in r_pg if not onets.is_noise_grad(name, k)]
     low_worst = max([_rel(l_pg[k], r_pg[k]) for k in real] + [_rel(a, b) for a, b in zip(l_in, r_in)])
-    bound = 2.5 * low_worst + 2e-3
+    bound = GRAD_FACTOR * low_worst + 2e-3
+    ours_worst = max([_rel(dict(net.named_parameters())[k].grad, r_pg[k]) for k in real] + [_rel(a, b) for a, b in zip(ours_ingrads, r_in)])
+    record("network", name=name, prec=prec, grad_err=ours_worst, ref_lowprec_grad_err=low_worst, grad_ratio=ours_worst / max(low_worst, 1e-12))
     for a, b in zip(ours_ingrads, r_in):
         assert _rel(a, b) < bound, (name, "dx", _rel(a, b), bound)
     pg = dict(net.named_parameters())
@@ -119,6 +122,102 @@ def test_cin_generator(prec):
     ref = _run_oracle(onets.cin_resnet_generator, sd, [x, z], wgt)
     low = _run_oracle(onets.cin_resnet_generator, sd, [x, z], wgt, prec)
     _compare("netG_A_B", prec, net, [y], [x.grad, z.grad], ref, low)
+
+
+# our plan's activation index -> the oracle's capture name (post norm + activation outputs, networks.py:158-189)
+_GEN_ACTS = {1: "model.3", 2: "model.6", 3: "model.9", 5: "model.10", 7: "model.11", 9: "model.12", 10: "model.15",
+             11: "model.18"}
+
+
+@pytest.mark.parametrize("which", ["netG_A_B", "netG_B_A"])
+def test_generator_per_layer_activations_tf32(which):
+    """north_star: per-layer activations within 1e-3 relative in the fp32/TF32 mode.  The reference's top-level layers
+    bypass forward hooks (modules.py:35-36,51-55), so the oracle captures them by walking the layer list; ours
+    are the planes of the fused plan.  Each layer must be within max(1e-3, 1.5 x cuDNN-TF32's own error at that layer)
+    of the fp32 reference (rel-L2); the measured values go to gpurun_out/test_ratios.jsonl."""
+    engine.set_precision("tf32")
+    sd = STATE[which]
+    cin = which == "netG_A_B"
+    net = (networks.CINResnetGenerator(16, 3, 3, 32) if cin else networks.ResnetGenerator(3, 3, 32)).to(DEV)
+    _load(net, sd)
+    g = torch.Generator().manual_seed(5)
+    x = (torch.rand(4, 3, 64, 64, generator=g) * 2 - 1).to(DEV)
+    z = torch.randn(4, 16, 1, 1, generator=g).to(DEV)
+    with torch.no_grad():
+        y = net(x, z) if cin else net(x)
+    c = net._ex.new_ctx(4, 64, 64, tag=("autograd", 0))
+    op = _oracle_params(sd)
+    fn = onets.cin_resnet_generator if cin else onets.resnet_generator
+    ref, low = {}, {}
+    with torch.no_grad():
+        yr = fn(op, x, z, capture=ref) if cin else fn(op, x, capture=ref)
+        with _lowprec("tf32"):
+            yl = fn(op, x, z, capture=low) if cin else fn(op, x, capture=low)
+    rows = []
+    for idx, name in sorted(_GEN_ACTS.items()):
+        r = ref[name]
+        ours = c.acts[idx].to_nchw(r.shape[1])
+        e, el = _rel(ours, r), _rel(low[name], r)
+        rows.append((name, e, el))
+        assert e <= max(1e-3, GRAD_FACTOR * el), (which, name, e, el)
+    e, el = _rel(y, yr), _rel(yl, yr)
+    rows.append(("out", e, el))
+    assert e <= max(1e-3, GRAD_FACTOR * el), (which, "out", e, el)
+    record("per_layer_tf32", net=which, layers={n: [round(a, 6), round(b, 6)] for n, a, b in rows})
+
+
+@pytest.mark.parametrize("prec", ["tf32", "bf16"])
+@pytest.mark.parametrize("kind", ["cin", "plain"])
+def test_standalone_residual_blocks(kind, prec):
+    """CINResnetBlock.forward(x, noise) / ResnetBlock.forward(x) on their own (modules.py:185-188, 232-235): output,
+    dx, dz and the parameter gradients against the oracle, with the block weights of the generator state"""
+    engine.set_precision(prec)
+    from dtg_b200 import modules as M
+    gsd = STATE["netG_A_B" if kind == "cin" else "netG_B_A"]
+    sd = {k[len("model.10."):]: v for k, v in gsd.items() if k.startswith("model.10.conv_block.")}
+    blk = (M.CINResnetBlock(128, 16, "reflect", M.CondInstanceNorm, False, True) if kind == "cin"
+           else M.ResnetBlock(128, "reflect", M.InstanceNorm2d, False, True)).to(DEV)
+    blk.load_state_dict({k: v.clone() for k, v in sd.items()}, strict=False)
+    g = torch.Generator().manual_seed(11)
+    q = (lambda t: t.to(torch.bfloat16).float()) if prec == "bf16" else (lambda t: t)
+    x = q(torch.randn(3, 128, 32, 32, generator=g).relu()).to(DEV).requires_grad_(True)
+    z = torch.randn(3, 16, 1, 1, generator=g).to(DEV).requires_grad_(True)
+    wgt = torch.randn(3, 128, 32, 32, generator=g).to(DEV)
+    ins = [x, z] if kind == "cin" else [x]
+    y = blk(*ins)
+    (y * wgt).sum().backward()
+    fn = onets.cin_resnet_block if kind == "cin" else onets.resnet_block
+    r_outs, r_in, r_pg, _ = _run_oracle(fn, sd, ins, wgt)
+    l_outs, l_in, l_pg, _ = _run_oracle(fn, sd, ins, wgt, prec)
+    assert _rel(y, r_outs[0]) < OUT_TOL[prec], _rel(y, r_outs[0])
+    noise = ("conv_block.1.module1.bias", "conv_block.4.bias")       # biases in front of a mean-removing norm
+    real = [k for k in r_pg if k not in noise]
+    low_worst = max([_rel(l_pg[k], r_pg[k]) for k in real] + [_rel(a, b) for a, b in zip(l_in, r_in)])
+    bound = GRAD_FACTOR * low_worst + 2e-3
+    for a, b in zip([t.grad for t in ins], r_in):
+        assert _rel(a, b) < bound, (kind, "input grad", _rel(a, b), bound)
+    pg = dict(blk.named_parameters())
+    for k in real:
+        assert _rel(pg[k].grad, r_pg[k]) < bound, (kind, k, _rel(pg[k].grad, r_pg[k]), bound)
+    # a second call must not leak activation contexts (the slot of the first call was released by its backward)
+    y2 = blk(*[t.detach() for t in ins])
+    assert sum(1 for k in blk._ex._ctx_cache if isinstance(k, tuple) and k[-1] == ("autograd", 1)) == 0
+    assert _rel(y2, y) < 1e-6
+
+
+def test_dropped_grad_forward_releases_its_context():
+    """a grad-enabled forward that is never back-propagated must not pin an activation context for ever"""
+    engine.set_precision("bf16")
+    net = networks.ResnetGenerator(3, 3, 32).to(DEV)
+    _load(net, STATE["netG_B_A"])
+    x = torch.rand(2, 3, 64, 64, device=DEV).requires_grad_(True)
+    for _ in range(4):
+        y = net(x)
+        del y
+    import gc
+    gc.collect()
+    slots = [k[-1][1] for k in net._ex._ctx_cache if isinstance(k, tuple) and isinstance(k[-1], tuple) and k[-1][0] == "autograd"]
+    assert max(slots) <= 1, slots
 
 
 @pytest.mark.parametrize("prec", ["tf32", "bf16"])

@@ -23,6 +23,15 @@ def _act(t, act):
     return {L.ACT_NONE: lambda v: v, L.ACT_RELU: F.relu, L.ACT_LRELU: lambda v: F.leaky_relu(v, 0.2)}[act](t)
 
 
+@pytest.fixture(params=[0, 1], ids=["regnorm", "tmanorm"])
+def tma(request):
+    """both instance-norm kernel families behind dtg_norm_fwd / dtg_norm_bwd: register-resident cluster kernels
+    (norm_fused.cu, the default) and the TMA-staged ones (norm_tma.cu, dtg_set_option("tma_norm", 1))"""
+    prev = L.set_option("tma_norm", request.param)
+    yield request.param
+    L.set_option("tma_norm", prev)
+
+
 @pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
 @pytest.mark.parametrize("mode,act,residual,halo,shape", [
     (L.NORM_INSTANCE, L.ACT_RELU, False, 0, (3, 64, 64, 64)),
@@ -33,8 +42,11 @@ def _act(t, act):
     (L.NORM_BATCH, L.ACT_RELU, False, 0, (5, 64, 16, 16)),
     (L.NORM_BATCH, L.ACT_LRELU, False, 0, (37, 64, 1, 1)),
     (L.NORM_NONE, L.ACT_RELU, False, 1, (2, 128, 32, 32)),
+    (L.NORM_INSTANCE, L.ACT_RELU, True, 1, (80, 128, 32, 32)),        # the benched residual-stack shape
+    (L.NORM_COND_INSTANCE, L.ACT_RELU, False, 0, (80, 64, 64, 64)),
+    (L.NORM_INSTANCE, L.ACT_LRELU, False, 0, (160, 128, 16, 16)),
 ])
-def test_norm_fwd_bwd(mode, act, residual, halo, shape, dtype):
+def test_norm_fwd_bwd(mode, act, residual, halo, shape, dtype, tma):
     n, c, h, w = shape
     g = torch.Generator().manual_seed(n * 1000 + c + h)
     # inputs are made exactly representable in the plane's storage format (bf16 / tf32) so that both sides

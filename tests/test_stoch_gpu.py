@@ -3,7 +3,7 @@
 (model.py:293-313, 750-778) against the oracle restatements (pinned to the live reference by tests/test_oracle.py)
 and the committed golden vectors.
 
-Tolerances follow test_step_gpu.py: reduced-precision errors are bounded by 2.5x the error of the reference's own
+Tolerances follow test_step_gpu.py: reduced-precision errors are bounded by 1.5x the error of the reference's own
 path at that precision (cuDNN TF32 / torch.autocast bf16) measured in the same test."""
 import argparse
 import os
@@ -15,6 +15,7 @@ import dtg  # noqa: F401
 from dtg_b200 import engine, model as dmodel
 from oracle import nets as onets, step as ostep
 from test_step_gpu import _prec_ctx, _rel
+from tolerances import GRAD_FACTOR, record
 
 pytestmark = pytest.mark.gpu
 DEV = "cuda"
@@ -76,7 +77,7 @@ def test_stoch_train_instance_matches_oracle(prec, size, out_nc, ignore_noise):
     ltol = 2e-3 if prec == "tf32" else 3e-2
     for k, v in rl.items():
         assert abs(losses[k] - v) <= ltol * max(1.0, abs(v)), (k, losses[k], v)
-    vis_bound = 2.5 * max(_rel(lv[k], rv[k]) for k in rv) + 1e-3
+    vis_bound = GRAD_FACTOR * max(_rel(lv[k], rv[k]) for k in rv) + 1e-3
     for k in rv:
         assert _rel(visuals[k], rv[k]) < vis_bound, (k, _rel(visuals[k], rv[k]), vis_bound)
     worst_low = 0.0
@@ -84,7 +85,11 @@ def test_stoch_train_instance_matches_oracle(prec, size, out_nc, ignore_noise):
         for k in rgrad[name]:
             if not onets.is_noise_grad(name, k):
                 worst_low = max(worst_low, _rel(lgrad[name][k], rgrad[name][k]))
-    bound = 2.5 * worst_low + 2e-3
+    bound = GRAD_FACTOR * worst_low + 2e-3
+    worst = max(_rel(got[name][k], rgk) for name in rgrad for k, rgk in rgrad[name].items()
+                if not onets.is_noise_grad(name, k) and float(rgk.norm()) > 0.0)
+    record("stoch_train_instance", prec=prec, size=size, grad_err=worst, ref_lowprec_grad_err=worst_low,
+           grad_ratio=worst / max(worst_low, 1e-12))
     for name in rgrad:
         for k, rgk in rgrad[name].items():
             if onets.is_noise_grad(name, k):

@@ -59,3 +59,13 @@ for _ in range(3):
     ts.append(e0.elapsed_time(e1) * 1e3 / reps)
 fl = 2.0 * N * oh * oh * cin * cout * k * k
 print(case, "us per call (graph of %d):" % reps, ["%.1f" % t for t in ts], "TFLOP/s best %.1f" % (fl / min(ts) / 1e6))
+if os.environ.get("PROF_KERNELS"):
+    # per-kernel device durations (CUPTI activity records through torch.profiler; no replay, warm caches)
+    from torch.profiler import profile, ProfilerActivity
+    with profile(activities=[ProfilerActivity.CUDA]) as prof:
+        for _ in range(5):
+            f()
+        torch.cuda.synchronize()
+    for e in prof.key_averages():
+        if e.device_time_total > 0:
+            print("  %-70s n=%d avg %.1f us" % (e.key[:70], e.count, e.device_time_total / e.count))
