@@ -40,6 +40,14 @@ class PackItem(C.Structure):
                 ("fold_fc", C.c_int32), ("s2d_k", C.c_int32)]
 
 
+class LossSeg(C.Structure):
+    _fields_ = [("kind", C.c_int32), ("a", C.c_void_p), ("b", C.c_void_p), ("n", C.c_int32), ("c", C.c_int32),
+                ("h", C.c_int32), ("w", C.c_int32), ("target", C.c_float), ("grad_scale", C.c_float),
+                ("tanh_bwd", C.c_int32), ("slot_loss", C.c_int32), ("slot_aux", C.c_int32), ("grad", C.POINTER(Plane))]
+
+
+LOSS_LSGAN, LOSS_L1 = 0, 1
+
 _lib = None
 
 _P = C.c_void_p
@@ -74,6 +82,7 @@ _SIGS = {
                                  C.POINTER(Plane), _P, _P]),
     "dtg_loss_l1": (C.c_int, [_P, _P, C.c_int, C.c_int, C.c_int, C.c_int, C.c_float, C.c_int, _P, C.c_int, C.c_int,
                               C.POINTER(Plane), _P, _P]),
+    "dtg_loss_fused": (C.c_int, [C.POINTER(LossSeg), C.c_int, _P, _P, _P]),
     "dtg_grad_sumsq": (C.c_int, [_P, C.c_size_t, C.c_float, _P, _P, _P]),
     "dtg_adam_clip": (C.c_int, [_P, _P, _P, _P, C.c_size_t, _P, _P, _P, C.c_float, _P]),
     "dtg_step_increment": (C.c_int, [_P, _P]),

@@ -37,7 +37,7 @@ void count_launch();
 // its prologue while this one drains; every kernel calls pdl_enter() (trigger + wait) before touching global memory,
 // so data dependencies (RAW and WAR) are still honoured.  DTG_NO_PDL=1 disables the attribute.
 bool pdl_enabled();
-bool tma_norm_enabled();       // dtg_set_option("tma_norm")
+int norm_impl();               // dtg_set_option("norm_impl"): 0 cluster-fused, 1 TMA-staged, 2 two-phase streaming
 bool wgrad_atomic_enabled();   // dtg_set_option("wgrad_atomic")
 #ifdef __CUDACC__
 template <typename... KArgs, typename... Args>

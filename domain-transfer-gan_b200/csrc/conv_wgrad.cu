@@ -240,54 +240,43 @@ __global__ void __launch_bounds__(kWThreads, 1) wgrad_kernel(const __grid_consta
 // dw[(a*qb + b)*ntaps + t] += sum_s ws[(((s*ntaps + t)*(n_umma/4) + b/4)*mtot + a)*4 + b%4]
 // fold = 1: accumulator column b' = j*fc + b holds filter column kw = j          (t = kh, KW real columns)
 // fold = 2: accumulator row    a' = j*fc + a holds filter column kw = KW - 1 - j
-// One thread per float4 of accumulator columns: consecutive threads take consecutive rows (= consecutive float4 of the
-// workspace: every warp load is 512 contiguous bytes), all split loads of a thread are independent (16 in flight) and
-// summed in split order (deterministic, no atomics, no shared memory, no barrier).
+// kRSub (default 4) threads per float4 of accumulator columns: lane q of the group loads splits q, q+kRSub, ... (a handful of
+// independent 16-byte loads; the memory-level parallelism comes from the number of resident warps, ptxas sinks
+// per-thread load batches behind the adds), sums them in split order, then the lane sums are combined by a fixed xor
+// tree: deterministic, no shared memory.  A warp load instruction covers 32 / kRSub consecutive rows of kRSub splits.
+template <int kRSub>
 __global__ void __launch_bounds__(256) wgrad_reduce_kernel(const float4* __restrict__ ws, float* __restrict__ dw, int splits,
                                                            int ntaps, int mtot, int n_umma, int pa, int qb, int fold, int KW,
-                                                           int fc, int rows, int ncv4, int total) {
+                                                           int fc, int rows, int ncv4, int total, int dbg) {
   pdl_enter();
-  const int i = blockIdx.x * 256 + threadIdx.x;
-  if (i >= total) return;
+  const int gi = blockIdx.x * 256 + threadIdx.x;
+  const int i = gi / kRSub, sub = gi % kRSub;
+  const bool ok = i < total;
   const int ncol4 = n_umma / 4;
-  const int row = i % rows;
-  const int c4 = (i / rows) % ncv4;
-  const int t = i / (ncv4 * rows);
+  const int row = ok ? i % rows : 0;
+  const int c4 = ok ? (i / rows) % ncv4 : 0;
+  const int t = ok ? i / (ncv4 * rows) : 0;
   const float4* src = ws + (static_cast<size_t>(t) * ncol4 + c4) * mtot + row;
   const size_t sstride = static_cast<size_t>(ntaps) * mtot * ncol4;
   float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
-  int s = 0;
-  for (; s + 16 <= splits; s += 16) {
-    float4 v[16];
-#pragma unroll
-    for (int u = 0; u < 16; ++u) v[u] = __ldcg(src + (s + u) * sstride);
-#pragma unroll
-    for (int u = 0; u < 16; ++u) {
-      acc.x += v[u].x;
-      acc.y += v[u].y;
-      acc.z += v[u].z;
-      acc.w += v[u].w;
+  if (ok) {
+#pragma unroll 4
+    for (int s = sub; s < splits; s += kRSub) {
+      const float4 v = __ldcg(src + s * sstride);
+      acc.x += v.x;
+      acc.y += v.y;
+      acc.z += v.z;
+      acc.w += v.w;
     }
   }
-  for (; s + 4 <= splits; s += 4) {
-    float4 v[4];
 #pragma unroll
-    for (int u = 0; u < 4; ++u) v[u] = __ldcg(src + (s + u) * sstride);
-#pragma unroll
-    for (int u = 0; u < 4; ++u) {
-      acc.x += v[u].x;
-      acc.y += v[u].y;
-      acc.z += v[u].z;
-      acc.w += v[u].w;
-    }
+  for (int off = 1; off < kRSub; off <<= 1) {
+    acc.x += __shfl_xor_sync(0xffffffffu, acc.x, off);
+    acc.y += __shfl_xor_sync(0xffffffffu, acc.y, off);
+    acc.z += __shfl_xor_sync(0xffffffffu, acc.z, off);
+    acc.w += __shfl_xor_sync(0xffffffffu, acc.w, off);
   }
-  for (; s < splits; ++s) {
-    const float4 v = __ldcg(src + s * sstride);
-    acc.x += v.x;
-    acc.y += v.y;
-    acc.z += v.z;
-    acc.w += v.w;
-  }
+  if (!ok || sub != 0 || (dbg & 8)) return;
   const float av[4] = {acc.x, acc.y, acc.z, acc.w};
 #pragma unroll
   for (int e = 0; e < 4; ++e) {
@@ -301,11 +290,14 @@ __global__ void __launch_bounds__(256) wgrad_reduce_kernel(const float4* __restr
       a = row % fc;
     }
     if (a >= pa || b >= qb || j >= KW) continue;
+    // every gradient element is owned by exactly ONE thread of this launch, so the accumulation into dw is a single
+    // red.global.add per address: deterministic, and fire-and-forget (a load-add-store here costs a dependent L2 round
+    // trip per element on a scattered, 36-byte-stride pattern: measured 17 of the kernel's 23 us)
     if (fold) {
       const int kw = fold == 2 ? KW - 1 - j : j;
-      dw[((static_cast<size_t>(a) * qb + b) * ntaps + t) * KW + kw] += av[e];
+      atomicAdd(&dw[((static_cast<size_t>(a) * qb + b) * ntaps + t) * KW + kw], av[e]);
     } else {
-      dw[(static_cast<size_t>(a) * qb + b) * ntaps + t] += av[e];
+      atomicAdd(&dw[(static_cast<size_t>(a) * qb + b) * ntaps + t], av[e]);
     }
   }
 }
@@ -562,7 +554,20 @@ extern "C" int dtg_conv_wgrad(const dtg_wgrad_args* a, const dtg_plane* pp, cons
   const int rrows = p.rows_valid;
   const int ncv4 = (p.cols_valid + 3) / 4;
   const int total = pl.ntaps * rrows * ncv4;
-  DTG_CHECK_CUDA(launch_k(wgrad_reduce_kernel, (total + 255) / 256, 256, 0, stream, reinterpret_cast<const float4*>(p.ws), dw, pl.splits,
-                          pl.ntaps, p.mtot, pl.n_umma, a->pa, a->qb, fold, a->kw, 16 / es, rrows, ncv4, total));
+  static const int rsub = getenv("DTG_REDUCE_SUB") ? atoi(getenv("DTG_REDUCE_SUB")) : 4;
+#define DTG_REDUCE(SUB)                                                                                                        \
+  DTG_CHECK_CUDA(launch_k(wgrad_reduce_kernel<SUB>, static_cast<int>((static_cast<long long>(SUB) * total + 255) / 256), 256, 0, \
+                          stream, reinterpret_cast<const float4*>(p.ws), dw, pl.splits, pl.ntaps, p.mtot, pl.n_umma, a->pa, \
+                          a->qb, fold, a->kw, 16 / es, rrows, ncv4, total, p.dbg))
+  if (rsub == 1) {
+    DTG_REDUCE(1);
+  } else if (rsub == 4) {
+    DTG_REDUCE(4);
+  } else if (rsub == 8) {
+    DTG_REDUCE(8);
+  } else {
+    DTG_REDUCE(16);
+  }
+#undef DTG_REDUCE
   return DTG_OK;
 }

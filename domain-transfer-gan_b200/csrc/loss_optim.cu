@@ -62,10 +62,9 @@ __device__ __forceinline__ void st_plane(const dtg_plane& p, size_t idx, float v
     reinterpret_cast<float*>(p.ptr)[idx] = round_tf32(v);
 }
 
-__global__ void __launch_bounds__(kRedThreads) lsgan_kernel(const float* __restrict__ pred, int n, int h, int w, float target,
-                                                            float gscale, float* __restrict__ scalars, int slot_loss,
-                                                            int slot_mean, dtg_plane dp, RedWs* ws) {
-  pdl_enter();
+__device__ __forceinline__ void lsgan_body(const float* __restrict__ pred, int n, int h, int w, float target, float gscale,
+                                           float* __restrict__ scalars, int slot_loss, int slot_mean, const dtg_plane& dp,
+                                           RedWs* ws) {
   __shared__ float sm[(kRedThreads / 32) * 2];
   const int count = n * h * w;
   float v[2] = {0.f, 0.f};
@@ -93,11 +92,16 @@ __global__ void __launch_bounds__(kRedThreads) lsgan_kernel(const float* __restr
   }
 }
 
-__global__ void __launch_bounds__(kRedThreads) l1_kernel(const float* __restrict__ a, const float* __restrict__ b, int n, int c,
-                                                         int h, int w, float gscale, int tanh_bwd,
-                                                         float* __restrict__ scalars, int slot_loss, int slot_aux,
-                                                         dtg_plane da, RedWs* ws) {
+__global__ void __launch_bounds__(kRedThreads) lsgan_kernel(const float* __restrict__ pred, int n, int h, int w, float target,
+                                                            float gscale, float* __restrict__ scalars, int slot_loss,
+                                                            int slot_mean, dtg_plane dp, RedWs* ws) {
   pdl_enter();
+  lsgan_body(pred, n, h, w, target, gscale, scalars, slot_loss, slot_mean, dp, ws);
+}
+
+__device__ __forceinline__ void l1_body(const float* __restrict__ a, const float* __restrict__ b, int n, int c, int h, int w,
+                                        float gscale, int tanh_bwd, float* __restrict__ scalars, int slot_loss, int slot_aux,
+                                        const dtg_plane& da, RedWs* ws) {
   __shared__ float sm[(kRedThreads / 32) * 2];
   __shared__ float smm[(kRedThreads / 32) * 2];
   const int count = n * c * h * w;
@@ -154,6 +158,40 @@ __global__ void __launch_bounds__(kRedThreads) l1_kernel(const float* __restrict
       scalars[slot_aux + 2] = gmx;
     }
   }
+}
+
+__global__ void __launch_bounds__(kRedThreads) l1_kernel(const float* __restrict__ a, const float* __restrict__ b, int n, int c,
+                                                         int h, int w, float gscale, int tanh_bwd,
+                                                         float* __restrict__ scalars, int slot_loss, int slot_aux,
+                                                         dtg_plane da, RedWs* ws) {
+  pdl_enter();
+  l1_body(a, b, n, c, h, w, gscale, tanh_bwd, scalars, slot_loss, slot_aux, da, ws);
+}
+
+// Multi-segment loss reduction: blockIdx.y selects one loss term (LSGAN MSE against a constant target, or L1 with the
+// optional tanh-backward factor and the KLD / min / max side outputs); every term reduces into its own slots of the
+// packed scalar vector and writes its own seed-gradient plane, all in ONE launch (model.py:432-439, 458-505).
+constexpr int kMaxLossSegs = 8;
+struct LossSegDev {
+  const float* a;
+  const float* b;
+  int kind, n, c, h, w;
+  float target, gscale;
+  int tanh_bwd, slot_loss, slot_aux;
+  dtg_plane d;
+};
+struct LossSegs {
+  LossSegDev s[kMaxLossSegs];
+};
+
+__global__ void __launch_bounds__(kRedThreads) loss_fused_kernel(const __grid_constant__ LossSegs L, float* __restrict__ scalars,
+                                                                 RedWs* ws) {
+  pdl_enter();
+  const LossSegDev& g = L.s[blockIdx.y];
+  if (g.kind == 0)
+    lsgan_body(g.a, g.n, g.h, g.w, g.target, g.gscale, scalars, g.slot_loss, g.slot_aux, g.d, ws + blockIdx.y);
+  else
+    l1_body(g.a, g.b, g.n, g.c, g.h, g.w, g.gscale, g.tanh_bwd, scalars, g.slot_loss, g.slot_aux, g.d, ws + blockIdx.y);
 }
 
 __global__ void __launch_bounds__(kRedThreads) sumsq_kernel(const float* __restrict__ g, size_t count, float gscale,
@@ -240,6 +278,38 @@ extern "C" int dtg_loss_l1(const float* a, const float* b, int n, int c, int h, 
     dp = *da;
   }
   DTG_CHECK_CUDA(launch_k(l1_kernel, red_blocks(static_cast<size_t>(n) * c * h * w), kRedThreads, 0, static_cast<cudaStream_t>(stream), a, b, n, c, h, w, grad_scale, tanh_bwd, scalars, slot_loss, slot_aux, dp, reinterpret_cast<RedWs*>(workspace)));
+  return DTG_OK;
+}
+
+extern "C" int dtg_loss_fused(const dtg_loss_seg* segs, int nseg, float* scalars, void* workspace, void* stream) {
+  DTG_REQUIRE(segs && scalars && workspace && nseg >= 1 && nseg <= kMaxLossSegs, "dtg_loss_fused: 1..%d segments", kMaxLossSegs);
+  LossSegs L;
+  memset(&L, 0, sizeof(L));
+  size_t most = 1;
+  for (int i = 0; i < nseg; ++i) {
+    const dtg_loss_seg& q = segs[i];
+    DTG_REQUIRE(q.a && (q.kind == DTG_LOSS_LSGAN || (q.kind == DTG_LOSS_L1 && q.b)), "dtg_loss_fused: segment %d: null tensor / bad kind", i);
+    LossSegDev& d = L.s[i];
+    d.a = q.a;
+    d.b = q.b;
+    d.kind = q.kind;
+    d.n = q.n;
+    d.c = q.kind == DTG_LOSS_LSGAN ? 1 : q.c;
+    d.h = q.h;
+    d.w = q.w;
+    d.target = q.target;
+    d.gscale = q.grad_scale;
+    d.tanh_bwd = q.tanh_bwd;
+    d.slot_loss = q.slot_loss;
+    d.slot_aux = q.slot_aux;
+    if (q.grad && q.grad->ptr) {
+      DTG_REQUIRE(q.grad->n == q.n && q.grad->h == q.h && q.grad->w == q.w && q.grad->c >= d.c, "dtg_loss_fused: segment %d: gradient plane mismatch", i);
+      d.d = *q.grad;
+    }
+    most = std::max(most, static_cast<size_t>(d.n) * d.c * d.h * d.w);
+  }
+  DTG_CHECK_CUDA(launch_k(loss_fused_kernel, dim3(red_blocks(most), nseg, 1), kRedThreads, 0, static_cast<cudaStream_t>(stream), L, scalars,
+                          reinterpret_cast<RedWs*>(workspace)));
   return DTG_OK;
 }
 

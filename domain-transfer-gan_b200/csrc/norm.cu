@@ -478,7 +478,8 @@ extern "C" int dtg_norm_fwd(const dtg_norm_args* a, const dtg_plane* x, const dt
     DTG_REQUIRE(gamma && beta && stats && coef && partial, "dtg_norm_fwd: missing buffers");
     DTG_REQUIRE(mode != DTG_NORM_COND_INSTANCE || hw > 1, "dtg_norm_fwd: conditional instance norm needs H*W > 1");
     {
-      int rc = try_norm_fwd_tma(a, x, residual, gamma, beta, stats, out, stream);
+      int rc = try_norm_fwd_lean(a, x, residual, gamma, beta, stats, partial + 2 * x->c, out, stream);
+      if (rc == 1) rc = try_norm_fwd_tma(a, x, residual, gamma, beta, stats, out, stream);
       if (rc == 1) rc = try_norm_fwd_fused(a, x, residual, gamma, beta, stats, out, stream);
       if (rc <= 0) return rc;    // launched (0) or failed (<0); 1 = not handled by the cluster kernel
     }
@@ -545,7 +546,8 @@ extern "C" int dtg_norm_bwd(const dtg_norm_args* a, const dtg_plane* dy, const d
   float* sums_buf = sums ? sums : kcoef + static_cast<size_t>(n) * c * 4;   // scratch when the caller wants none
   const int nc = n * c;
   if (mode == DTG_NORM_INSTANCE || mode == DTG_NORM_COND_INSTANCE || (mode == DTG_NORM_NONE && d_beta != nullptr)) {
-    int rc = try_norm_bwd_tma(a, dy, dy2, y, &p_x, stats, gamma, sums_buf, dx, d_res, stream);
+    int rc = try_norm_bwd_lean(a, dy, dy2, y, &p_x, stats, gamma, sums_buf, part, dx, d_res, stream);
+    if (rc == 1) rc = try_norm_bwd_tma(a, dy, dy2, y, &p_x, stats, gamma, sums_buf, dx, d_res, stream);
     if (rc == 1) rc = try_norm_bwd_fused(a, dy, dy2, y, &p_x, stats, gamma, sums_buf, dx, d_res, stream);
     if (rc < 0) return rc;
     if (rc == 0) {

@@ -598,7 +598,7 @@ static int launch_tma_norm(K kernel, const P& p0, size_t smem, cudaStream_t stre
 int try_norm_bwd_tma(const dtg_norm_args* a, const dtg_plane* dy, const dtg_plane* dy2, const dtg_plane* y,
                      const dtg_plane* x, const float* stats, const float* gamma, float* sums, const dtg_plane* dx,
                      const dtg_plane* d_res, cudaStream_t stream) {
-  if (!tma_norm_enabled() || a->phase != 0 || a->mode == DTG_NORM_BATCH) return 1;
+  if (norm_impl() != 1 || a->phase != 0 || a->mode == DTG_NORM_BATCH) return 1;
   const bool has_norm = a->mode != DTG_NORM_NONE;
   const bool has_dy2 = dy2 && dy2->ptr, has_y = a->act != DTG_ACT_NONE, has_dres = d_res && d_res->ptr;
   if (!has_norm && !has_y) return 1;
@@ -686,7 +686,7 @@ int try_norm_bwd_tma(const dtg_norm_args* a, const dtg_plane* dy, const dtg_plan
 
 int try_norm_fwd_tma(const dtg_norm_args* a, const dtg_plane* x, const dtg_plane* residual, const float* gamma,
                      const float* beta, float* stats, const dtg_plane* out, cudaStream_t stream) {
-  if (!tma_norm_enabled() || a->phase != 0 || (a->mode != DTG_NORM_INSTANCE && a->mode != DTG_NORM_COND_INSTANCE)) return 1;
+  if (norm_impl() != 1 || a->phase != 0 || (a->mode != DTG_NORM_INSTANCE && a->mode != DTG_NORM_COND_INSTANCE)) return 1;
   if (a->act == DTG_ACT_TANH) return 1;
   const bool has_res = residual && residual->ptr;
   if (x->halo != 0 || x->h * x->w < 2 || x->n > 65535) return 1;

@@ -162,7 +162,7 @@ class _FusedCycleModel(object):
         self.scalars = torch.zeros(N_SCALARS, dtype=torch.float32, device=self.device)
         self.scalars_host = torch.zeros(N_SCALARS, dtype=torch.float32).pin_memory()
         self.lanes = ops.Lanes(5, self.device)
-        self.red_ws = torch.zeros(5, 1024, dtype=torch.float32, device=self.device)    # reduction scratch, per lane
+        self.red_ws = torch.zeros(5, 4096, dtype=torch.float32, device=self.device)    # reduction scratch, per lane (4 x 4 KB)
         self.criterionGAN = functools.partial(criterion_GAN, use_sigmoid=opt.use_sigmoid)
         self.criterionCycle = torch.nn.functional.l1_loss
         self.dp = None                 # parallel.DataParallelPlan when running one process per GPU
@@ -514,8 +514,9 @@ class AugmentedCycleGAN(_FusedCycleModel):
             ops.pack_nchw(fake, c.acts[0].batch_slice(0, n), 0)
             ops.pack_nchw(real, c.acts[0].batch_slice(n, 2 * n), 0)
             p = ex.forward(c)["out"]
-            ops.loss_lsgan(p[:n], 0.0, 0.5, sc, s_fake, s_pf, c.dyraw[i].batch_slice(0, n), ws())
-            ops.loss_lsgan(p[n:], 1.0, 0.5, sc, s_true, s_pt, c.dyraw[i].batch_slice(n, 2 * n), ws())
+            # 0.5 * (mse(D(fake), 0) + mse(D(real), 1)) and both seed gradients: ONE two-segment reduction (model.py:327-334)
+            ops.loss_fused([ops.lsgan_seg(p[:n], 0.0, 0.5, s_fake, s_pf, c.dyraw[i].batch_slice(0, n)),
+                            ops.lsgan_seg(p[n:], 1.0, 0.5, s_true, s_pt, c.dyraw[i].batch_slice(n, 2 * n))], sc, ws())
             ex.backward(c, {"out": True})
             r[ex] = ar(ex.arena)
 
@@ -539,9 +540,11 @@ class AugmentedCycleGAN(_FusedCycleModel):
 
         def d_z():      # batch-norm net: separate calls, reference order
             ops.pack_nchw(r["mu"], cz1.acts[0], 0)
-            ops.loss_lsgan(DZ.forward(cz1, sync_bn)["out"], 0.0, 0.5, sc, S_DPZ, -1, cz1.dyraw[iZ], ws())
+            p_post = DZ.forward(cz1, sync_bn)["out"]
             ops.pack_nchw(z_prior4, cz2.acts[0], 0)
-            ops.loss_lsgan(DZ.forward(cz2, sync_bn)["out"], 1.0, 0.5, sc, S_DQZ, -1, cz2.dyraw[iZ], ws())
+            p_prior = DZ.forward(cz2, sync_bn)["out"]
+            ops.loss_fused([ops.lsgan_seg(p_post, 0.0, 0.5, S_DPZ, -1, cz1.dyraw[iZ]),
+                            ops.lsgan_seg(p_prior, 1.0, 0.5, S_DQZ, -1, cz2.dyraw[iZ])], sc, ws())
             if o.z_gan:
                 DZ.backward(cz1, {"out": True}, sync_bn=sync_bn)
                 DZ.backward(cz2, {"out": True}, sync_bn=sync_bn)
@@ -820,8 +823,9 @@ class StochCycleGAN(_FusedCycleModel):
             ops.pack_nchw(fake, c.acts[0].batch_slice(0, n), 0)
             ops.pack_nchw(real, c.acts[0].batch_slice(n, 2 * n), 0)
             p = ex.forward(c)["out"]
-            ops.loss_lsgan(p[:n], 0.0, 0.5, sc, s_fake, s_pf, c.dyraw[i].batch_slice(0, n), ws())
-            ops.loss_lsgan(p[n:], 1.0, 0.5, sc, s_true, s_pt, c.dyraw[i].batch_slice(n, 2 * n), ws())
+            # 0.5 * (mse(D(fake), 0) + mse(D(real), 1)) and both seed gradients: ONE two-segment reduction (model.py:327-334)
+            ops.loss_fused([ops.lsgan_seg(p[:n], 0.0, 0.5, s_fake, s_pf, c.dyraw[i].batch_slice(0, n)),
+                            ops.lsgan_seg(p[n:], 1.0, 0.5, s_true, s_pt, c.dyraw[i].batch_slice(n, 2 * n))], sc, ws())
             ex.backward(c, {"out": True})
             r[ex] = ar(ex.arena)
 

@@ -447,6 +447,26 @@ def loss_l1(a, b, grad_scale, tanh_bwd, scalars, slot_loss, slot_aux, da, ws):
                                 slot_loss, slot_aux, da.s if da is not None else NULL_PLANE, _ptr(ws), _stream()), "loss_l1")
 
 
+def lsgan_seg(pred, target, grad_scale, slot_loss, slot_mean, dpred):
+    """one LSGAN term of loss_fused (same meaning as loss_lsgan's arguments)"""
+    n, _, h, w = pred.shape
+    return L.LossSeg(L.LOSS_LSGAN, pred.data_ptr(), None, n, 1, h, w, float(target), float(grad_scale), 0, slot_loss, slot_mean,
+                     C.pointer(dpred._s) if dpred is not None else None), (pred, dpred)
+
+
+def l1_seg(a, b, grad_scale, tanh_bwd, slot_loss, slot_aux, da):
+    n, c, h, w = a.shape
+    return L.LossSeg(L.LOSS_L1, a.data_ptr(), b.data_ptr(), n, c, h, w, 0.0, float(grad_scale), 1 if tanh_bwd else 0, slot_loss,
+                     slot_aux, C.pointer(da._s) if da is not None else None), (a, b, da)
+
+
+def loss_fused(segs, scalars, ws):
+    """several loss terms in ONE launch (dtg_loss_fused); segs: results of lsgan_seg / l1_seg; ws: nseg x 1024 floats"""
+    arr = (L.LossSeg * len(segs))(*[s for s, _ in segs])
+    assert ws.numel() >= 1024 * len(segs)
+    L.check(L.lib().dtg_loss_fused(arr, len(segs), _ptr(scalars), _ptr(ws), _stream()), "loss_fused")
+
+
 def grad_sumsq(g, grad_scale, out, ws):
     L.check(L.lib().dtg_grad_sumsq(_ptr(g), g.numel(), float(grad_scale), _ptr(out), _ptr(ws), _stream()), "grad_sumsq")
 
@@ -503,7 +523,7 @@ def _logged(name, fn, work=None):
 for _n, _w in (("conv", _conv_work), ("conv_wgrad", _wgrad_work), ("norm_fwd", _norm_fwd_work), ("norm_bwd", _norm_bwd_work),
                ("pack_nchw", None), ("unpack_nchw", None), ("s2d_unfold_add", None), ("head1_fwd", None), ("head1_dgrad", None),
                ("head1_wgrad", None), ("cin_affine_fwd", None), ("cin_affine_bwd", None), ("grad_gather", None),
-               ("channel_sum", None), ("loss_lsgan", None), ("loss_l1", None), ("grad_sumsq", None), ("adam_clip", None),
+               ("channel_sum", None), ("loss_lsgan", None), ("loss_l1", None), ("loss_fused", None), ("grad_sumsq", None), ("adam_clip", None),
                ("step_increment", None)):
     globals()[_n] = _logged(_n, globals()[_n], _w)
 PackTable.run = _logged("pack_weights", PackTable.run)

@@ -28,7 +28,7 @@
 extern "C" {
 #endif
 
-#define DTG_VERSION 120 /* 120: dtg_set_option; TMA-staged instance-norm kernels behind dtg_norm_fwd / dtg_norm_bwd */
+#define DTG_VERSION 120 /* 120: dtg_set_option, dtg_loss_fused; two-phase / TMA-staged instance-norm kernels behind dtg_norm_fwd / dtg_norm_bwd */
 
 enum { DTG_OK = 0, DTG_ERR_INVALID = -1, DTG_ERR_CUDA = -2, DTG_ERR_UNSUPPORTED = -3 };
 enum { DTG_BF16 = 0, DTG_F32 = 1 };
@@ -57,8 +57,10 @@ int dtg_last_error(char* buf, size_t cap);
  *                 attribute and start with griddepcontrol.launch_dependents / .wait, so a prologue overlaps the previous
  *                 kernel's tail.  0 = plain stream-ordered launches: per-kernel device durations (CUPTI, ncu) then do not
  *                 include time spent waiting for a predecessor (bench.py's per-kernel roofline pass).
- *   "tma_norm"    0 (default; env DTG_TMA_NORM=1 -> 1): dtg_norm_fwd / dtg_norm_bwd use the TMA-staged cluster kernels
- *                 (norm_tma.cu) instead of the register-resident ones (norm_fused.cu) where the geometry allows.
+ *   "norm_impl"   which kernels serve the instance / conditional-instance modes of dtg_norm_fwd / dtg_norm_bwd where the
+ *                 geometry allows (env DTG_NORM_IMPL): 2 (default) two-phase streaming forward (norm_lean.cu) + register-
+ *                 resident cluster backward (norm_fused.cu) -- the fastest pair measured on B200; 3 two-phase streaming
+ *                 forward and backward; 1 TMA-staged cluster kernels (norm_tma.cu); 0 cluster kernels of norm_fused.cu.
  *   "smem_cap_kb" 227 (env DTG_SMEM_CAP_KB): shared-memory budget of one tensor-core CTA; what it leaves free decides
  *                 whether bandwidth-bound kernels of other streams can be co-resident on the same SM.
  *   "wgrad_atomic" 0 (env DTG_WGRAD_ATOMIC=1 -> 1): the weight-gradient split-K partials are accumulated with
@@ -268,6 +270,23 @@ int dtg_loss_lsgan(const float* pred, int n, int h, int w, float target, float g
                    int slot_loss, int slot_mean, const dtg_plane* dpred, void* workspace, void* stream);
 int dtg_loss_l1(const float* a, const float* b, int n, int c, int h, int w, float grad_scale, int tanh_bwd,
                 float* scalars, int slot_loss, int slot_aux, const dtg_plane* da, void* workspace, void* stream);
+
+/* Multi-segment form: up to 8 loss terms (each exactly one dtg_loss_lsgan or dtg_loss_l1 call) reduced in ONE launch --
+ * e.g. the fake / real pair of a discriminator's D-pass loss (model.py:327-334, 432-434) or the latent discriminator's
+ * posterior / prior pair.  kind DTG_LOSS_LSGAN: a = pred [n][1][h][w], slot_aux = the mean(pred) slot; kind DTG_LOSS_L1:
+ * a, b [n][c][h][w], slot_aux as in dtg_loss_l1.  `grad`: the segment's seed-gradient plane or NULL.
+ * workspace: nseg x 4 KB, zero-initialised once by the caller (self-resetting). */
+enum { DTG_LOSS_LSGAN = 0, DTG_LOSS_L1 = 1 };
+typedef struct dtg_loss_seg {
+  int32_t kind;
+  const float* a;
+  const float* b;
+  int32_t n, c, h, w;
+  float target, grad_scale;
+  int32_t tanh_bwd, slot_loss, slot_aux;
+  const dtg_plane* grad;
+} dtg_loss_seg;
+int dtg_loss_fused(const dtg_loss_seg* segs, int nseg, float* scalars, void* workspace, void* stream);
 
 /* ---------------------------------------------------------------------------------------------
  * clip_grad_norm + Adam over one flat fp32 arena (model.py:447-452,510-515; torch.optim.Adam,

@@ -52,7 +52,7 @@ def test_ctypes_structs_match_header():
         return names
 
     for cname, pyt in (("dtg_plane", _lib.Plane), ("dtg_conv_args", _lib.ConvArgs), ("dtg_wgrad_args", _lib.WgradArgs),
-                       ("dtg_norm_args", _lib.NormArgs), ("dtg_pack_item", _lib.PackItem)):
+                       ("dtg_norm_args", _lib.NormArgs), ("dtg_pack_item", _lib.PackItem), ("dtg_loss_seg", _lib.LossSeg)):
         assert fields(cname) == [f[0] for f in pyt._fields_], cname
 
 

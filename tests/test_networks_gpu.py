@@ -93,7 +93,7 @@ def _compare(name, prec, net, ours_outs, ours_ingrads, ref, low):
         assert _rel(o, r) < OUT_TOL[prec], (name, "out", _rel(o, r))
     real = [k for k in r_pg if not onets.is_noise_grad(name, k)]
     low_worst = max([_rel(l_pg[k], r_pg[k]) for k in real] + [_rel(a, b) for a, b in zip(l_in, r_in)])
-    bound = GRAD_FACTOR * low_worst + 2e-3
+    bound = GRAD_FACTOR[prec] * low_worst + 2e-3
     ours_worst = max([_rel(dict(net.named_parameters())[k].grad, r_pg[k]) for k in real] + [_rel(a, b) for a, b in zip(ours_ingrads, r_in)])
     record("network", name=name, prec=prec, grad_err=ours_worst, ref_lowprec_grad_err=low_worst, grad_ratio=ours_worst / max(low_worst, 1e-12))
     for a, b in zip(ours_ingrads, r_in):
@@ -159,10 +159,10 @@ def test_generator_per_layer_activations_tf32(which):
         ours = c.acts[idx].to_nchw(r.shape[1])
         e, el = _rel(ours, r), _rel(low[name], r)
         rows.append((name, e, el))
-        assert e <= max(1e-3, GRAD_FACTOR * el), (which, name, e, el)
+        assert e <= max(1e-3, 1.5 * el), (which, name, e, el)
     e, el = _rel(y, yr), _rel(yl, yr)
     rows.append(("out", e, el))
-    assert e <= max(1e-3, GRAD_FACTOR * el), (which, "out", e, el)
+    assert e <= max(1e-3, 1.5 * el), (which, "out", e, el)
     record("per_layer_tf32", net=which, layers={n: [round(a, 6), round(b, 6)] for n, a, b in rows})
 
 
@@ -193,7 +193,7 @@ def test_standalone_residual_blocks(kind, prec):
     noise = ("conv_block.1.module1.bias", "conv_block.4.bias")       # biases in front of a mean-removing norm
     real = [k for k in r_pg if k not in noise]
     low_worst = max([_rel(l_pg[k], r_pg[k]) for k in real] + [_rel(a, b) for a, b in zip(l_in, r_in)])
-    bound = GRAD_FACTOR * low_worst + 2e-3
+    bound = GRAD_FACTOR[prec] * low_worst + 2e-3
     for a, b in zip([t.grad for t in ins], r_in):
         assert _rel(a, b) < bound, (kind, "input grad", _rel(a, b), bound)
     pg = dict(blk.named_parameters())

@@ -99,7 +99,7 @@ def _check_step(prec, n, seed_x=4321, **opt_kw):
     assert list(losses.keys()) == list(rl.keys()) and list(gnorms.keys()) == list(rg.keys())
     assert list(visuals.keys()) == list(rv.keys())
     vis_low = max(_rel(lv[k], rv[k]) for k in rv)
-    vis_bound = GRAD_FACTOR * vis_low + 1e-3     # rec_* run through three networks
+    vis_bound = GRAD_FACTOR[prec] * vis_low + 1e-3     # rec_* run through three networks
     vis_worst = max(_rel(visuals[k], rv[k]) for k in rv)
     worst_low, worst = 0.0, 0.0
     for name in rgrad:
@@ -111,7 +111,7 @@ def _check_step(prec, n, seed_x=4321, **opt_kw):
             grad_ratio=worst / max(worst_low, 1e-12), vis_err=vis_worst, ref_lowprec_vis_err=vis_low)
     for k in rv:
         assert _rel(visuals[k], rv[k]) < vis_bound, (k, _rel(visuals[k], rv[k]), vis_bound)
-    bound = GRAD_FACTOR * worst_low + 2e-3
+    bound = GRAD_FACTOR[prec] * worst_low + 2e-3
     for name in rgrad:
         for k, rgk in rgrad[name].items():
             if onets.is_noise_grad(name, k):

@@ -77,7 +77,7 @@ def test_stoch_train_instance_matches_oracle(prec, size, out_nc, ignore_noise):
     ltol = 2e-3 if prec == "tf32" else 3e-2
     for k, v in rl.items():
         assert abs(losses[k] - v) <= ltol * max(1.0, abs(v)), (k, losses[k], v)
-    vis_bound = GRAD_FACTOR * max(_rel(lv[k], rv[k]) for k in rv) + 1e-3
+    vis_bound = GRAD_FACTOR[prec] * max(_rel(lv[k], rv[k]) for k in rv) + 1e-3
     for k in rv:
         assert _rel(visuals[k], rv[k]) < vis_bound, (k, _rel(visuals[k], rv[k]), vis_bound)
     worst_low = 0.0
@@ -85,7 +85,7 @@ def test_stoch_train_instance_matches_oracle(prec, size, out_nc, ignore_noise):
         for k in rgrad[name]:
             if not onets.is_noise_grad(name, k):
                 worst_low = max(worst_low, _rel(lgrad[name][k], rgrad[name][k]))
-    bound = GRAD_FACTOR * worst_low + 2e-3
+    bound = GRAD_FACTOR[prec] * worst_low + 2e-3
     worst = max(_rel(got[name][k], rgk) for name in rgrad for k, rgk in rgrad[name].items()
                 if not onets.is_noise_grad(name, k) and float(rgk.norm()) > 0.0)
     record("stoch_train_instance", prec=prec, size=size, grad_err=worst, ref_lowprec_grad_err=worst_low,

@@ -45,7 +45,7 @@ for name, f, passes in (("fwd", fwd, 2 + (1 if residual else 0)), ("bwd", bwd, 4
     torch.cuda.synchronize()
     us = e0.elapsed_time(e1) * 1e3 / reps
     print("norm %s [%d,%d,%d,%d] halo %d res %d%s: %.1f us  algorithmic %.0f MB -> %.0f GB/s" %
-          (name, N, h, h, c, halo, residual, " (TMA kernels)" if os.environ.get("DTG_TMA_NORM") else "", us, passes * nbytes / 1e6, passes * nbytes / us / 1e3))
+          (name, N, h, h, c, halo, residual, " (norm_impl %s)" % os.environ.get("DTG_NORM_IMPL", "default"), us, passes * nbytes / 1e6, passes * nbytes / us / 1e3))
 if os.environ.get("PROF_KERNELS"):
     from torch.profiler import profile, ProfilerActivity
     with profile(activities=[ProfilerActivity.CUDA]) as prof:
