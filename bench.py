@@ -475,6 +475,8 @@ def main():
             "config": {"workload": _desc(wl, args),
                        "global_batch": world * n, "parallelism": "dp%d" % world, "cuda_graph": bool(graph_ok),
                        "sync_bn": bool(world > 1 and not args.no_sync_bn),
+                       "sync_bn_exchange": ("symmetric-memory one-shot" if (m.dp is not None and m.dp.sync_bn is not None and m.dp.sync_bn.symm)
+                                            else ("nccl" if (m.dp is not None and m.dp.sync_bn is not None) else None)),
                        "l2": "no flush needed: each step streams > 4 GB of activations, far above the 126 MB L2"},
             "e2e": e2e, "gpu_launches": int(launches_per_step * K), "launches_per_step": int(launches_per_step),
             "clocks": clocks,

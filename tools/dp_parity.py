@@ -78,6 +78,15 @@ l1, _, g1 = m1.train_instance(a, b, z)
 torch.cuda.synchronize()
 gone, wone = snapshot(m1)
 
+# ---- noise floor: the same single-GPU step with the samples in reversed order (a mathematically neutral change; only
+# floating-point summation order differs).  The BatchNorm-coupled networks are ill-conditioned at this initialisation,
+# so this floor -- not fp32 epsilon -- is what a data-parallel run can be expected to reproduce.
+m2 = build()
+perm = torch.arange(args.batch - 1, -1, -1, device="cuda")
+m2.train_instance(a[perm].contiguous(), b[perm].contiguous(), z[perm].contiguous())
+torch.cuda.synchronize()
+gperm, _ = snapshot(m2)
+
 
 def rel(x, y):
     return float((x - y).norm() / y.norm().clamp_min(1e-20))
@@ -86,6 +95,7 @@ def rel(x, y):
 res = {"world": world, "precision": args.precision, "batch": args.batch, "graph": bool(args.graph),
        "sync_bn": not args.no_sync_bn,
        "grad_rel": {n: rel(gpar[n], gone[n]) for n in gone},
+       "perm_noise_grad_rel": {n: rel(gperm[n], gone[n]) for n in gone},
        "weight_rel": {n: rel(wpar[n], wone[n]) for n in wone},
        "loss_abs": {kk: abs(float(lt[i]) - l1[kk]) for i, kk in enumerate(keys)},
        "gnorm_rel": {kk: abs(gp[kk] - g1[kk]) / max(abs(g1[kk]), 1e-12) for kk in g1 if kk.startswith("gnorm")}}
