@@ -465,6 +465,7 @@ constexpr int kRegNT = 256;    // its threads per CTA (512 x 2 pixels measured s
 struct FusedGeom {
   int nv, cblocks, cs, chunk;
   int reg_cs, reg_chunk;       // register-resident backward: cluster size / pixels per CTA (0 = not applicable)
+  int reg_nt, reg_nv, reg_cblocks;
 };
 
 static bool fused_geom(const dtg_plane* x, FusedGeom* g) {
@@ -472,7 +473,8 @@ static bool fused_geom(const dtg_plane* x, FusedGeom* g) {
   if (disabled) return false;
   const int es = elem_size(x->dtype);
   const int rowb = x->c * es;
-  const int slabb = std::min(rowb, 128);
+  static const int slab_env = getenv("DTG_FUSED_SLAB") ? atoi(getenv("DTG_FUSED_SLAB")) : 128;
+  const int slabb = std::min(rowb, slab_env);
   if (slabb != 32 && slabb != 64 && slabb != 128) return false;
   if (rowb % slabb != 0) return false;
   const int hw = x->h * x->w;
@@ -484,7 +486,23 @@ static bool fused_geom(const dtg_plane* x, FusedGeom* g) {
   g->cs = cs;
   g->chunk = (hw + cs - 1) / cs;
   // register-resident backward: one CTA covers lanes * kRegPPT pixels, a cluster (<= 8 CTAs) covers the slab
-  const int per_cta = (kRegNT / g->nv) * kRegPPT;
+  // 128-thread CTAs on 64-byte slabs (4 clusters in flight per SM instead of 2, so that one cluster's load phase
+  // overlaps another's reduce / store phase): 50 vs 60 us on [80,32,32,128] + residual.  DTG_REG_VAR: 0 = 256 threads
+  // on 128-byte slabs, 2 = 64 threads on 32-byte slabs.
+  static const int reg_var = getenv("DTG_REG_VAR") ? atoi(getenv("DTG_REG_VAR")) : 1;
+  g->reg_nt = kRegNT;
+  g->reg_nv = g->nv;
+  g->reg_cblocks = g->cblocks;
+  if (reg_var == 1 && slabb >= 64) {
+    g->reg_nt = 128;
+    g->reg_nv = 4;
+    g->reg_cblocks = rowb / 64;
+  } else if (reg_var == 2) {
+    g->reg_nt = 64;
+    g->reg_nv = 2;
+    g->reg_cblocks = rowb / 32;
+  }
+  const int per_cta = (g->reg_nt / g->reg_nv) * kRegPPT;
   g->reg_cs = 0;
   for (int r = 1; r <= 8; r *= 2)
     if (r * per_cta >= hw) {
@@ -560,17 +578,25 @@ int try_norm_bwd_fused(const dtg_norm_args* a, const dtg_plane* dy, const dtg_pl
   const bool hal = dy->halo > 0 || (p_y.ptr && p_y.halo > 0);
   static const bool no_reg = getenv("DTG_NO_REG_NORM") != nullptr;
   static const int dbgv = getenv("DTG_NORM_DBG") ? atoi(getenv("DTG_NORM_DBG")) : 0;
-  const dim3 rgrid(g.cblocks, x->n, g.reg_cs);
+  const dim3 rgrid(g.reg_cblocks, x->n, g.reg_cs);
   const bool reg_ok = dy->halo == 0 || (dy->halo == 1 && dy->h >= 4 && dy->w >= 4);
+#define DTG_REG_LAUNCH(TT, AA, NTV)                                                                                     \
+  do {                                                                                                                  \
+    if (hal)                                                                                                            \
+      return launch_cluster_nt(norm_bwd_reg_kernel<TT, AA, true, kRegPPT, NTV>, rgrid, NTV, g.reg_cs, stream, *dy,      \
+                               p_dy2, p_y, *x, stats, gamma, sums, *dx, p_res, static_cast<int>(a->mode), g.reg_nv,     \
+                               g.reg_chunk, dbgv);                                                                      \
+    return launch_cluster_nt(norm_bwd_reg_kernel<TT, AA, false, kRegPPT, NTV>, rgrid, NTV, g.reg_cs, stream, *dy,       \
+                             p_dy2, p_y, *x, stats, gamma, sums, *dx, p_res, static_cast<int>(a->mode), g.reg_nv,       \
+                             g.reg_chunk, dbgv);                                                                        \
+  } while (0)
 #define DTG_BWD_LAUNCH(TT, AA)                                                                                          \
   do {                                                                                                                  \
     if (a->mode == DTG_NORM_NONE && !(g.reg_cs > 0 && !no_reg && reg_ok)) return 1;                                     \
     if (g.reg_cs > 0 && !no_reg && reg_ok) {                                                                            \
-      if (hal)                                                                                                          \
-        return launch_cluster_nt(norm_bwd_reg_kernel<TT, AA, true, kRegPPT, kRegNT>, rgrid, kRegNT, g.reg_cs, stream, *dy, p_dy2, p_y, *x,   \
-                              stats, gamma, sums, *dx, p_res, static_cast<int>(a->mode), g.nv, g.reg_chunk, dbgv);       \
-      return launch_cluster_nt(norm_bwd_reg_kernel<TT, AA, false, kRegPPT, kRegNT>, rgrid, kRegNT, g.reg_cs, stream, *dy, p_dy2, p_y, *x,    \
-                            stats, gamma, sums, *dx, p_res, static_cast<int>(a->mode), g.nv, g.reg_chunk, dbgv);         \
+      if (g.reg_nt == 128) DTG_REG_LAUNCH(TT, AA, 128);                                                                 \
+      if (g.reg_nt == 64) DTG_REG_LAUNCH(TT, AA, 64);                                                                   \
+      DTG_REG_LAUNCH(TT, AA, 256);                                                                                      \
     }                                                                                                                   \
     if (hal)                                                                                                            \
       return launch_cluster(norm_bwd_fused_kernel<TT, AA, true>, grid, g.cs, stream, *dy, p_dy2, p_y, *x, stats, gamma,    \
@@ -588,6 +614,7 @@ int try_norm_bwd_fused(const dtg_norm_args* a, const dtg_plane* dy, const dtg_pl
     if (a->act == DTG_ACT_NONE) DTG_BWD_LAUNCH(float, DTG_ACT_NONE);
   }
 #undef DTG_BWD_LAUNCH
+#undef DTG_REG_LAUNCH
   return 1;
 }
 

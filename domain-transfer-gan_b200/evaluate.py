@@ -5,8 +5,8 @@ real_B, KL to the prior, backward to (mu, logvar), RMSprop.  The network passes 
 (model.predict_B stays differentiable with respect to z_B, networks._NetFn); the variational objective around them
 (elementwise on [N,3,64,64] and [N,nlatent]) is plain PyTorch host code here -- it is NOT yet fused into kernels, and the
 generator backward also produces the (unused) weight gradients exactly as the reference's autograd does.
-Visualisation (evaluate.py:79-86, 136-147) is left to the caller.  Like the reference, 64x64x3 is hard-coded in the
-bits-per-pixel constant.
+Visualisation (evaluate.py:79-86, 136-147) is left to the caller.  The reference hard-codes 64x64x3 in the
+bits-per-pixel constant and the default logvar_B; here both follow real_B's shape (identical at 64x64x3).
 """
 import math
 
@@ -57,7 +57,7 @@ def variational_ubo(model, real_A, real_B, steps, logvar_B=None, compute_l1=Fals
     mu = torch.zeros(size[0], nz, device=dev, requires_grad=True)                         # :48-50
     logvar = torch.zeros(size[0], nz).fill_(math.log(0.01)).to(dev).requires_grad_(True)
     if logvar_B is None:
-        logvar_B = torch.zeros(1, 3, 64, 64).fill_(math.log(0.01)).to(dev)                # :52
+        logvar_B = torch.zeros(1, *real_B.shape[1:]).fill_(math.log(0.01)).to(dev)        # :52 ([1,3,64,64] there)
     if hasattr(model, 'netE_B'):                                                          # :56-62
         params = model.predict_enc_params(real_A, real_B)
         mu = params[0].detach().clone().requires_grad_(True)
@@ -72,13 +72,14 @@ def variational_ubo(model, real_A, real_B, steps, logvar_B=None, compute_l1=Fals
         with torch.no_grad():
             rec_B = fake_B.detach() if model.opt.stoch_enc else model.predict_B(real_A, mu.detach().view(size[0], nz, 1, 1))
     ubo_val = kld_val = bpp = None
+    ndim = real_B[0].numel()          # the reference hard-codes 64 * 64 * 3 (:103, :106); generalised for N3's larger grids
     for i in range(steps):                                                                # :89
         log_prob = log_prob_laplace(real_B, fake_B, logvar_B).view(size[0], -1).sum(1)    # :93-94
         kld = kld_std_guss(mu, logvar)                                                    # :101
-        ubo = (-log_prob + kld) + (64 * 64 * 3) * math.log(127.5)                         # :103
+        ubo = (-log_prob + kld) + ndim * math.log(127.5)                                  # :103
         ubo_val = float(ubo.detach().mean(0))
         kld_val = float(kld.detach().mean(0))
-        bpp = ubo_val / (64 * 64 * 3 * math.log(2.))                                      # :106
+        bpp = ubo_val / (ndim * math.log(2.))                                             # :106
         if verbose:
             msg = '[%d] UBO: %.4f, KLD: %.4f, BPP: %.4f' % (i, ubo_val, kld_val, bpp)
             if compute_l1:

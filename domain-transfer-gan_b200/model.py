@@ -402,18 +402,23 @@ class AugmentedCycleGAN(_FusedCycleModel):
     def __init__(self, opt, testing=False):
         self._init_common(opt)
         gpu = [0]    # networks always live on the current CUDA device; one process per GPU
+        # N3 extensions, both off unless the option is present: opt.n_blocks (int) is honoured as the number
+        # of res-blocks (the reference ignores it, networks.py:173/225 -> 3); opt.encoder_grid_size = 64 * 2^k gives
+        # E_B k extra stride-2 stages so that the model runs above 64x64 (the reference cannot)
+        nb = getattr(opt, "n_blocks", None)
+        self.grid = int(getattr(opt, "encoder_grid_size", 64) or 64)
         self.netG_A_B = networks.define_stochastic_G(nlatent=opt.nlatent, input_nc=opt.input_nc,
                                                      output_nc=opt.output_nc, ngf=opt.ngf,
                                                      which_model_netG=opt.which_model_netG, norm=opt.norm,
-                                                     use_dropout=opt.use_dropout, gpu_ids=gpu)
+                                                     use_dropout=opt.use_dropout, gpu_ids=gpu, n_blocks=nb)
         self.netG_B_A = networks.define_G(input_nc=opt.output_nc, output_nc=opt.input_nc, ngf=opt.ngf,
                                           which_model_netG=opt.which_model_netG, norm=opt.norm,
-                                          use_dropout=opt.use_dropout, gpu_ids=gpu)
+                                          use_dropout=opt.use_dropout, gpu_ids=gpu, n_blocks=nb)
         enc_input_nc = opt.output_nc
         if opt.enc_A_B:
             enc_input_nc += opt.input_nc
         self.netE_B = networks.define_E(nlatent=opt.nlatent, input_nc=enc_input_nc, nef=opt.nef, norm='batch',
-                                        gpu_ids=gpu)
+                                        gpu_ids=gpu, img_size=self.grid)
         self.netE_B._inactive = ("enc_logvar.weight", "enc_logvar.bias")   # no gradient
         self.netD_A = networks.define_D_A(input_nc=opt.input_nc, ndf=32, which_model_netD=opt.which_model_netD,
                                           norm=opt.norm, use_sigmoid=opt.use_sigmoid, gpu_ids=gpu)
@@ -601,9 +606,11 @@ class AugmentedCycleGAN(_FusedCycleModel):
 
     def _check_inputs(self, real_A, real_B, prior_z_B, free_prior=False):
         ins = self._check_common(real_A, real_B, prior_z_B, free_prior)
-        if real_A.shape[2] != 64 or real_A.shape[3] != 64:
-            raise ValueError("dtg_b200: AugmentedCycleGAN needs 64x64 inputs, exactly like the reference "
-                             "(LatentEncoder yields [N, nlatent] only at 64x64); StochCycleGAN takes any size")
+        if real_A.shape[2] != self.grid or real_A.shape[3] != self.grid:
+            raise ValueError("dtg_b200: this AugmentedCycleGAN needs %dx%d inputs: the reference's LatentEncoder yields "
+                             "[N, nlatent] only at 64x64; build the model with opt.encoder_grid_size = 64 * 2^k for "
+                             "larger grids (extension), or use StochCycleGAN, which takes any size"
+                             % (self.grid, self.grid))
         return ins
 
     def _dicts(self, s):
@@ -754,13 +761,14 @@ class StochCycleGAN(_FusedCycleModel):
         self.ignore_noise = ignore_noise
         self._init_common(opt)
         gpu = [0]
+        nb = getattr(opt, "n_blocks", None)     # honoured when present (N3 extension); None = the reference's 3 blocks
         self.netG_A_B = networks.define_stochastic_G(nlatent=opt.nlatent, input_nc=opt.input_nc,
                                                      output_nc=opt.output_nc, ngf=opt.ngf,
                                                      which_model_netG=opt.which_model_netG, norm=opt.norm,
-                                                     use_dropout=opt.use_dropout, gpu_ids=gpu)
+                                                     use_dropout=opt.use_dropout, gpu_ids=gpu, n_blocks=nb)
         self.netG_B_A = networks.define_G(input_nc=opt.output_nc, output_nc=opt.input_nc, ngf=opt.ngf,
                                           which_model_netG=opt.which_model_netG, norm=opt.norm,
-                                          use_dropout=opt.use_dropout, gpu_ids=gpu)
+                                          use_dropout=opt.use_dropout, gpu_ids=gpu, n_blocks=nb)
         self.netD_A = networks.define_D_A(input_nc=opt.input_nc, ndf=32, which_model_netD=opt.which_model_netD,
                                           norm=opt.norm, use_sigmoid=opt.use_sigmoid, gpu_ids=gpu)
         self.netD_B = networks.define_D_B(input_nc=opt.output_nc, ndf=opt.ndf, which_model_netD=opt.which_model_netD,

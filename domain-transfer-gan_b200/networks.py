@@ -136,20 +136,28 @@ class _FusedNet(nn.Module):
         return _NetFn.apply(self, heads, x, z, *extra)
 
 
-def _gen_layers(model, cin_mode, input_nc, output_nc, ngf):
-    """Layer plan shared by CINResnetGenerator / ResnetGenerator (networks.py:158-189, 210-244)."""
+def _res_block_count(n_blocks, honor_n_blocks):
+    """The reference builds 3 res-blocks whatever n_blocks says (`for i in range(3)`, networks.py:173, 225).
+    honor_n_blocks=True is the N3 extension: range(n_blocks)."""
+    return int(n_blocks) if honor_n_blocks else 3
+
+
+def _gen_layers(model, cin_mode, input_nc, output_nc, ngf, nb=3):
+    """Layer plan shared by CINResnetGenerator / ResnetGenerator (networks.py:158-189, 210-244); nb res-blocks at
+    model.10 .. model.(9+nb), the decoder tail follows at model.(10+nb)."""
     m = model
     relu = L.ACT_RELU
     nk = lambda mod: _norm_kind(mod)
     ls = [
         Layer("model.1", 0, m[1], input_nc, ngf, 7, 1, 3, norm=nk(m[2]), act=relu, norm_mod=m[2]),
         Layer("model.4", 1, m[4], ngf, 2 * ngf, 3, 1, 1, norm=nk(m[5]), act=relu, norm_mod=m[5]),
-        Layer("model.7", 2, m[7], 2 * ngf, 4 * ngf, 3, 2, 1, norm=nk(m[8]), act=relu, norm_mod=m[8], out_halo=1),
+        Layer("model.7", 2, m[7], 2 * ngf, 4 * ngf, 3, 2, 1, norm=nk(m[8]), act=relu, norm_mod=m[8],
+              out_halo=1 if nb > 0 else 0),
     ]
     src = 3
-    for bi, idx in enumerate((10, 11, 12)):
+    for bi, idx in enumerate(range(10, 10 + nb)):
         cb = m[idx].conv_block
-        last = bi == 2
+        last = bi == nb - 1
         if cin_mode:
             conv1, n1 = cb[1].module1, cb[1].module2
             ls.append(Layer("model.%d.a" % idx, src, conv1, 4 * ngf, 4 * ngf, 3, 1, 1, norm=nk(n1), act=relu,
@@ -160,21 +168,26 @@ def _gen_layers(model, cin_mode, input_nc, output_nc, ngf):
         ls.append(Layer("model.%d.b" % idx, src + 1, cb[4], 4 * ngf, 4 * ngf, 3, 1, 1, norm=nk(cb[5]), act=relu,
                         norm_mod=cb[5], out_halo=0 if last else 1, residual=src))
         src += 2
+    t0 = 10 + nb
     ls += [
-        Layer("model.13", src, m[13], 4 * ngf, 2 * ngf, 3, 2, 1, transposed=True, norm=nk(m[14]), act=relu, norm_mod=m[14]),
-        Layer("model.16", src + 1, m[16], 2 * ngf, ngf, 3, 1, 1, norm=nk(m[17]), act=relu, norm_mod=m[17]),
-        Layer("out", src + 2, m[19], ngf, output_nc, 7, 1, 3, act=L.ACT_TANH, head=True),
+        Layer("model.%d" % t0, src, m[t0], 4 * ngf, 2 * ngf, 3, 2, 1, transposed=True, norm=nk(m[t0 + 1]), act=relu,
+              norm_mod=m[t0 + 1]),
+        Layer("model.%d" % (t0 + 3), src + 1, m[t0 + 3], 2 * ngf, ngf, 3, 1, 1, norm=nk(m[t0 + 4]), act=relu,
+              norm_mod=m[t0 + 4]),
+        Layer("out", src + 2, m[t0 + 6], ngf, output_nc, 7, 1, 3, act=L.ACT_TANH, head=True),
     ]
     return ls
 
 
 class CINResnetGenerator(_FusedNet):
-    """networks.py:149-197.  n_blocks is accepted and ignored exactly like the reference (3 blocks)."""
+    """networks.py:149-197.  n_blocks is accepted and ignored exactly like the reference (3 blocks) unless
+    honor_n_blocks=True (extension N3)."""
 
     def __init__(self, nlatent, input_nc, output_nc, ngf=64, norm_layer=CondInstanceNorm,
-                 use_dropout=False, n_blocks=9, gpu_ids=[], padding_type='reflect'):
+                 use_dropout=False, n_blocks=9, gpu_ids=[], padding_type='reflect', honor_n_blocks=False):
         assert (n_blocks >= 0)
         super().__init__()
+        self.n_res = _res_block_count(n_blocks, honor_n_blocks)
         if use_dropout or padding_type != 'reflect' or norm_layer is not CondInstanceNorm:
             raise NotImplementedError("dtg_b200: only the reference's default generator configuration "
                                       "(CondInstanceNorm, reflect padding, no dropout) is implemented")
@@ -187,7 +200,7 @@ class CINResnetGenerator(_FusedNet):
                  norm_layer(2 * ngf, nlatent), nn.ReLU(True),
                  nn.Conv2d(2 * ngf, 4 * ngf, kernel_size=3, padding=1, stride=2, bias=True),
                  norm_layer(4 * ngf, nlatent), nn.ReLU(True)]
-        for i in range(3):
+        for i in range(self.n_res):
             model += [CINResnetBlock(x_dim=4 * ngf, z_dim=nlatent, padding_type=padding_type,
                                      norm_layer=norm_layer, use_dropout=use_dropout, use_bias=True)]
         model += [nn.ConvTranspose2d(4 * ngf, 2 * ngf, kernel_size=3, stride=2, padding=1, output_padding=1, bias=True),
@@ -198,7 +211,7 @@ class CINResnetGenerator(_FusedNet):
         self.model = TwoInputSequential(*model)
 
     def _build_exec(self, arena):
-        return NetExec(self, _gen_layers(self.model, True, self.input_nc, self.output_nc, self.ngf),
+        return NetExec(self, _gen_layers(self.model, True, self.input_nc, self.output_nc, self.ngf, self.n_res),
                        self.input_nc, 3, arena, nz=self.nlatent)
 
     def forward(self, input, noise):
@@ -206,12 +219,13 @@ class CINResnetGenerator(_FusedNet):
 
 
 class ResnetGenerator(_FusedNet):
-    """networks.py:203-252."""
+    """networks.py:203-252 (3 res-blocks like the reference unless honor_n_blocks=True, extension N3)."""
 
     def __init__(self, input_nc, output_nc, ngf=64, norm_layer=InstanceNorm2d, use_dropout=False,
-                 n_blocks=9, gpu_ids=[], padding_type='reflect'):
+                 n_blocks=9, gpu_ids=[], padding_type='reflect', honor_n_blocks=False):
         assert (n_blocks >= 0)
         super().__init__()
+        self.n_res = _res_block_count(n_blocks, honor_n_blocks)
         if use_dropout or padding_type != 'reflect':
             raise NotImplementedError("dtg_b200: only reflect padding without dropout is implemented")
         self.gpu_ids = gpu_ids
@@ -221,7 +235,7 @@ class ResnetGenerator(_FusedNet):
                  nn.Conv2d(ngf, 2 * ngf, kernel_size=3, padding=1, stride=1, bias=True), norm_layer(2 * ngf), nn.ReLU(True),
                  nn.Conv2d(2 * ngf, 4 * ngf, kernel_size=3, padding=1, stride=2, bias=True), norm_layer(4 * ngf),
                  nn.ReLU(True)]
-        for i in range(3):
+        for i in range(self.n_res):
             model += [ResnetBlock(4 * ngf, padding_type=padding_type, norm_layer=norm_layer,
                                   use_dropout=use_dropout, use_bias=True)]
         model += [nn.ConvTranspose2d(4 * ngf, 2 * ngf, kernel_size=3, stride=2, padding=1, output_padding=1, bias=True),
@@ -231,7 +245,7 @@ class ResnetGenerator(_FusedNet):
         self.model = nn.Sequential(*model)
 
     def _build_exec(self, arena):
-        return NetExec(self, _gen_layers(self.model, False, self.input_nc, self.output_nc, self.ngf),
+        return NetExec(self, _gen_layers(self.model, False, self.input_nc, self.output_nc, self.ngf, self.n_res),
                        self.input_nc, 3, arena)
 
     def forward(self, input):
@@ -328,31 +342,51 @@ class DiscriminatorLatent(_FusedNet):
 
 
 class LatentEncoder(_FusedNet):
-    """networks.py:438-482; returns (mu, logvar) flattened to [N, -1].  64x64 inputs only, like the
-    reference (four stride-2 convs then a 4x4 valid conv)."""
+    """networks.py:438-482; returns (mu, logvar) flattened to [N, -1].
 
-    def __init__(self, nlatent, input_nc, nef, norm_layer, gpu_ids=[]):
+    The reference's encoder only yields [N, nlatent] codes for 64x64 inputs (four stride-2 convs then a 4x4 valid conv,
+    SURVEY section 0): at 128x128 it returns [N, 25 * nlatent] and AugmentedCycleGAN fails.  img_size = 64 * 2^k is the
+    N3 extension: k further stride-2 stages (conv 8nef -> 8nef, k3 s2 p1, no bias + norm + ReLU) are inserted
+    before the 4x4 valid conv, so the code stays [N, nlatent]; img_size=64 builds exactly the reference's modules and
+    state-dict keys."""
+
+    def __init__(self, nlatent, input_nc, nef, norm_layer, gpu_ids=[], img_size=64):
         super().__init__()
         self.gpu_ids, self.nlatent, self.input_nc, self.nef = gpu_ids, nlatent, input_nc, nef
+        extra, s = 0, int(img_size)
+        while s > 64 and s % 2 == 0:
+            s //= 2
+            extra += 1
+        if s != 64:
+            raise ValueError("dtg_b200: LatentEncoder img_size must be 64 * 2^k, got %r" % (img_size,))
+        self.img_size, self.n_extra = int(img_size), extra
         kw = 3
-        self.conv_modules = nn.Sequential(
+        seq = [
             nn.Conv2d(input_nc, nef, kernel_size=kw, stride=2, padding=1, bias=True), nn.ReLU(True),
             nn.Conv2d(nef, 2 * nef, kernel_size=kw, stride=2, padding=1, bias=False), norm_layer(2 * nef), nn.ReLU(True),
             nn.Conv2d(2 * nef, 4 * nef, kernel_size=kw, stride=2, padding=1, bias=False), norm_layer(4 * nef), nn.ReLU(True),
-            nn.Conv2d(4 * nef, 8 * nef, kernel_size=kw, stride=2, padding=1, bias=False), norm_layer(8 * nef), nn.ReLU(True),
-            nn.Conv2d(8 * nef, 8 * nef, kernel_size=4, stride=1, padding=0, bias=False), norm_layer(8 * nef), nn.ReLU(True))
+            nn.Conv2d(4 * nef, 8 * nef, kernel_size=kw, stride=2, padding=1, bias=False), norm_layer(8 * nef), nn.ReLU(True)]
+        for _ in range(extra):
+            seq += [nn.Conv2d(8 * nef, 8 * nef, kernel_size=kw, stride=2, padding=1, bias=False), norm_layer(8 * nef),
+                    nn.ReLU(True)]
+        seq += [nn.Conv2d(8 * nef, 8 * nef, kernel_size=4, stride=1, padding=0, bias=False), norm_layer(8 * nef), nn.ReLU(True)]
+        self.conv_modules = nn.Sequential(*seq)
         self.enc_mu = nn.Conv2d(8 * nef, nlatent, kernel_size=1, stride=1, padding=0, bias=True)
         self.enc_logvar = nn.Conv2d(8 * nef, nlatent, kernel_size=1, stride=1, padding=0, bias=True)
 
     def _build_exec(self, arena):
         m, nef, r = self.conv_modules, self.nef, L.ACT_RELU
-        ls = [Layer("conv_modules.0", 0, m[0], self.input_nc, nef, 3, 2, 1, act=r),
-              Layer("conv_modules.2", 1, m[2], nef, 2 * nef, 3, 2, 1, norm=_norm_kind(m[3]), act=r, norm_mod=m[3]),
-              Layer("conv_modules.5", 2, m[5], 2 * nef, 4 * nef, 3, 2, 1, norm=_norm_kind(m[6]), act=r, norm_mod=m[6]),
-              Layer("conv_modules.8", 3, m[8], 4 * nef, 8 * nef, 3, 2, 1, norm=_norm_kind(m[9]), act=r, norm_mod=m[9]),
-              Layer("conv_modules.11", 4, m[11], 8 * nef, 8 * nef, 4, 1, 0, norm=_norm_kind(m[12]), act=r, norm_mod=m[12]),
-              Layer("mu", 5, self.enc_mu, 8 * nef, self.nlatent, 1, head=True),
-              Layer("logvar", 5, self.enc_logvar, 8 * nef, self.nlatent, 1, head=True)]
+        ls = [Layer("conv_modules.0", 0, m[0], self.input_nc, nef, 3, 2, 1, act=r)]
+        chans = [nef, 2 * nef, 4 * nef, 8 * nef] + [8 * nef] * self.n_extra
+        for j in range(1, len(chans)):
+            ci = 2 + 3 * (j - 1)
+            ls.append(Layer("conv_modules.%d" % ci, j, m[ci], chans[j - 1], chans[j], 3, 2, 1, norm=_norm_kind(m[ci + 1]),
+                            act=r, norm_mod=m[ci + 1]))
+        ci, j = 2 + 3 * (len(chans) - 1), len(chans)
+        ls += [Layer("conv_modules.%d" % ci, j, m[ci], 8 * nef, 8 * nef, 4, 1, 0, norm=_norm_kind(m[ci + 1]), act=r,
+                     norm_mod=m[ci + 1]),
+               Layer("mu", j + 1, self.enc_mu, 8 * nef, self.nlatent, 1, head=True),
+               Layer("logvar", j + 1, self.enc_logvar, 8 * nef, self.nlatent, 1, head=True)]
         return NetExec(self, ls, self.input_nc, 0, arena)
 
     def forward(self, input):
@@ -362,11 +396,14 @@ class LatentEncoder(_FusedNet):
 
 # ---- factories (networks.py:33-127) ----------------------------------------------------------------
 
-def define_G(input_nc, output_nc, ngf, norm='instance', which_model_netG='resnet', use_dropout=False, gpu_ids=[]):
+def define_G(input_nc, output_nc, ngf, norm='instance', which_model_netG='resnet', use_dropout=False, gpu_ids=[],
+             n_blocks=None):
+    """n_blocks=None: the reference's call (n_blocks=9 passed and ignored -> 3 blocks); an int is honoured (N3)"""
     if len(gpu_ids) > 0:
         assert (torch.cuda.is_available())
     netG = ResnetGenerator(input_nc, output_nc, ngf, norm_layer=get_norm_layer(norm_type=norm),
-                           use_dropout=use_dropout, n_blocks=9, gpu_ids=gpu_ids)
+                           use_dropout=use_dropout, n_blocks=9 if n_blocks is None else n_blocks, gpu_ids=gpu_ids,
+                           honor_n_blocks=n_blocks is not None)
     if len(gpu_ids) > 0:
         netG.cuda()
     netG.apply(weights_init)
@@ -374,11 +411,12 @@ def define_G(input_nc, output_nc, ngf, norm='instance', which_model_netG='resnet
 
 
 def define_stochastic_G(nlatent, input_nc, output_nc, ngf, norm='instance', which_model_netG='resnet',
-                        use_dropout=False, gpu_ids=[]):
+                        use_dropout=False, gpu_ids=[], n_blocks=None):
     if len(gpu_ids) > 0:
         assert (torch.cuda.is_available())
     netG = CINResnetGenerator(nlatent, input_nc, output_nc, ngf, norm_layer=CondInstanceNorm,
-                              use_dropout=use_dropout, n_blocks=9, gpu_ids=gpu_ids)
+                              use_dropout=use_dropout, n_blocks=9 if n_blocks is None else n_blocks, gpu_ids=gpu_ids,
+                              honor_n_blocks=n_blocks is not None)
     if len(gpu_ids) > 0:
         netG.cuda()
     netG.apply(weights_init)
@@ -417,10 +455,11 @@ def define_LAT_D(nlatent, ndf, use_sigmoid=False, gpu_ids=[]):
     return netD
 
 
-def define_E(nlatent, input_nc, nef, norm='batch', gpu_ids=[]):
+def define_E(nlatent, input_nc, nef, norm='batch', gpu_ids=[], img_size=64):
     if len(gpu_ids) > 0:
         assert (torch.cuda.is_available())
-    netE = LatentEncoder(nlatent, input_nc, nef, norm_layer=get_norm_layer(norm_type=norm), gpu_ids=gpu_ids)
+    netE = LatentEncoder(nlatent, input_nc, nef, norm_layer=get_norm_layer(norm_type=norm), gpu_ids=gpu_ids,
+                         img_size=img_size)
     if len(gpu_ids) > 0:
         netE.cuda()
     netE.apply(weights_init)

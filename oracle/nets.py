@@ -26,8 +26,19 @@ def _in(p, pre, x):
     return instance_norm(x, p[pre + ".scale"], p[pre + ".shift"])
 
 
+def _n_blocks(p):
+    """res-blocks present in a generator state dict: 3 for every reference model (networks.py:173, 225 ignore n_blocks);
+    other counts are the N3 extension with model indices 10 .. 9+n and the tail shifted accordingly"""
+    n = 0
+    while "model.%d.conv_block.4.weight" % (10 + n) in p:
+        n += 1
+    return n
+
+
 def cin_resnet_generator(p, x, z, capture=None):
     """networks.py:149-197 (3 CIN res-blocks regardless of n_blocks, networks.py:173)."""
+    nb = _n_blocks(p)
+    t0 = 10 + nb
     def cap(name, t):
         if capture is not None:
             capture[name] = t
@@ -38,23 +49,26 @@ def cin_resnet_generator(p, x, z, capture=None):
     h = cap("model.6", F.relu(_cin(p, "model.5", cap("model.4", h), z)))
     h = F.conv2d(h, p["model.7.weight"], p["model.7.bias"], stride=2, padding=1)
     h = cap("model.9", F.relu(_cin(p, "model.8", cap("model.7", h), z)))
-    for i in (10, 11, 12):  # modules.py:139-188
+    for i in range(10, t0):  # modules.py:139-188
         b = "model.%d.conv_block" % i
         t = F.conv2d(_rpad(h, 1), p[b + ".1.module1.weight"], p[b + ".1.module1.bias"])
         t = F.relu(_cin(p, b + ".1.module2", t, z))
         t = F.conv2d(_rpad(t, 1), p[b + ".4.weight"], p[b + ".4.bias"])
         t = _in(p, b + ".5", t)
         h = cap("model.%d" % i, F.relu(h + t))
-    h = F.conv_transpose2d(h, p["model.13.weight"], p["model.13.bias"], stride=2, padding=1, output_padding=1)
-    h = cap("model.15", F.relu(_cin(p, "model.14", cap("model.13", h), z)))
-    h = F.conv2d(h, p["model.16.weight"], p["model.16.bias"], padding=1)
-    h = cap("model.18", F.relu(_cin(p, "model.17", cap("model.16", h), z)))
-    h = F.conv2d(h, p["model.19.weight"], p["model.19.bias"], padding=3)
-    return torch.tanh(cap("model.19", h))
+    k = lambda j: "model.%d" % (t0 + j)
+    h = F.conv_transpose2d(h, p[k(0) + ".weight"], p[k(0) + ".bias"], stride=2, padding=1, output_padding=1)
+    h = cap(k(2), F.relu(_cin(p, k(1), cap(k(0), h), z)))
+    h = F.conv2d(h, p[k(3) + ".weight"], p[k(3) + ".bias"], padding=1)
+    h = cap(k(5), F.relu(_cin(p, k(4), cap(k(3), h), z)))
+    h = F.conv2d(h, p[k(6) + ".weight"], p[k(6) + ".bias"], padding=3)
+    return torch.tanh(cap(k(6), h))
 
 
 def resnet_generator(p, x, capture=None):
     """networks.py:203-252; res-block = conv-ReLU-conv-IN, relu(x+.) (modules.py:193-235)."""
+    nb = _n_blocks(p)
+    t0 = 10 + nb
     def cap(name, t):
         if capture is not None:
             capture[name] = t
@@ -65,18 +79,19 @@ def resnet_generator(p, x, capture=None):
     h = cap("model.6", F.relu(_in(p, "model.5", cap("model.4", h))))
     h = F.conv2d(h, p["model.7.weight"], p["model.7.bias"], stride=2, padding=1)
     h = cap("model.9", F.relu(_in(p, "model.8", cap("model.7", h))))
-    for i in (10, 11, 12):
+    for i in range(10, t0):
         b = "model.%d.conv_block" % i
         t = F.relu(F.conv2d(_rpad(h, 1), p[b + ".1.weight"], p[b + ".1.bias"]))
         t = F.conv2d(_rpad(t, 1), p[b + ".4.weight"], p[b + ".4.bias"])
         t = _in(p, b + ".5", t)
         h = cap("model.%d" % i, F.relu(h + t))
-    h = F.conv_transpose2d(h, p["model.13.weight"], p["model.13.bias"], stride=2, padding=1, output_padding=1)
-    h = cap("model.15", F.relu(_in(p, "model.14", cap("model.13", h))))
-    h = F.conv2d(h, p["model.16.weight"], p["model.16.bias"], padding=1)
-    h = cap("model.18", F.relu(_in(p, "model.17", cap("model.16", h))))
-    h = F.conv2d(h, p["model.19.weight"], p["model.19.bias"], padding=3)
-    return torch.tanh(cap("model.19", h))
+    k = lambda j: "model.%d" % (t0 + j)
+    h = F.conv_transpose2d(h, p[k(0) + ".weight"], p[k(0) + ".bias"], stride=2, padding=1, output_padding=1)
+    h = cap(k(2), F.relu(_in(p, k(1), cap(k(0), h))))
+    h = F.conv2d(h, p[k(3) + ".weight"], p[k(3) + ".bias"], padding=1)
+    h = cap(k(5), F.relu(_in(p, k(4), cap(k(3), h))))
+    h = F.conv2d(h, p[k(6) + ".weight"], p[k(6) + ".bias"], padding=3)
+    return torch.tanh(cap(k(6), h))
 
 
 def cin_resnet_block(p, x, z):
@@ -137,13 +152,18 @@ def discriminator_latent(p, z):
 
 
 def latent_encoder(p, x):
-    """networks.py:438-482; returns (mu, logvar) flattened to [N, -1]."""
+    """networks.py:438-482; returns (mu, logvar) flattened to [N, -1].
+
+    N3 extension: a state dict with extra stride-2 stages (conv 8nef->8nef k3 s2 p1 no bias + BN + ReLU at
+    conv_modules.11, 14, ... before the 4x4 valid conv) is the encoder for 64 * 2^k inputs; with none it is the reference's."""
     h = F.relu(F.conv2d(x, p["conv_modules.0.weight"], p["conv_modules.0.bias"], stride=2, padding=1))
-    for ci, bi in ((2, 3), (5, 6), (8, 9)):
+    ci = 2
+    while p["conv_modules.%d.weight" % ci].shape[-1] == 3:
         h = F.conv2d(h, p["conv_modules.%d.weight" % ci], None, stride=2, padding=1)
-        h = F.relu(_bn(p, "conv_modules.%d" % bi, h))
-    h = F.conv2d(h, p["conv_modules.11.weight"], None)
-    h = F.relu(_bn(p, "conv_modules.12", h))
+        h = F.relu(_bn(p, "conv_modules.%d" % (ci + 1), h))
+        ci += 3
+    h = F.conv2d(h, p["conv_modules.%d.weight" % ci], None)
+    h = F.relu(_bn(p, "conv_modules.%d" % (ci + 1), h))
     mu = F.conv2d(h, p["enc_mu.weight"], p["enc_mu.bias"])
     lv = F.conv2d(h, p["enc_logvar.weight"], p["enc_logvar.bias"])
     return mu.reshape(mu.shape[0], -1), lv.reshape(lv.shape[0], -1)
@@ -179,8 +199,8 @@ def _bnorm(p, name, c, g, two_d):
     p[name + ".num_batches_tracked"] = torch.zeros((), dtype=torch.long)
 
 
-def init_generator(g, in_nc, out_nc, ngf, nlatent=None):
-    """nlatent=None -> ResnetGenerator keys, else CINResnetGenerator keys."""
+def init_generator(g, in_nc, out_nc, ngf, nlatent=None, n_blocks=3):
+    """nlatent=None -> ResnetGenerator keys, else CINResnetGenerator keys.  n_blocks != 3 is the N3 extension."""
     p = {}
     cin = nlatent is not None
     def norm(name, c):
@@ -188,7 +208,8 @@ def init_generator(g, in_nc, out_nc, ngf, nlatent=None):
     _conv(p, "model.1", ngf, in_nc, 7, g); norm("model.2", ngf)
     _conv(p, "model.4", 2 * ngf, ngf, 3, g); norm("model.5", 2 * ngf)
     _conv(p, "model.7", 4 * ngf, 2 * ngf, 3, g); norm("model.8", 4 * ngf)
-    for i in (10, 11, 12):
+    t0 = 10 + n_blocks
+    for i in range(10, t0):
         b = "model.%d.conv_block" % i
         if cin:
             _conv(p, b + ".1.module1", 4 * ngf, 4 * ngf, 3, g)
@@ -198,11 +219,11 @@ def init_generator(g, in_nc, out_nc, ngf, nlatent=None):
         _conv(p, b + ".4", 4 * ngf, 4 * ngf, 3, g)
         _inorm(p, b + ".5", 4 * ngf, g)
     # ConvTranspose2d weight layout [Cin, Cout, k, k] (networks.py:178-179)
-    p["model.13.weight"] = torch.empty(4 * ngf, 2 * ngf, 3, 3).normal_(0.0, 0.02, generator=g)
-    p["model.13.bias"] = torch.zeros(2 * ngf)
-    norm("model.14", 2 * ngf)
-    _conv(p, "model.16", ngf, 2 * ngf, 3, g); norm("model.17", ngf)
-    _conv(p, "model.19", out_nc, ngf, 7, g)
+    p["model.%d.weight" % t0] = torch.empty(4 * ngf, 2 * ngf, 3, 3).normal_(0.0, 0.02, generator=g)
+    p["model.%d.bias" % t0] = torch.zeros(2 * ngf)
+    norm("model.%d" % (t0 + 1), 2 * ngf)
+    _conv(p, "model.%d" % (t0 + 3), ngf, 2 * ngf, 3, g); norm("model.%d" % (t0 + 4), ngf)
+    _conv(p, "model.%d" % (t0 + 6), out_nc, ngf, 7, g)
     return p
 
 
@@ -229,13 +250,19 @@ def init_discriminator_latent(g, nlatent, ndf):
     return p
 
 
-def init_encoder(g, nlatent, in_nc, nef):
+def init_encoder(g, nlatent, in_nc, nef, img_size=64):
+    """img_size = 64 * 2^k adds k stride-2 stages before the 4x4 valid conv (N3 extension; 64 = the reference)"""
     p = {}
     _conv(p, "conv_modules.0", nef, in_nc, 3, g)
     _conv(p, "conv_modules.2", 2 * nef, nef, 3, g, bias=False); _bnorm(p, "conv_modules.3", 2 * nef, g, True)
     _conv(p, "conv_modules.5", 4 * nef, 2 * nef, 3, g, bias=False); _bnorm(p, "conv_modules.6", 4 * nef, g, True)
     _conv(p, "conv_modules.8", 8 * nef, 4 * nef, 3, g, bias=False); _bnorm(p, "conv_modules.9", 8 * nef, g, True)
-    _conv(p, "conv_modules.11", 8 * nef, 8 * nef, 4, g, bias=False); _bnorm(p, "conv_modules.12", 8 * nef, g, True)
+    ci = 11
+    while img_size > 64:
+        _conv(p, "conv_modules.%d" % ci, 8 * nef, 8 * nef, 3, g, bias=False); _bnorm(p, "conv_modules.%d" % (ci + 1), 8 * nef, g, True)
+        ci += 3
+        img_size //= 2
+    _conv(p, "conv_modules.%d" % ci, 8 * nef, 8 * nef, 4, g, bias=False); _bnorm(p, "conv_modules.%d" % (ci + 1), 8 * nef, g, True)
     _conv(p, "enc_mu", nlatent, 8 * nef, 1, g)
     _conv(p, "enc_logvar", nlatent, 8 * nef, 1, g)
     return p
@@ -245,16 +272,16 @@ NET_NAMES = ("netG_A_B", "netG_B_A", "netE_B", "netD_A", "netD_B", "netD_z_B")
 
 
 def init_model_state(seed=1234, input_nc=3, output_nc=3, ngf=32, nef=32, ndf=64, nlatent=16,
-                     enc_A_B=True, perturb=0.0):
+                     enc_A_B=True, perturb=0.0, n_blocks=3, img_size=64):
     """Parameters of the six networks AugmentedCycleGAN.__init__ builds (model.py:348-376).
 
     perturb > 0 adds N(0, perturb) to every bias / shift so tests exercise non-zero values.
     """
     g = torch.Generator().manual_seed(seed)
     st = {
-        "netG_A_B": init_generator(g, input_nc, output_nc, ngf, nlatent),
-        "netG_B_A": init_generator(g, output_nc, input_nc, ngf, None),
-        "netE_B": init_encoder(g, nlatent, output_nc + (input_nc if enc_A_B else 0), nef),
+        "netG_A_B": init_generator(g, input_nc, output_nc, ngf, nlatent, n_blocks),
+        "netG_B_A": init_generator(g, output_nc, input_nc, ngf, None, n_blocks),
+        "netE_B": init_encoder(g, nlatent, output_nc + (input_nc if enc_A_B else 0), nef, img_size),
         "netD_A": init_discriminator(g, input_nc, 32, edges=True),   # ndf hard-coded, model.py:367
         "netD_B": init_discriminator(g, output_nc, ndf, edges=False),
         "netD_z_B": init_discriminator_latent(g, nlatent, ndf),
@@ -267,7 +294,7 @@ def init_model_state(seed=1234, input_nc=3, output_nc=3, ngf=32, nef=32, ndf=64,
     return st
 
 
-def is_noise_grad(net_name, key):
+def is_noise_grad(net_name, key, n_blocks=3):
     """True for biases whose exact gradient is 0 because a mean-removing norm follows the layer
     (instance / conditional-instance / batch norm): the reference's autograd produces pure fp32
     rounding noise there (|g| ~ 1e-6 of the weight gradient), so parity is checked against a noise
@@ -276,7 +303,7 @@ def is_noise_grad(net_name, key):
         return False
     k = key[:-5]
     if net_name in ("netG_A_B", "netG_B_A"):
-        if k in ("model.1", "model.4", "model.7", "model.13", "model.16"):
+        if k in ("model.1", "model.4", "model.7", "model.%d" % (10 + n_blocks), "model.%d" % (13 + n_blocks)):
             return True
         if k.endswith("conv_block.4") or k.endswith("conv_block.1.module1"):
             return True

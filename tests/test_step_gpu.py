@@ -79,13 +79,15 @@ def _no_tf32():
     yield
 
 
-def _check_step(prec, n, seed_x=4321, **opt_kw):
+def _check_step(prec, n, seed_x=4321, size=64, **opt_kw):
     """one fused train_instance against the fp32 oracle; every reduced-precision bound is GRAD_FACTOR x the error of the
     reference's own path at that precision (cuDNN TF32 / torch.autocast bf16) on the same inputs"""
     engine.set_precision(prec)
     oopt = ostep.default_opt(**opt_kw)
-    state = onets.init_model_state(seed=1234, perturb=0.05, enc_A_B=bool(oopt.enc_A_B))
-    a, b, z = [t.to(DEV) for t in ostep.synthetic_batch(n, seed=seed_x)]
+    nb = opt_kw.get("n_blocks", 3)
+    state = onets.init_model_state(seed=1234, perturb=0.05, enc_A_B=bool(oopt.enc_A_B), n_blocks=nb,
+                                   img_size=opt_kw.get("encoder_grid_size", 64))
+    a, b, z = [t.to(DEV) for t in ostep.synthetic_batch(n, size=size, seed=seed_x)]
     ours = _build(state, **opt_kw)
     losses, visuals, gnorms = ours.train_instance(a, b, z)
     # D-side .grad holds the clipped D-pass gradients; G-side the clipped G-pass gradients
@@ -104,7 +106,7 @@ def _check_step(prec, n, seed_x=4321, **opt_kw):
     worst_low, worst = 0.0, 0.0
     for name in rgrad:
         for k in rgrad[name]:
-            if not onets.is_noise_grad(name, k):
+            if not onets.is_noise_grad(name, k, nb):
                 worst_low = max(worst_low, _rel(lgrad[name][k], rgrad[name][k]))
                 worst = max(worst, _rel(got[name][k], rgrad[name][k]))
     _record("train_instance", prec=prec, n=n, opt=opt_kw, grad_err=worst, ref_lowprec_grad_err=worst_low,
@@ -114,7 +116,7 @@ def _check_step(prec, n, seed_x=4321, **opt_kw):
     bound = GRAD_FACTOR[prec] * worst_low + 2e-3
     for name in rgrad:
         for k, rgk in rgrad[name].items():
-            if onets.is_noise_grad(name, k):
+            if onets.is_noise_grad(name, k, nb):
                 assert float(got[name][k].abs().max()) <= 1e-3 * (1.0 + float(rgk.abs().max())), (name, k)
                 continue
             assert _rel(got[name][k], rgk) < bound, (name, k, _rel(got[name][k], rgk), bound)
@@ -141,6 +143,25 @@ def test_train_instance_without_enc_A_B():
     """opt.enc_A_B = 0 (options.py:69): the encoder sees real_B only, so fake_A gets no gradient through it
     (model.py:409-413, 471-473)"""
     _check_step("tf32", 4, enc_A_B=0)
+
+
+def test_train_instance_128_extended_encoder():
+    """N3 extension: AugmentedCycleGAN at 128x128 (BASELINE config 3's grid) -- opt.encoder_grid_size=128 adds one
+    stride-2 stage to E_B so that the latent code stays [N, nlatent]; the oracle mirrors it (oracle/nets.py:latent_encoder)."""
+    _check_step("tf32", 4, size=128, encoder_grid_size=128)
+
+
+def test_train_instance_honoured_n_blocks():
+    """N3 extension: opt.n_blocks is honoured (range(n_blocks) res-blocks; the reference ignores it, networks.py:173/225)"""
+    _check_step("tf32", 4, n_blocks=5)
+    _check_step("bf16", 4, n_blocks=1)
+
+
+def test_wrong_grid_rejected():
+    m = _build(onets.init_model_state(seed=3))
+    a, b, z = [t.to(DEV) for t in ostep.synthetic_batch(2, size=128, seed=5)]
+    with pytest.raises(ValueError, match="encoder_grid_size"):
+        m.train_instance(a, b, z)
 
 
 def test_train_instance_matches_golden(golden_dir):
