@@ -44,6 +44,10 @@ WORKLOADS = {
     "stoch128": dict(model="stoch", size=128, output_nc=1, kind="climate", batch=40,
                      desc="StochCycleGAN 128x128 Livneh-style climate fields (3 -> 1 channels), batch %d per GPU, bf16, "
                           "one train_instance step (G_A_B, G_B_A, D_A, D_B fwd+bwd, clip, Adam)"),
+    "aug128": dict(model="aug", size=128, output_nc=1, kind="climate", batch=40, enc_grid=128,
+                   desc="Augmented CycleGAN 128x128 Livneh-style climate fields (3 -> 1 channels) with the N3 encoder "
+                        "extension (one extra stride-2 stage; the reference's E_B cannot run above 64x64), batch %d per GPU, "
+                        "bf16, one train_instance step (G_A_B, G_B_A, E_B, D_A, D_B, D_z_B fwd+bwd, clip, Adam)"),
     "stoch256": dict(model="stoch", size=256, output_nc=3, kind="edges2shoes", batch=10,
                      desc="StochCycleGAN 256x256 edges2shoes-shaped (the reference's 3-block generators), batch %d per GPU, "
                           "bf16, one train_instance step (G_A_B, G_B_A, D_A, D_B fwd+bwd, clip, Adam)"),
@@ -54,7 +58,7 @@ def _oracle_for(wl, device="cpu"):
     """(oracle model, batch maker) of a workload: the CPU / cuDNN restatement of the same step"""
     from oracle import nets as onets, step as ostep
     opt = ostep.default_opt(output_nc=wl["output_nc"])
-    state = onets.init_model_state(seed=1234, output_nc=wl["output_nc"])
+    state = onets.init_model_state(seed=1234, output_nc=wl["output_nc"], img_size=wl.get("enc_grid", 64))
     om = (ostep.OracleModel if wl["model"] == "aug" else ostep.OracleStochModel)(opt, state, device=device)
     mk = lambda n, seed=4321: ostep.synthetic_batch(n, size=wl["size"], seed=seed, output_nc=wl["output_nc"], kind=wl["kind"])
     return om, mk
@@ -66,7 +70,7 @@ def _reference_for(wl, device="cpu"):
     port when the sources are not available -> kind "port"."""
     import copy
     from oracle import live_reference as lr, nets as onets, step as ostep
-    if not lr.available():
+    if not lr.available() or wl.get("enc_grid", 64) != 64:      # the reference itself has no encoder above 64x64
         return _oracle_for(wl, device)[0], "port"
     opt = ostep.default_opt(output_nc=wl["output_nc"])
     opt.gpu_ids = [torch.cuda.current_device()] if device != "cpu" else []
@@ -371,7 +375,8 @@ def main():
     K = max(1, args.steps)
     wl = WORKLOADS[args.workload]
     n = args.batch or wl["batch"]
-    opt = argparse.Namespace(**vars(ostep.default_opt(output_nc=wl["output_nc"])), expr_dir="/tmp", niter_decay=25)
+    opt = argparse.Namespace(**vars(ostep.default_opt(output_nc=wl["output_nc"])), expr_dir="/tmp", niter_decay=25,
+                             encoder_grid_size=wl.get("enc_grid", 64))
     torch.manual_seed(1234)
     m = (dmodel.AugmentedCycleGAN if wl["model"] == "aug" else dmodel.StochCycleGAN)(opt, testing=True)
     m.prepare()

@@ -249,6 +249,81 @@ __global__ void __launch_bounds__(256) adam_clip_kernel(float* __restrict__ p, f
 __global__ void step_inc_kernel(int32_t* s) {
   pdl_enter(); *s += 1; }
 
+// ---- evaluate.py:89-124 (variational_ubo): the objective around G_A_B and the RMSprop step on q(z) -------------------
+// Laplace log-likelihood of real_B under (fake_B, logvar_B) (model.py:24-28), summed over everything and divided by n
+// (= mean over samples of the per-sample sums, evaluate.py:93-94, 118), plus the seed gradient of
+// loss = mean_n(-log_prob_n) with respect to the generator's pre-tanh output.
+__global__ void __launch_bounds__(kRedThreads) ubo_laplace_kernel(const float* __restrict__ fake, const float* __restrict__ real,
+                                                                  const float* __restrict__ logvar_b, int n, int c, int h, int w,
+                                                                  float* __restrict__ scalars, int slot_logp, dtg_plane df,
+                                                                  RedWs* ws) {
+  pdl_enter();
+  __shared__ float sm[kRedThreads / 32];
+  const int chw = c * h * w, count = n * chw;
+  const float k = 1.f / static_cast<float>(n);
+  float v[1] = {0.f};
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < count; i += gridDim.x * blockDim.x) {
+    const float fv = fake[i];
+    const float d = real[i] - fv;
+    const float lv = logvar_b[i % chw];
+    const float isd = __expf(-0.5f * lv);
+    v[0] += -0.5f * lv - fabsf(d) * isd - 0.69314718056f;
+    if (df.ptr) {
+      const int x = i % w, y = (i / w) % h, ch = (i / (w * h)) % c, bi = i / chw;
+      // d(-log_prob)/d fake = -sign(real - fake) / sd, through tanh
+      float g = d > 0.f ? -k * isd : (d < 0.f ? k * isd : 0.f);
+      g *= (1.f - fv * fv);
+      const size_t pix = (static_cast<size_t>(bi) * (df.h + 2 * df.halo) + y + df.halo) * (df.w + 2 * df.halo) + x + df.halo;
+      st_plane(df, pix * df.c + ch, g);
+    }
+  }
+  block_sum<1>(v, sm);
+  if (publish_and_check_last(ws, v, 1)) {
+    double a = 0.0;
+    for (unsigned int i = 0; i < gridDim.x; ++i) a += ws->part[i][0];
+    scalars[slot_logp] = static_cast<float>(a / n);
+  }
+}
+
+// One block: KL(q || N(0,I)) of the CURRENT (mu, logvar) (model.py:45-53, mean over samples), the gradients of
+// loss = mean_n(-log_prob_n + kld_n) with respect to (mu, logvar) from dz (through z = clamp(mu + eps * sd, -4, 4),
+// model.py:15-22), torch.optim.RMSprop's update (alpha, eps; no momentum, not centered; evaluate.py:65, 119-121) and the
+// next iterate z' = clamp(mu' + eps_next * sd', -4, 4) (evaluate.py:123).
+__global__ void __launch_bounds__(kRedThreads) ubo_latent_step_kernel(float* __restrict__ mu, float* __restrict__ logvar,
+                                                                      float* __restrict__ sq_mu, float* __restrict__ sq_lv,
+                                                                      const float* __restrict__ eps_cur,
+                                                                      const float* __restrict__ eps_next,
+                                                                      const float* __restrict__ dz, int n, int nz, float lr,
+                                                                      float alpha, float rms_eps, float* __restrict__ z_out,
+                                                                      float* __restrict__ scalars, int slot_kld) {
+  pdl_enter();
+  __shared__ float sm[kRedThreads / 32];
+  const int count = n * nz;
+  const float inv_n = 1.f / static_cast<float>(n);
+  float v[1] = {0.f};
+  for (int i = threadIdx.x; i < count; i += blockDim.x) {
+    float m = mu[i], lv = logvar[i];
+    const float ex = expf(lv), sd = expf(0.5f * lv);
+    v[0] += -0.5f * (lv + 1.f - m * m - ex);
+    const float e = eps_cur[i];
+    const float zr = m + e * sd;
+    const float g = (zr >= -4.f && zr <= 4.f) ? dz[i] : 0.f;
+    const float g_mu = g + m * inv_n;
+    const float g_lv = g * e * 0.5f * sd - 0.5f * (1.f - ex) * inv_n;
+    const float s1 = alpha * sq_mu[i] + (1.f - alpha) * g_mu * g_mu;
+    const float s2 = alpha * sq_lv[i] + (1.f - alpha) * g_lv * g_lv;
+    sq_mu[i] = s1;
+    sq_lv[i] = s2;
+    m -= lr * g_mu / (sqrtf(s1) + rms_eps);
+    lv -= lr * g_lv / (sqrtf(s2) + rms_eps);
+    mu[i] = m;
+    logvar[i] = lv;
+    z_out[i] = fminf(4.f, fmaxf(-4.f, m + eps_next[i] * expf(0.5f * lv)));
+  }
+  block_sum<1>(v, sm);
+  if (threadIdx.x == 0) scalars[slot_kld] = v[0] * inv_n;
+}
+
 }  // namespace dtg
 
 using namespace dtg;
@@ -332,5 +407,30 @@ extern "C" int dtg_adam_clip(float* p, float* g, float* m, float* v, size_t coun
 extern "C" int dtg_step_increment(int32_t* step_dev, void* stream) {
   DTG_REQUIRE(step_dev, "dtg_step_increment: null");
   DTG_CHECK_CUDA(launch_k(step_inc_kernel, 1, 1, 0, static_cast<cudaStream_t>(stream), step_dev));
+  return DTG_OK;
+}
+
+extern "C" int dtg_ubo_laplace(const float* fake, const float* real, const float* logvar_b, int n, int c, int h, int w,
+                               float* scalars, int slot_logp, const dtg_plane* dfake, void* workspace, void* stream) {
+  DTG_REQUIRE(fake && real && logvar_b && scalars && workspace && slot_logp >= 0, "dtg_ubo_laplace: null argument");
+  dtg_plane d;
+  memset(&d, 0, sizeof(d));
+  if (dfake && dfake->ptr) {
+    DTG_REQUIRE(dfake->n == n && dfake->h == h && dfake->w == w && dfake->c >= c, "dtg_ubo_laplace: gradient plane mismatch");
+    d = *dfake;
+  }
+  DTG_CHECK_CUDA(launch_k(ubo_laplace_kernel, red_blocks(static_cast<size_t>(n) * c * h * w), kRedThreads, 0,
+                          static_cast<cudaStream_t>(stream), fake, real, logvar_b, n, c, h, w, scalars, slot_logp, d,
+                          reinterpret_cast<RedWs*>(workspace)));
+  return DTG_OK;
+}
+
+extern "C" int dtg_ubo_latent_step(float* mu, float* logvar, float* sq_mu, float* sq_logvar, const float* eps_cur,
+                                   const float* eps_next, const float* dz, int n, int nz, float lr, float alpha,
+                                   float rms_eps, float* z_out, float* scalars, int slot_kld, void* stream) {
+  DTG_REQUIRE(mu && logvar && sq_mu && sq_logvar && eps_cur && eps_next && dz && z_out && scalars && slot_kld >= 0 && n > 0 && nz > 0,
+              "dtg_ubo_latent_step: null argument");
+  DTG_CHECK_CUDA(launch_k(ubo_latent_step_kernel, 1, kRedThreads, 0, static_cast<cudaStream_t>(stream), mu, logvar, sq_mu, sq_logvar,
+                          eps_cur, eps_next, dz, n, nz, lr, alpha, rms_eps, z_out, scalars, slot_kld));
   return DTG_OK;
 }

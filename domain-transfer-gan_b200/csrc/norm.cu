@@ -545,13 +545,27 @@ extern "C" int dtg_norm_bwd(const dtg_norm_args* a, const dtg_plane* dy, const d
   const bool need_reduce = mode != DTG_NORM_NONE || d_beta != nullptr || sums != nullptr;
   float* sums_buf = sums ? sums : kcoef + static_cast<size_t>(n) * c * 4;   // scratch when the caller wants none
   const int nc = n * c;
+  // phase 3 / 4 split the per-channel parameter-gradient reduction (d_gamma / d_beta from the per-(n,c) sums) off the
+  // data-gradient chain: 4 = everything but that reduction, 3 = that reduction alone (same arguments; the caller issues
+  // it on another stream, after the phase-4 call).  Not for batch norm, whose channel sums feed dx.
+  if (a->phase == 3) {
+    DTG_REQUIRE(mode != DTG_NORM_COND_INSTANCE && mode != DTG_NORM_BATCH && (d_beta || d_gamma),
+                "dtg_norm_bwd: phase 3 needs an instance / activation-only layer with parameter gradients");
+    DTG_CHECK_CUDA(launch_k(norm_bwd_channel_kernel, (c + 31) / 32, 256, 0, stream, sums_buf, n, c, mode, bnsum, d_gamma, d_beta));
+    return DTG_OK;
+  }
+  const bool defer_channel = a->phase == 4;
+  DTG_REQUIRE(!defer_channel || mode != DTG_NORM_BATCH, "dtg_norm_bwd: phase 4 is not available for batch norm");
+  dtg_norm_args a2 = *a;
+  if (defer_channel) a2.phase = 0;
+  a = &a2;
   if (mode == DTG_NORM_INSTANCE || mode == DTG_NORM_COND_INSTANCE || (mode == DTG_NORM_NONE && d_beta != nullptr)) {
     int rc = try_norm_bwd_lean(a, dy, dy2, y, &p_x, stats, gamma, sums_buf, part, dx, d_res, stream);
     if (rc == 1) rc = try_norm_bwd_tma(a, dy, dy2, y, &p_x, stats, gamma, sums_buf, dx, d_res, stream);
     if (rc == 1) rc = try_norm_bwd_fused(a, dy, dy2, y, &p_x, stats, gamma, sums_buf, dx, d_res, stream);
     if (rc < 0) return rc;
     if (rc == 0) {
-      if (mode != DTG_NORM_COND_INSTANCE && (d_beta || d_gamma)) {
+      if (!defer_channel && mode != DTG_NORM_COND_INSTANCE && (d_beta || d_gamma)) {
         DTG_CHECK_CUDA(launch_k(norm_bwd_channel_kernel, (c + 31) / 32, 256, 0, stream, sums_buf, n, c, mode, bnsum, d_gamma, d_beta));
       }
       return DTG_OK;
@@ -564,7 +578,7 @@ extern "C" int dtg_norm_bwd(const dtg_norm_args* a, const dtg_plane* dy, const d
     else
       DTG_CHECK_CUDA(launch_k(norm_bwd_reduce_kernel<float>, grid, kNormThreads, 0, stream, *dy, p_dy2, p_y, p_x, stats, mode, a->act, cg, splits, part));
     DTG_CHECK_CUDA(launch_k(norm_bwd_sums_kernel, (nc + 127) / 128, 128, 0, stream, part, splits, n, c, hw, mode, stats, gamma, sums_buf, kcoef));
-    if (mode != DTG_NORM_COND_INSTANCE && (mode == DTG_NORM_BATCH || d_beta || d_gamma)) {
+    if (!defer_channel && mode != DTG_NORM_COND_INSTANCE && (mode == DTG_NORM_BATCH || d_beta || d_gamma)) {
       DTG_CHECK_CUDA(launch_k(norm_bwd_channel_kernel, (c + 31) / 32, 256, 0, stream, sums_buf, n, c, mode, bnsum, d_gamma, d_beta));
     }
   }

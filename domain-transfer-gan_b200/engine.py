@@ -8,6 +8,8 @@ PyTorch parameter layout, so ``param.grad`` views and the fused clip+Adam kernel
 """
 import os
 
+import functools
+
 import torch
 
 from . import _lib as L
@@ -384,7 +386,7 @@ class NetExec:
                 y = c.acts[i + 1] if ly.act != L.ACT_NONE else None
                 if ly.norm == L.NORM_NONE:
                     ops.norm_bwd(dy, dyr, c.nst[i], mode=L.NORM_NONE, act=ly.act, y=y, dy2=dy2,
-                                 d_beta=A.g(ly.conv.bias) if (want_dw and ly.use_bias) else None)
+                                 d_beta=A.g(ly.conv.bias) if (want_dw and ly.use_bias) else None, defer_channel=True)
                 elif ly.norm == L.NORM_COND_INSTANCE:
                     gam, bet = c.cin[i]
                     ops.norm_bwd(dy, dyr, c.nst[i], mode=ly.norm, act=ly.act, y=y, x=c.yraw[i], gamma=gam, dy2=dy2,
@@ -395,12 +397,13 @@ class NetExec:
                             tg = (A.g(sc.weight), A.g(sc.bias), A.g(sh.weight), A.g(sh.bias))
                         else:
                             tg = self._scratch_cin(sc)
-                        ops.cin_affine_bwd(c.z, sc.weight, sh.weight, gam, bet, c.nst[i].sums, *tg,
-                                           c.dz if want_dz else None)
+                        # parameter / noise gradients of the two 1x1 convs: nothing on the chain reads them
+                        ops.off_chain(functools.partial(ops.cin_affine_bwd, c.z, sc.weight, sh.weight, gam, bet,
+                                                        c.nst[i].sums, *tg, c.dz if want_dz else None))
                 elif ly.norm == L.NORM_INSTANCE:
                     ops.norm_bwd(dy, dyr, c.nst[i], mode=ly.norm, act=ly.act, y=y, x=c.yraw[i], gamma=nm.scale, dy2=dy2,
                                  d_res=d_res, d_gamma=A.g(nm.scale) if want_dw else None,
-                                 d_beta=A.g(nm.shift) if want_dw else None)
+                                 d_beta=A.g(nm.shift) if want_dw else None, defer_channel=True)
                 else:
                     kw = dict(mode=ly.norm, act=ly.act, y=y, x=c.yraw[i], gamma=nm.weight, dy2=dy2, d_res=d_res,
                               d_gamma=A.g(nm.weight) if want_dw else None, d_beta=A.g(nm.bias) if want_dw else None)
@@ -432,8 +435,8 @@ class NetExec:
                 d0, d1 = pending.get(ly.src, (None, None))
                 assert d0 is None or d1 is None, "more than two gradient contributions for one activation"
                 pending[ly.src] = (gin, d1) if d0 is None else (gin, d0)
-        if want_dw:
-            ops.off_chain_join()        # the arena is complete when backward() returns (in stream order)
+        if want_dw or want_dz:
+            ops.off_chain_join()        # the arena (and dz) is complete when backward() returns (in stream order)
         if want_dx == "pair":
             return pending.get(0, (None, None))
         return pending.get(0, (None, None))[0] if want_dx else None

@@ -2,9 +2,11 @@
 ``eval_mse_A`` (/root/reference/augmented_cyclegan/evaluate.py:10-19) and ``variational_ubo`` / ``eval_ubo_B``
 (evaluate.py:21-148) -- per batch, `steps` iterations of: G_A_B forward on (real_A, z_B ~ q), Laplace log-likelihood of
 real_B, KL to the prior, backward to (mu, logvar), RMSprop.  The network passes run through the fused plans
-(model.predict_B stays differentiable with respect to z_B, networks._NetFn); the variational objective around them
-(elementwise on [N,3,64,64] and [N,nlatent]) is plain PyTorch host code here -- it is NOT yet fused into kernels, and the
-generator backward also produces the (unused) weight gradients exactly as the reference's autograd does.
+(model.predict_B stays differentiable with respect to z_B, networks._NetFn).  On the drop-in CUDA models the whole
+iteration is fused (_variational_ubo_fused): dtg_ubo_laplace (objective + seed gradient), the generator backward to z
+only (the reference's autograd also produces weight gradients nobody reads), dtg_ubo_latent_step (KLD, reparametrisation
+backward, RMSprop, next z); the plain PyTorch objective below remains for any other model object (the reference's own, the
+oracle adapter of the tests) and for compute_l1.
 Visualisation (evaluate.py:79-86, 136-147) is left to the caller.  The reference hard-codes 64x64x3 in the
 bits-per-pixel constant and the default logvar_B; here both follow real_B's shape (identical at 64x64x3).
 """
@@ -47,9 +49,69 @@ def eval_mse_A(dataset, model, device="cuda"):
     return np.mean(mse_A)
 
 
-def variational_ubo(model, real_A, real_B, steps, logvar_B=None, compute_l1=False, verbose=False):
+def _fused_model(model, real_A):
+    """True for the drop-in models of dtg_b200.model on a CUDA device: variational_ubo then runs entirely on the C ABI"""
+    try:
+        from .model import _FusedCycleModel
+    except Exception:       # pragma: no cover
+        return False
+    return (isinstance(model, _FusedCycleModel) and real_A.is_cuda and not model.opt.stoch_enc
+            and not getattr(model, "ignore_noise", False))
+
+
+def _variational_ubo_fused(model, real_A, real_B, steps, logvar_B, mu, logvar, verbose, q_out=None):
+    """The loop of evaluate.py:89-124 on the fused kernels: per iteration ONE G_A_B forward, dtg_ubo_laplace (objective
+    + seed gradient), G_A_B backward to z only (no weight gradients: the reference's autograd computes and drops
+    them), dtg_ubo_latent_step (KLD, gradients through the reparametrisation, RMSprop, next z).  Nothing is read back
+    before the loop ends (unless verbose).  The random draws are the reference's, in the reference's order."""
+    from . import ops
+    dev = real_A.device
+    n, _, h, w = real_A.shape
+    nz = model.opt.nlatent
+    ex = model.netG_A_B._exec()
+    c = ex.new_ctx(n, h, w, "ubo")
+    i_out = model._head_idx(ex, "out")
+    ops.pack_nchw(real_A.contiguous(), c.acts[0], 0)
+    mu, logvar = mu.detach().clone().contiguous(), logvar.detach().clone().contiguous()
+    sq_mu, sq_lv = torch.zeros_like(mu), torch.zeros_like(logvar)
+    scal = torch.zeros(4, dtype=torch.float32, device=dev)
+    ws = torch.zeros(1024, dtype=torch.float32, device=dev)
+    lvb = logvar_B.to(dev).float().expand(1, *real_B.shape[1:]).contiguous()
+    real_B = real_B.contiguous()
+    ndim = real_B[0].numel()
+    draw = lambda: mu.new_empty(n, 1, nz).normal_().view(n, nz)          # gauss_reparametrize's eps (model.py:19)
+    eps = draw()
+    z = torch.clamp(mu + eps * logvar.mul(0.5).exp(), -4., 4.)
+    ubo_val = kld_val = bpp = None
+
+    def read():
+        logp, kld = scal[:2].tolist()
+        u = -logp + kld + ndim * math.log(127.5)
+        return u, kld, u / (ndim * math.log(2.))
+
+    for i in range(steps):
+        c.z.copy_(z)
+        fake = ex.forward(c)["out"]
+        ops.ubo_laplace(fake, real_B, lvb, scal, 0, c.dyraw[i_out], ws)
+        ex.backward(c, {"out": True}, want_dx=False, want_dw=False, want_dz=True)
+        eps_next = draw()
+        ops.ubo_latent_step(mu, logvar, sq_mu, sq_lv, eps, eps_next, c.dz, 1e-2, 0.99, 1e-8, z, scal, 1)
+        eps = eps_next
+        if verbose:
+            ubo_val, kld_val, bpp = read()
+            print('[%d] UBO: %.4f, KLD: %.4f, BPP: %.4f' % (i, ubo_val, kld_val, bpp))
+    if steps > 0 and not verbose:
+        ubo_val, kld_val, bpp = read()
+    if q_out is not None:
+        q_out.update(mu=mu, logvar=logvar)
+    return ubo_val, kld_val, bpp
+
+
+def variational_ubo(model, real_A, real_B, steps, logvar_B=None, compute_l1=False, verbose=False, q_out=None):
     """evaluate.py:39-148 without the PNG dumps.  real_A / real_B live on the model's device.  Returns
-    (ubo, kld, bpp) of the LAST evaluated iterate, like the reference."""
+    (ubo, kld, bpp) of the LAST evaluated iterate, like the reference.  On the drop-in models (CUDA) the whole loop
+    runs on the fused kernels (_variational_ubo_fused); any other model object (e.g. the reference's, on CPU) takes
+    the plain PyTorch restatement below."""
     dev = real_A.device
     nz = model.opt.nlatent
     dequant = torch.zeros(*real_B.size()).uniform_(0, 1. / 127.5).to(dev)                 # :43
@@ -63,8 +125,10 @@ def variational_ubo(model, real_A, real_B, steps, logvar_B=None, compute_l1=Fals
         mu = params[0].detach().clone().requires_grad_(True)
         if len(params) == 2:
             logvar = params[1].detach().clone().requires_grad_(True)
-    iterative_opt = torch.optim.RMSprop([mu, logvar], lr=1e-2)                            # :65
     real_B = real_B + dequant                                                             # :67
+    if _fused_model(model, real_A) and not compute_l1:
+        return _variational_ubo_fused(model, real_A, real_B, steps, logvar_B, mu, logvar, verbose, q_out)
+    iterative_opt = torch.optim.RMSprop([mu, logvar], lr=1e-2)                            # :65
     z_B = gauss_reparametrize(mu, logvar)                                                 # :70-71
     fake_B = model.predict_B(real_A, z_B)
     rec_B = None
@@ -97,6 +161,8 @@ def variational_ubo(model, real_A, real_B, steps, logvar_B=None, compute_l1=Fals
         if compute_l1:
             with torch.no_grad():
                 rec_B = fake_B.detach() if model.opt.stoch_enc else model.predict_B(real_A, mu.detach().view(size[0], nz, 1, 1))
+    if q_out is not None:       # the optimised q(z) parameters (the reference drops them; tests compare them)
+        q_out.update(mu=mu.detach(), logvar=logvar.detach())
     return ubo_val, kld_val, bpp
 
 

@@ -389,13 +389,24 @@ def norm_fwd(x, out, st, *, mode, act, gamma=None, beta=None, residual=None, bn_
 
 
 def norm_bwd(dy, dx, st, *, mode, act, y=None, x=None, gamma=None, dy2=None, d_res=None, d_gamma=None, d_beta=None,
-             want_sums=False, phase=0, world_size=1):
-    a = L.NormArgs(mode, act, 1e-5, 0.1, phase, world_size)
+             want_sums=False, phase=0, world_size=1, defer_channel=False):
+    """defer_channel: the per-channel d_gamma / d_beta reduction (a launch-latency-bound kernel that only the optimizer
+    consumes) goes to the lane's companion stream instead of the data-gradient chain (dtg_norm_bwd phases 4 + 3)"""
     P = lambda p: p.s if p is not None else NULL_PLANE
-    rc = L.lib().dtg_norm_bwd(C.byref(a), dy.s, P(dy2), P(y), P(x), _ptr(st.stats), _ptr(gamma),
-                              _ptr(st.sums) if (want_sums or mode == L.NORM_COND_INSTANCE) else C.c_void_p(0),
-                              _ptr(d_gamma), _ptr(d_beta), _ptr(st.ws), dx.s, P(d_res), _stream())
-    L.check(rc, "norm_bwd")
+    sums = _ptr(st.sums) if (want_sums or mode == L.NORM_COND_INSTANCE) else C.c_void_p(0)
+
+    def call(ph):
+        a = L.NormArgs(mode, act, 1e-5, 0.1, ph, world_size)
+        rc = L.lib().dtg_norm_bwd(C.byref(a), dy.s, P(dy2), P(y), P(x), _ptr(st.stats), _ptr(gamma), sums,
+                                  _ptr(d_gamma), _ptr(d_beta), _ptr(st.ws), dx.s, P(d_res), _stream())
+        L.check(rc, "norm_bwd")
+
+    if (defer_channel and phase == 0 and ACTIVE is not None and mode in (L.NORM_NONE, L.NORM_INSTANCE)
+            and (d_gamma is not None or d_beta is not None)):
+        call(4)
+        off_chain(lambda: call(3))
+    else:
+        call(phase)
 
 
 def cin_affine_fwd(z, ws, bs, wb, bb, gamma, beta):
@@ -465,6 +476,22 @@ def loss_fused(segs, scalars, ws):
     arr = (L.LossSeg * len(segs))(*[s for s, _ in segs])
     assert ws.numel() >= 1024 * len(segs)
     L.check(L.lib().dtg_loss_fused(arr, len(segs), _ptr(scalars), _ptr(ws), _stream()), "loss_fused")
+
+
+def ubo_laplace(fake, real, logvar_b, scalars, slot_logp, dfake, ws):
+    """evaluate.py:93-94: mean over samples of the summed Laplace log-likelihood + seed gradient of its negative"""
+    n, c, h, w = fake.shape
+    assert logvar_b.numel() == c * h * w and real.shape == fake.shape
+    L.check(L.lib().dtg_ubo_laplace(_ptr(fake), _ptr(real), _ptr(logvar_b), n, c, h, w, _ptr(scalars), slot_logp,
+                                    dfake.s if dfake is not None else NULL_PLANE, _ptr(ws), _stream()), "ubo_laplace")
+
+
+def ubo_latent_step(mu, logvar, sq_mu, sq_logvar, eps_cur, eps_next, dz, lr, alpha, rms_eps, z_out, scalars, slot_kld):
+    """evaluate.py:101, 118-123: KLD of the current iterate, RMSprop step on (mu, logvar), next z"""
+    n, nz = mu.shape
+    L.check(L.lib().dtg_ubo_latent_step(_ptr(mu), _ptr(logvar), _ptr(sq_mu), _ptr(sq_logvar), _ptr(eps_cur), _ptr(eps_next),
+                                        _ptr(dz), n, nz, float(lr), float(alpha), float(rms_eps), _ptr(z_out), _ptr(scalars),
+                                        slot_kld, _stream()), "ubo_latent_step")
 
 
 def grad_sumsq(g, grad_scale, out, ws):

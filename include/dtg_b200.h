@@ -28,7 +28,7 @@
 extern "C" {
 #endif
 
-#define DTG_VERSION 120 /* 120: dtg_set_option, dtg_loss_fused; two-phase / TMA-staged instance-norm kernels behind dtg_norm_fwd / dtg_norm_bwd */
+#define DTG_VERSION 122 /* 122: dtg_ubo_laplace, dtg_ubo_latent_step; 121: dtg_norm_bwd phases 3 / 4; 120: dtg_set_option, dtg_loss_fused; two-phase / TMA-staged instance-norm kernels behind dtg_norm_fwd / dtg_norm_bwd */
 
 enum { DTG_OK = 0, DTG_ERR_INVALID = -1, DTG_ERR_CUDA = -2, DTG_ERR_UNSUPPORTED = -3 };
 enum { DTG_BF16 = 0, DTG_F32 = 1 };
@@ -189,7 +189,7 @@ typedef struct dtg_norm_args {
   int32_t act;  /* DTG_ACT_NONE / RELU / LRELU */
   float eps;
   float momentum;     /* BATCH */
-  int32_t phase;      /* 0 / 1 / 2 */
+  int32_t phase;      /* 0 / 1 / 2; dtg_norm_bwd also 3 / 4 */
   int32_t world_size; /* BATCH phase 2: statistics were summed over this many ranks */
 } dtg_norm_args;
 size_t dtg_norm_workspace_bytes(const dtg_plane* x);
@@ -208,7 +208,10 @@ int dtg_norm_fwd(const dtg_norm_args* a, const dtg_plane* x, const dtg_plane* re
  *            INSTANCE / BATCH / NONE additionally accumulate d_beta[c] += sum_n, d_gamma[c] += sum_n
  *            (NONE: d_beta only = bias gradient of the preceding conv)
  *   dx     : out plane (halo 0); d_res: optional out plane (halo 0)
- *   phase  : as in forward (BATCH: 1 leaves per-channel sums in `partial` for all-reduce)
+ *   phase  : as in forward (BATCH: 1 leaves per-channel sums in `partial` for all-reduce);
+ *            INSTANCE / NONE only: 4 = everything except the d_gamma / d_beta accumulation, 3 = that accumulation
+ *            alone from the sums the phase-4 call left (same arguments; lets the caller issue the small
+ *            parameter-gradient reduction on another stream, off the data-gradient chain)
  * ------------------------------------------------------------------------------------------- */
 int dtg_norm_bwd(const dtg_norm_args* a, const dtg_plane* dy, const dtg_plane* dy2, const dtg_plane* y,
                  const dtg_plane* x, const float* stats, const float* gamma, float* sums, float* d_gamma,
@@ -287,6 +290,22 @@ typedef struct dtg_loss_seg {
   const dtg_plane* grad;
 } dtg_loss_seg;
 int dtg_loss_fused(const dtg_loss_seg* segs, int nseg, float* scalars, void* workspace, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * evaluate.py:39-148 variational_ubo: the objective around G_A_B and the update of q(z).
+ * dtg_ubo_laplace: scalars[slot_logp] = (1/n) sum over everything of log_prob_laplace(real, fake, logvar_b)
+ *   (model.py:24-28; logvar_b is [1][c][h][w], broadcast over n; evaluate.py:93-94) and, if dfake is given, the seed
+ *   gradient of mean_n(-log_prob_n) with respect to the generator's PRE-tanh output (fake = tanh(.), networks.py:188).
+ * dtg_ubo_latent_step: scalars[slot_kld] = mean_n kld_std_guss(mu, logvar) (model.py:45-53) of the current iterate;
+ *   gradients of mean_n(-log_prob_n + kld_n) w.r.t. (mu, logvar) from dz [n][nz] through z = clamp(mu + eps_cur * sd,
+ *   -4, 4) (model.py:15-22); one torch.optim.RMSprop step (lr, alpha, eps; square averages sq_mu / sq_logvar,
+ *   evaluate.py:65, 119-121) in place; z_out = clamp(mu' + eps_next * sd', -4, 4) (evaluate.py:123).
+ * ------------------------------------------------------------------------------------------- */
+int dtg_ubo_laplace(const float* fake, const float* real, const float* logvar_b, int n, int c, int h, int w,
+                    float* scalars, int slot_logp, const dtg_plane* dfake, void* workspace, void* stream);
+int dtg_ubo_latent_step(float* mu, float* logvar, float* sq_mu, float* sq_logvar, const float* eps_cur,
+                        const float* eps_next, const float* dz, int n, int nz, float lr, float alpha, float rms_eps,
+                        float* z_out, float* scalars, int slot_kld, void* stream);
 
 /* ---------------------------------------------------------------------------------------------
  * clip_grad_norm + Adam over one flat fp32 arena (model.py:447-452,510-515; torch.optim.Adam,

@@ -6,6 +6,7 @@ import pytest
 import torch
 
 import dtg  # noqa: F401
+from dtg_b200 import _lib
 from dtg_b200 import engine, model as dmodel, trainer
 from oracle import nets as onets, step as ostep
 
@@ -120,9 +121,33 @@ def test_variational_ubo_on_the_fused_model_matches_oracle():
     torch.manual_seed(3)
     r = ev.variational_ubo(Adapter(), a, b, 3)
     torch.manual_seed(3)
-    o = ev.variational_ubo(ours, a, b, 3)
+    n0 = _lib.lib().dtg_launch_count()
+    o = ev.variational_ubo(ours, a, b, 3)            # the fused loop: dtg_ubo_laplace / dtg_ubo_latent_step
+    assert _lib.lib().dtg_launch_count() - n0 > 3 * 40
     for x, y, name in zip(o, r, ("ubo", "kld", "bpp")):
         assert abs(x - y) <= 5e-3 * abs(y) + 1e-3, (name, x, y)
+    # longer run: RMSprop state, clamp mask and the reparametrisation backward keep tracking the PyTorch restatement
+    torch.manual_seed(4)
+    r = ev.variational_ubo(Adapter(), a, b, 12)
+    torch.manual_seed(4)
+    o = ev.variational_ubo(ours, a, b, 12)
+    for x, y, name in zip(o, r, ("ubo", "kld", "bpp")):
+        assert abs(x - y) <= 1e-2 * abs(y) + 1e-3, (name, x, y)
+    # the generic path (PyTorch objective around the differentiable predict_B) still works on the fused model.  RMSprop's
+    # first steps are sign-like (g / sqrt(0.01 g^2)): a handful of the 64 latent coordinates whose gradient is near zero
+    # flip by 2 * 0.1 under TF32 rounding of dz in ANY pair of implementations (fused / generic / cuDNN oracle:
+    # tools/ubo_debug.py), so the q(z) parameters are compared in the mean and the objective at 1e-2
+    qg, qf = {}, {}
+    torch.manual_seed(3)
+    g = ev.variational_ubo(ours, a, b, 3, compute_l1=True, q_out=qg)
+    torch.manual_seed(3)
+    o = ev.variational_ubo(ours, a, b, 3, q_out=qf)
+    for x, y, name in zip(o, g, ("ubo", "kld", "bpp")):
+        assert abs(x - y) <= 1e-2 * abs(y) + 1e-3, (name, x, y)
+    for k in ("mu", "logvar"):
+        assert qf[k].shape == qg[k].shape == (4, 16)
+        assert float((qf[k] - qg[k]).abs().mean()) < 0.15, k
+        assert float((qf[k] - qg[k]).abs().median()) < 0.05, k
     data = [{'A': a.cpu(), 'B': b.cpu()}]
     with torch.no_grad():
         ref_mse = float(torch.nn.functional.mse_loss(om.G_B_A(b), a))
