@@ -86,6 +86,7 @@ _SIGS = {
     "dtg_ubo_laplace": (C.c_int, [_P, _P, _P, C.c_int, C.c_int, C.c_int, C.c_int, _P, C.c_int, C.POINTER(Plane), _P, _P]),
     "dtg_ubo_latent_step": (C.c_int, [_P, _P, _P, _P, _P, _P, _P, C.c_int, C.c_int, C.c_float, C.c_float, C.c_float, _P, _P,
                                       C.c_int, _P]),
+    "dtg_preprocess_fields": (C.c_int, [_P, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, _P, _P, _P]),
     "dtg_grad_sumsq": (C.c_int, [_P, C.c_size_t, C.c_float, _P, _P, _P]),
     "dtg_adam_clip": (C.c_int, [_P, _P, _P, _P, C.c_size_t, _P, _P, _P, C.c_float, _P]),
     "dtg_step_increment": (C.c_int, [_P, _P]),

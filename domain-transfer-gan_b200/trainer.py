@@ -104,38 +104,96 @@ def _py2_shuffle(x, rng):
         x[i], x[j] = x[j], x[i]
 
 
-def preprocess_fields(arr, grid_size=None):
+def _resize_fields_host(arr, gh, gw):
+    """skimage.transform.resize as dataloader.py:30 calls it, vectorised numpy on [b, h, w, c] float64: the reference is
+    Python 2, whose last scikit-image line (0.14) defaults to bilinear interpolation at input = scale * (o + 0.5) - 0.5,
+    mode 'constant' (cval 0: samples outside the image contribute 0), no anti-aliasing.  skimage's clip to the image's
+    range is a no-op on fields that have just been scaled to [-1, 1] (0 is inside the range) and is left out."""
+    b, h, w, c = arr.shape
+    arr = arr.astype(np.float64)
+
+    def taps(n_in, n_out):
+        x = (float(n_in) / n_out) * (np.arange(n_out) + 0.5) - 0.5
+        i0, i1 = np.floor(x).astype(np.int64), np.ceil(x).astype(np.int64)
+        return i0, i1, x - i0
+
+    def gather(a, idx, axis, n_in):
+        ok = (idx >= 0) & (idx < n_in)
+        g = np.take(a, np.clip(idx, 0, n_in - 1), axis=axis)
+        shape = [1] * a.ndim
+        shape[axis] = len(idx)
+        return g * ok.reshape(shape)
+
+    r0, r1, dr = taps(h, gh)
+    q0, q1, dq = taps(w, gw)
+    dq = dq.reshape(1, 1, gw, 1)
+    dr = dr.reshape(1, gh, 1, 1)
+    rows0, rows1 = gather(arr, r0, 1, h), gather(arr, r1, 1, h)
+    top = (1 - dq) * gather(rows0, q0, 2, w) + dq * gather(rows0, q1, 2, w)
+    bot = (1 - dq) * gather(rows1, q0, 2, w) + dq * gather(rows1, q1, 2, w)
+    return (1 - dr) * top + dr * bot
+
+
+def preprocess_fields(arr, grid_size=None, device=None):
     """dataloader.py:17-34 for one array [b, h, w(, c)]: first three channels, NaN -> 0, per-sample / per-channel
-    min-max scaling to [-1, 1] (constant fields -> 0), optional resize to grid_size x grid_size, NHWC -> NCHW float32.
-    The reference resizes with skimage.transform.resize (not available here, and its defaults changed between
-    versions); this uses bilinear interpolation with anti-aliasing when shrinking -- the one documented deviation."""
+    min-max scaling to [-1, 1] (constant fields -> 0), optional resize to grid_size x grid_size (skimage.transform.resize
+    with the defaults of its Python-2 releases, see _resize_fields_host / dtg_preprocess_fields), NHWC -> NCHW float32.
+
+    device=None: numpy on the host, like the reference.  device="cuda" (or a torch device): the stack is copied to the GPU
+    once and the whole pipeline is ONE C-ABI call (dtg_preprocess_fields, csrc/fields.cu); returns a CUDA tensor."""
     arr = np.asarray(arr)[..., :3]
-    arr = np.nan_to_num(arr)
     if arr.ndim == 3:
-        arr = np.expand_dims(arr, axis=2)
+        arr = np.expand_dims(arr, axis=2)        # the reference's quirk: [b, h, w] is read as [b, h, 1, w] (:20-21)
+    if device is not None:
+        return _preprocess_fields_device(arr, grid_size, device)
+    arr = np.nan_to_num(arr)
     lo = arr.min((1, 2))[:, np.newaxis, np.newaxis]
     hi = arr.max((1, 2))[:, np.newaxis, np.newaxis]
-    with np.errstate(divide="ignore", invalid="ignore"):
+    with np.errstate(divide="ignore", invalid="ignore", over="ignore"):
         arr = -1 + 2 * (arr - lo) / (hi - lo)
     arr = np.nan_to_num(arr, nan=0.0, posinf=0.0, neginf=0.0)
     if grid_size is not None and (arr.shape[1] != grid_size or arr.shape[2] != grid_size):
-        t = torch.from_numpy(np.ascontiguousarray(arr.transpose(0, 3, 1, 2))).double()
-        shrink = grid_size < min(arr.shape[1], arr.shape[2])
-        t = torch.nn.functional.interpolate(t, size=(grid_size, grid_size), mode="bilinear", align_corners=False,
-                                            antialias=bool(shrink))
-        return t.float().numpy()
+        arr = _resize_fields_host(arr, grid_size, grid_size)
     return np.ascontiguousarray(arr.transpose(0, 3, 1, 2)).astype('float32')
 
 
-def load_numpy_data(root, shuffle=True, grid_size=None):
+def _preprocess_fields_device(arr, grid_size, device, chunk=4096):
+    from . import _lib
+    import ctypes
+    dev = torch.device("cuda", torch.cuda.current_device()) if str(device) == "cuda" else torch.device(device)
+    if arr.dtype not in (np.float32, np.float64):
+        arr = arr.astype(np.float64)
+    b, h, w, c = arr.shape
+    gh = gw = int(grid_size) if grid_size is not None else None
+    gh, gw = (h, w) if gh is None else (gh, gw)
+    out = torch.empty(b, c, gh, gw, dtype=torch.float32, device=dev)
+    f64 = arr.dtype == np.float64
+    with torch.cuda.device(dev):
+        stream = torch.cuda.current_stream().cuda_stream
+        for s0 in range(0, b, chunk):       # bounded staging: a chunk of the stack in HBM at a time
+            src = torch.from_numpy(np.ascontiguousarray(arr[s0:s0 + chunk])).to(dev)
+            nb = src.shape[0]
+            lohi = torch.empty(nb * c * 2, dtype=src.dtype, device=dev)
+            _lib.check(_lib.lib().dtg_preprocess_fields(ctypes.c_void_p(src.data_ptr()), 1 if f64 else 0, nb, h, w, c, c, gh, gw,
+                                                        ctypes.c_void_p(out[s0:s0 + nb].data_ptr()),
+                                                        ctypes.c_void_p(lohi.data_ptr()), ctypes.c_void_p(stream)),
+                       "preprocess_fields")
+            torch.cuda.current_stream().synchronize()      # src / lohi die with this iteration
+    return out
+
+
+def load_numpy_data(root, shuffle=True, grid_size=None, device=None):
     """dataloader.py:13-59: {train,test}{A,B}.npz (key 'data') -> (trainA, trainB, devA, devB, testA, testB); the first
     DEV_SIZE shuffled training samples become the dev split.  Note the reference quirk kept here: a 3-D array
-    [b, h, w] gets its channel axis inserted at position 2 (dataloader.py:20-21), i.e. it is read as [b, h, 1, w]."""
+    [b, h, w] gets its channel axis inserted at position 2 (dataloader.py:20-21), i.e. it is read as [b, h, 1, w].
+    device: preprocess on that GPU (dtg_preprocess_fields); the arrays still come back as host numpy, which is what the
+    iterators of dataloader.py:112-155 index."""
     import os
     import random
 
     def _load(fname):
-        return preprocess_fields(np.load(os.path.join(root, fname))['data'], grid_size)
+        out = preprocess_fields(np.load(os.path.join(root, fname))['data'], grid_size, device)
+        return out.cpu().numpy() if device is not None else out
 
     trainA, trainB = _load("trainA.npz"), _load("trainB.npz")
     testA, testB = _load("testA.npz"), _load("testB.npz")

@@ -28,7 +28,7 @@
 extern "C" {
 #endif
 
-#define DTG_VERSION 122 /* 122: dtg_ubo_laplace, dtg_ubo_latent_step; 121: dtg_norm_bwd phases 3 / 4; 120: dtg_set_option, dtg_loss_fused; two-phase / TMA-staged instance-norm kernels behind dtg_norm_fwd / dtg_norm_bwd */
+#define DTG_VERSION 123 /* 123: dtg_preprocess_fields; 122: dtg_ubo_laplace, dtg_ubo_latent_step; 121: dtg_norm_bwd phases 3 / 4; 120: dtg_set_option, dtg_loss_fused; two-phase / TMA-staged instance-norm kernels behind dtg_norm_fwd / dtg_norm_bwd */
 
 enum { DTG_OK = 0, DTG_ERR_INVALID = -1, DTG_ERR_CUDA = -2, DTG_ERR_UNSUPPORTED = -3 };
 enum { DTG_BF16 = 0, DTG_F32 = 1 };
@@ -225,6 +225,17 @@ int dtg_cin_affine_fwd(const float* z, const float* ws, const float* bs, const f
 int dtg_cin_affine_bwd(const float* z, const float* ws, const float* wb, const float* gamma, const float* beta,
                        const float* sums, int n, int c, int nz, float* d_ws, float* d_bs, float* d_wb,
                        float* d_bb, float* d_z, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * .npz field preprocessing of the loader (dataloader.py:17-34) for one stack src [b][h][w][cin]
+ * (float32, or float64 if is_f64) on the device: channels [0, c), NaN -> 0 / +-inf -> +-max (np.nan_to_num), per
+ * (sample, channel) min-max scaling to [-1, 1] in the array's dtype (constant fields -> 0), resize to gh x gw when
+ * that differs from h x w -- skimage.transform.resize as its Python-2 releases (<= 0.14) default: bilinear, input
+ * coordinate = scale * (o + 0.5) - 0.5, mode 'constant' (samples outside the image are 0), no anti-aliasing, double
+ * arithmetic -- and NHWC -> NCHW float32 into dst [b][c][gh][gw].  lohi: scratch of b * c * 2 elements of src's dtype.
+ * ------------------------------------------------------------------------------------------- */
+int dtg_preprocess_fields(const void* src, int is_f64, int b, int h, int w, int cin, int c, int gh, int gw, float* dst,
+                          void* lohi, void* stream);
 
 /* ---------------------------------------------------------------------------------------------
  * Layout conversion at network entry/exit (the reference tensors are fp32 NCHW, dataloader.py:33):

@@ -227,3 +227,45 @@ def test_parameter_order_matches_reference():
         b = [(n, tuple(p.shape)) for n, p in net.named_parameters()]
         assert a == b, k
         assert list(getattr(ref, k).state_dict().keys()) == list(net.state_dict().keys()), k
+
+
+def test_skimage014_resize_known_answers():
+    """oracle/fields.py:skimage014_resize against values computed by hand from the algorithm (bilinear, input coordinate
+    = scale * (o + 0.5) - 0.5, out-of-image samples = cval 0, clip to the image range) -- the resize has no golden
+    vectors (scikit-image is absent from the reference tree and from this image): PARITY UNPINNED, see the module header"""
+    import numpy as np
+    from oracle import fields as ofields
+    x = np.array([[-1.5, -0.5], [0.5, 1.5]])[:, :, None]
+    up = ofields.skimage014_resize(x, (4, 4))[:, :, 0]
+    # corner: coordinate (-0.25, -0.25): only pixel (0,0) is inside -> 0.75 * 0.75 * -1.5
+    assert abs(up[0, 0] - (-0.84375)) < 1e-12
+    # (0, 1): row -0.25 (weight 0.75 on row 0), column 0.25 -> 0.75 * (0.75 * -1.5 + 0.25 * -0.5)
+    assert abs(up[0, 1] - (-0.9375)) < 1e-12
+    # interior (1, 1): coordinate (0.25, 0.25): 0.75*0.75*-1.5 + 0.75*0.25*-0.5 + 0.25*0.75*0.5 + 0.25*0.25*1.5
+    assert abs(up[1, 1] - (-0.75)) < 1e-12
+    # point symmetry of the data survives
+    assert np.allclose(up, -up[::-1, ::-1])
+    # 2x shrink of a 4x4 ramp: coordinate 2o + 0.5 -> plain 2x2 box means, no border effect
+    r = np.arange(16, dtype=np.float64).reshape(4, 4, 1)
+    dn = ofields.skimage014_resize(r, (2, 2))[:, :, 0]
+    assert np.allclose(dn, [[2.5, 4.5], [10.5, 12.5]])
+    # same size: identity
+    assert np.array_equal(ofields.skimage014_resize(r, (4, 4)), r)
+    # clip: an all-positive image keeps exact cval outputs but clamps the darkened border up to the image minimum
+    p = ofields.skimage014_resize(np.full((2, 2, 1), 3.0), (4, 4))[:, :, 0]
+    assert np.all(p == 3.0)
+
+
+def test_oracle_preprocess_fields_scaling():
+    """dataloader.py:17-25 arithmetic of the oracle against first principles"""
+    import numpy as np
+    from oracle import fields as ofields
+    g = np.random.RandomState(0)
+    arr = g.rand(3, 5, 6, 4)
+    arr[0, 0, 0, 0] = np.nan
+    arr[1, :, :, 2] = 2.0
+    out = ofields.preprocess_fields(arr)
+    assert out.shape == (3, 3, 5, 6) and out.dtype == np.float32
+    f = np.nan_to_num(arr[0, :, :, 0])
+    assert np.allclose(out[0, 0], -1 + 2 * (f - f.min()) / (f.max() - f.min()), atol=1e-6)
+    assert np.all(out[1, 2] == 0) and out.min() >= -1 and out.max() <= 1

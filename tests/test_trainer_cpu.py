@@ -190,6 +190,26 @@ def test_preprocess_fields_follows_the_loader_arithmetic():
     assert np.array_equal(same, trainer.preprocess_fields(arr[:, :6, :6]))
 
 
+def test_preprocess_fields_host_matches_oracle():
+    """host numpy path (vectorised) against the oracle's loop restatement of dataloader.py:17-34 + skimage<=0.14 resize
+    (oracle/fields.py): shrink, enlarge (border samples mix with cval = 0), non-square input, float32 and float64"""
+    from oracle import fields as ofields
+    g = np.random.RandomState(3)
+    arr = g.randn(4, 10, 7, 5) * 2 - 1
+    arr[1, 2:4, 1:3, 2] = np.nan
+    arr[3, :, :, 0] = -7.5
+    for dt in (np.float64, np.float32):
+        for gs in (None, 5, 16, 7):
+            a = trainer.preprocess_fields(arr.astype(dt), gs)
+            b = ofields.preprocess_fields(arr.astype(dt), gs)
+            assert a.shape == b.shape and a.dtype == np.float32
+            assert np.array_equal(a, b), (dt, gs, np.abs(a - b).max())
+    # 3-D input [b, h, w]: the reference first keeps [..., :3] (the first three COLUMNS here) and then inserts the channel
+    # axis at position 2 (dataloader.py:17, 20-21), so it is read as [b, h, 1, 3] -> NCHW [b, 3, h, 1]
+    a3 = trainer.preprocess_fields(arr[..., 0])
+    assert a3.shape == (4, 3, 10, 1) and np.array_equal(a3, ofields.preprocess_fields(arr[..., 0]))
+
+
 def test_load_numpy_data_split_and_python2_shuffle(tmp_path):
     n = 230
     base = np.arange(n, dtype=np.float64)[:, None, None, None] + np.linspace(0, 1, 4 * 4 * 3).reshape(1, 4, 4, 3)

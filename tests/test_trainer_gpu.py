@@ -177,3 +177,25 @@ def test_deferred_report_equals_immediate_report():
     for (l1, _, g1), h in zip(now, handles):
         l2, g2 = h.get()
         assert dict(l1) == dict(l2) and dict(g1) == dict(g2)
+
+
+@pytest.mark.parametrize("dt", [np.float32, np.float64])
+def test_preprocess_fields_on_the_device_matches_oracle(dt):
+    """dtg_preprocess_fields (csrc/fields.cu) against the oracle's loop restatement of dataloader.py:17-34 with the
+    skimage<=0.14 resize: NaN cells, a constant channel, a dropped 4th channel, shrink / enlarge / identity, non-square"""
+    from oracle import fields as ofields
+    g = np.random.RandomState(5)
+    arr = (g.randn(6, 12, 9, 4) * 3 + 1).astype(dt)
+    arr[0, 3:6, 2:5, 1] = np.nan
+    arr[2, :, :, 0] = 1.25
+    arr[4, 0, 0, 2] = np.inf
+    for gs in (None, 6, 20, 9):
+        got = trainer.preprocess_fields(arr, gs, device="cuda")
+        assert got.is_cuda and got.dtype == torch.float32
+        exp = ofields.preprocess_fields(arr, gs)
+        assert tuple(got.shape) == exp.shape
+        err = np.abs(got.cpu().numpy() - exp).max()
+        assert err <= 2e-7, (gs, err)         # float32 outputs of the same double interpolation: equal up to contraction
+    # host and device loaders agree end to end
+    small = trainer.preprocess_fields(arr, 8)
+    assert np.abs(trainer.preprocess_fields(arr, 8, device="cuda").cpu().numpy() - small).max() <= 2e-7
