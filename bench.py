@@ -495,6 +495,8 @@ def main():
     # batch-norm collectives); rank 0 reports its own records.
     kp = None
     try:
+        if os.environ.get("DTG_BENCH_NO_KERNEL_PROFILE"):      # under ncu (launch lists): CUPTI belongs to the outer profiler
+            raise RuntimeError("DTG_BENCH_NO_KERNEL_PROFILE is set")
         kp = kernel_profile(m, dev, _lib, ops)
     except Exception as e:      # CUPTI unavailable etc.: the line still carries value / e2e
         sys.stderr.write("bench: kernel profile unavailable (%s)\n" % str(e).splitlines()[0][:200])

@@ -62,6 +62,10 @@ struct IgemmParams {
 int try_launch_pconv(const IgemmParams& p, const dtg_plane* in, const void* w, int w_rows, int w_cols, int taps_total,
                      int fold_w, cudaStream_t stream);
 
+// Filter-column-in-GEMM-N tail (conv_tail7.cu, dtg_conv_args.fold_w == 2): DTG_OK after launching, 1 if not eligible.
+int try_launch_tail7(const dtg_conv_args* a, const dtg_plane* in, const void* w, int w_rows, int w_cols, const float* bias,
+                     float* out_nchw, cudaStream_t stream);
+
 // ---- TMA-store epilogue ------------------------------------------------------------------------------------
 __device__ __forceinline__ void tma_store_4d(const CUtensorMap* m, const void* smem_src, int c0, int c1, int c2, int c3) {
   asm volatile("cp.async.bulk.tensor.4d.global.shared::cta.bulk_group [%0, {%2, %3, %4, %5}], [%1];"

@@ -302,6 +302,13 @@ extern "C" int dtg_conv(const dtg_conv_args* a, const dtg_plane* in, const void*
       return DTG_OK;
     }
   }
+  if (a->fold_w == 2) {
+    // filter column in GEMM-N (conv_tail7.cu): the weights are packed for that kernel only
+    const int rc = try_launch_tail7(a, in, w, w_rows, w_cols, bias, out_nchw, static_cast<cudaStream_t>(stream));
+    DTG_REQUIRE(rc != 1, "dtg_conv fold_w=2: geometry not eligible (stride-1 odd-kernel 'same' head, cout <= 4, kw * cout <= 28, "
+                         "input halo 0, 32/64/128 bytes per pixel, width a divisor of 128, dense fp32 NCHW output)");
+    return rc;
+  }
   DTG_REQUIRE(a->stride == 1 || a->stride == 2, "dtg_conv: stride %d unsupported", a->stride);
   DTG_REQUIRE(a->kh * a->kw <= kMaxTaps && a->kh >= 1 && a->kw >= 1, "dtg_conv: kernel %dx%d unsupported", a->kh, a->kw);
   DTG_REQUIRE(w_rows % 16 == 0 && w_rows >= 16 && w_rows <= 256, "dtg_conv: packed rows %d must be 16..256, multiple of 16", w_rows);

@@ -43,6 +43,11 @@ __global__ void pack_weights_kernel(const dtg_pack_item* items) {
       const int kh = 2 * (t / 3) + (sub >> 1) - 1, kw = 2 * (t % 3) + (sub & 1) - 1;
       if (r < it.rows && b < it.cols && sub < 4 && kh >= 0 && kh < K && kw >= 0 && kw < K)
         v = it.src[((static_cast<size_t>(r) * it.srs + static_cast<size_t>(b) * it.scs) * K + kh) * K + kw];
+    } else if (it.fold_kw > 0 && it.fold_flip == 2) {
+      // filter column folded into the ROWS (GEMM-N of conv_tail7.cu): row = kw * rows + r0, taps = KH
+      const int j = r / it.rows, r0 = r % it.rows;
+      if (j < it.fold_kw && c < it.cols)
+        v = it.src[((static_cast<size_t>(r0) * it.srs + static_cast<size_t>(c) * it.scs) * it.taps + t) * it.fold_kw + j];
     } else if (it.fold_kw > 0) {
       const int j = c / it.fold_fc, b = c % it.fold_fc;
       if (r < it.rows && j < it.fold_kw && b < it.cols) {

@@ -21,6 +21,7 @@ S2D = os.environ.get("DTG_NO_S2D") is None      # space-to-depth execution of th
 # tensor-core path (fwd 52 vs 44 us, dgrad 49 vs 55 us, wgrad 68 vs 59 us at batch 160; step time unchanged), so the
 # tensor-core path stays the default and this is opt-in
 HEAD1 = os.environ.get("DTG_HEAD1") is not None
+TAIL_KWN = os.environ.get("DTG_NO_TAIL_KWN") is None      # generators' 7x7 tail forward with (kw, cout) in GEMM-N (conv_tail7.cu)
 
 
 def set_precision(name):
@@ -155,6 +156,7 @@ class Layer:
         # fold_in : the INPUT is a 16-byte-per-pixel plane  -> forward conv and wgrad read it kw-folded
         # fold_out: the OUTPUT gradient is (head with <= fc channels) -> dgrad and wgrad read dy kw-folded
         self.fold_in = self.fold_out = False
+        self.tail_kwn, self.w_f_kwn = False, None
         # space-to-depth execution of a stride-2 first layer with a <= 64-byte input pixel (decided in
         # NetExec.prepare): the input plane is stored as 2x2 pixel blocks, forward conv and wgrad run as stride-1 3x3
         self.s2d = False
@@ -213,6 +215,12 @@ class NetExec:
                 ly.fold_in = foldable and ly.src == 0 and ly.cin <= fc and self.in_channels <= fc and self.in_halo >= ly.pad
                 src_halo = self.in_halo if ly.src == 0 else self.layers[ly.src - 1].out_halo
                 ly.fold_out = foldable and ly.head and ly.cout <= fc and not ly.fold_in and src_halo == 0
+                # 7x7 'same' head with <= 4 output channels on a halo-free 32/64/128-byte-per-pixel plane: forward with the
+                # filter column in GEMM-N (conv_tail7.cu) wherever the image width divides 128 (decided per context)
+                rowb = ops.cpad(ly.cin, dtype) * (2 if dtype == torch.bfloat16 else 4)
+                ly.tail_kwn = (TAIL_KWN and foldable and ly.head and ly.cout <= 4 and ly.k * ly.cout <= 28 and src_halo == 0
+                               and ly.src > 0 and rowb in (32, 64, 128) and ops.cpad(ly.cin, dtype) == ly.cin)
+                ly.w_f_kwn = ops.add_packed(self.pack, w4, dtype, "fwd_kwn") if ly.tail_kwn else None
                 ly.head1 = (HEAD1 and ly.head and ly.cout == 1 and not ly.transposed and ly.stride == 1 and w.dim() == 4 and
                             ly.k * ly.k <= 16 and ly.act == L.ACT_NONE and src_halo == 0 and ly.src > 0 and
                             ly.cin % 8 == 0 and ly.cin <= 512)
@@ -323,6 +331,9 @@ class NetExec:
                 ops.head1_fwd(a_in, ly.conv.weight, bias, c.heads[ly.name], ly.pad)
                 continue
             if ly.head:
+                if ly.tail_kwn and ops.tail_kwn_eligible(a_in.c, ly.k, ly.cout, iw, a_in.dtype):
+                    kw.update(fold_w=2)
+                    w_f = ly.w_f_kwn
                 ops.conv(a_in, w_f, bias, None, act=ly.act, out_nchw=c.heads[ly.name], **kw)
                 continue
             out = c.acts[i + 1]

@@ -240,14 +240,18 @@ class PackTable:
         128 bytes per row (8 filter-column slots of fc channels)."""
         rows_p = max(16, (rows + 15) // 16 * 16)
         q = 8 if dtype == torch.bfloat16 else 4
-        cols_p = 8 * q if fold_kw else (cols + q - 1) // q * q
-        assert not fold_kw or (cols <= q and fold_kw <= 8)
+        if fold_kw and int(fold_flip) == 2:     # filter column in the ROWS (dtg_conv fold_w = 2): [KH][32][cols_p]
+            assert fold_kw * rows <= 28
+            rows_p, cols_p = 32, (cols + q - 1) // q * q
+        else:
+            cols_p = 8 * q if fold_kw else (cols + q - 1) // q * q
+            assert not fold_kw or (cols <= q and fold_kw <= 8)
         if s2d_k:       # dtg_pack_item.s2d_k: 9 taps, 4 * cp columns
             assert taps == 9 and cols <= s2d_cp and not fold_kw
             cols_p = 4 * s2d_cp
         dst = torch.zeros(taps, rows_p, cols_p, dtype=dtype, device=self.device)
         self.items.append(L.PackItem(src.data_ptr(), dst.data_ptr(), rows, rows_p, cols, cols_p, taps, srs, scs,
-                                     _DT[dtype], fold_kw, 1 if fold_flip else 0, s2d_cp if s2d_k else q, s2d_k))
+                                     _DT[dtype], fold_kw, int(fold_flip), s2d_cp if s2d_k else q, s2d_k))
         self.keep.append((src, dst))
         self.max_elems = max(self.max_elems, dst.numel())
         self.dev = None
@@ -269,6 +273,7 @@ def pack_conv_weight(w, dtype, kind):
           'fwd_fold'   same, kw-folded for a <= 16-byte-per-pixel input (dtg_conv fold_w)
           'dgrad' conv weight [co,ci,kh,kw]  -> rows ci, cols co        (Conv2d data gradient)
           'dgrad_fold' same, kw-folded + flipped for a small-channel dy (dtg_conv fold_w, DGRAD)
+          'fwd_kwn'    conv weight [co,ci,kh,kw] -> [kh][(kw, co) padded to 32][ci]   (dtg_conv fold_w = 2)
           'tfwd'  convT weight [ci,co,kh,kw] -> rows co, cols ci        (ConvTranspose2d forward)
           'tdgrad' convT weight [ci,co,kh,kw]-> rows ci, cols co        (ConvTranspose2d data gradient)"""
     tab = PackTable(w.device)
@@ -290,6 +295,8 @@ def add_packed(tab, w, dtype, kind, s2d_cp=0):
         return tab.add(w, d0, d1, kh, d1, 1, dtype, fold_kw=kw)
     if kind == "dgrad_fold":
         return tab.add(w, d1, d0, kh, 1, d1, dtype, fold_kw=kw, fold_flip=True)
+    if kind == "fwd_kwn":              # filter column in GEMM-N (conv_tail7.cu): rows = (kw, dim0), cols = dim1, taps = kh
+        return tab.add(w, d0, d1, kh, d1, 1, dtype, fold_kw=kw, fold_flip=2)
     raise ValueError(kind)
 
 
@@ -311,11 +318,25 @@ def conv(x, wp, bias, out, *, mode=L.CONV_FWD, kh, kw, stride=1, pad=0, ring=0, 
     """x: PlaneT; wp: packed weight [taps, rows_p, cols_p]; out: PlaneT or None with out_nchw fp32 tensor.
     cin: real input channels (FLOP accounting only)."""
     a = L.ConvArgs(mode, kh, kw, stride, pad, ring, act, cout, 1 if out_nchw is not None else 0,
-                   1 if out_reflect else 0, out_h, out_w, 1 if fold_w else 0)
+                   1 if out_reflect else 0, out_h, out_w, int(fold_w))
     assert wp.shape[0] == (kh if fold_w else kh * kw)
     rc = L.lib().dtg_conv(C.byref(a), x.s, _ptr(wp), wp.shape[1], wp.shape[2], _ptr(bias),
                           out.s if out is not None else NULL_PLANE, _ptr(out_nchw), _stream())
     L.check(rc, "conv")
+
+
+def tail_kwn_eligible(cin_stored, k, cout, w, dtype):
+    """geometry test of dtg_conv fold_w = 2 (conv_tail7.cu: try_launch_tail7) for a k x k 'same' head on a halo-free plane
+    with cin_stored channels and image width w: row bytes 32 / 64 / 128, (kw, cout) <= 28 GEMM columns, the width a divisor
+    of 128, and two patch stages (128 / w + k - 1 image rows each) next to the weights and the staging tile in 227 KB"""
+    rb = cin_stored * (2 if dtype == torch.bfloat16 else 4)
+    if rb not in (32, 64, 128) or not (1 <= cout <= 4) or k % 2 == 0 or k > 8 or k * cout > 28:
+        return False
+    if w < 8 or w > 128 or 128 % w:
+        return False
+    stage = ((128 // w + k - 1) * w * rb + 1023) // 1024 * 1024
+    fixed = 1024 + (k * 32 * rb + 1023) // 1024 * 1024 + 1024 + 2 * 128 * 29 * 4
+    return 2 * stage + fixed <= 227 * 1024
 
 
 _ws_cache = {}

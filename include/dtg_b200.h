@@ -28,7 +28,7 @@
 extern "C" {
 #endif
 
-#define DTG_VERSION 123 /* 123: dtg_preprocess_fields; 122: dtg_ubo_laplace, dtg_ubo_latent_step; 121: dtg_norm_bwd phases 3 / 4; 120: dtg_set_option, dtg_loss_fused; two-phase / TMA-staged instance-norm kernels behind dtg_norm_fwd / dtg_norm_bwd */
+#define DTG_VERSION 124 /* 124: dtg_conv fold_w = 2; 123: dtg_preprocess_fields; 122: dtg_ubo_laplace, dtg_ubo_latent_step; 121: dtg_norm_bwd phases 3 / 4; 120: dtg_set_option, dtg_loss_fused; two-phase / TMA-staged instance-norm kernels behind dtg_norm_fwd / dtg_norm_bwd */
 
 enum { DTG_OK = 0, DTG_ERR_INVALID = -1, DTG_ERR_CUDA = -2, DTG_ERR_UNSUPPORTED = -3 };
 enum { DTG_BF16 = 0, DTG_F32 = 1 };
@@ -76,6 +76,8 @@ int dtg_set_option(const char* key, int value);
  * kw-folded form (fold_kw = KW > 0; small-channel 7x7 layers, see dtg_conv fold_w): `taps` = KH and a
  * destination column c = j*fold_fc + b holds filter column j (KW-1-j if fold_flip) of inner channel b:
  * dst[kh][r][j*fold_fc + b] = src[((r*srs + b*scs)*KH + kh)*KW + kw(j)] for j < KW, b < cols, else 0.
+ * fold_flip = 2: the filter column goes into the ROWS instead (dtg_conv fold_w = 2): `taps` = KH,
+ * dst[kh][kw*rows + r][c] = src[((r*srs + c*scs)*KH + kh)*KW + kw], rows_p >= KW*rows.
  * ------------------------------------------------------------------------------------------- */
 typedef struct dtg_pack_item {
   const float* src;
@@ -114,6 +116,11 @@ int dtg_pack_weights(const dtg_pack_item* items_dev, int nitems, int max_elems, 
  * `w` is the kw-folded packing [kh][w_rows][128 bytes] (dtg_pack_item fold_kw; fold_flip for DGRAD).
  * This is the generators' 7x7 head (networks.py:159-160,211-212) and the data gradient of their 7x7
  * tail (networks.py:187,242) without a materialised im2col.
+ * fold_w = 2 (FWD, stride 1, "same" odd kernel, cout <= 4 with kw*cout <= 28, input halo 0 and 32 / 64 / 128 bytes
+ * per pixel, width a divisor of 128, out_nchw_f32): the filter COLUMN goes into GEMM-N -- `w` is the
+ * [kh][32][cin] packing of fold_flip = 2, only the KH filter rows are taps (14 tcgen05.mma per 128-pixel tile
+ * instead of 98 for 32 -> 3 channels) and the epilogue adds the KW column partials with their pixel shift.
+ * This is the forward of the generators' 7x7 tail + tanh (networks.py:187-188, 242-243).
  * ------------------------------------------------------------------------------------------- */
 typedef struct dtg_conv_args {
   int32_t mode; /* DTG_CONV_FWD / DTG_CONV_DGRAD */
@@ -124,7 +131,7 @@ typedef struct dtg_conv_args {
   int32_t out_nchw_f32; /* 1: `out_nchw` is used instead of `out` */
   int32_t out_reflect;  /* 1: mirror results into out.halo */
   int32_t out_h, out_w; /* interior output extents (validated against the geometry) */
-  int32_t fold_w;       /* 1: kw-folded small-channel input (see above) */
+  int32_t fold_w;       /* 1: kw-folded small-channel input; 2: filter column in GEMM-N (see above) */
 } dtg_conv_args;
 int dtg_conv(const dtg_conv_args* a, const dtg_plane* in, const void* w, int w_rows, int w_cols,
              const float* bias, const dtg_plane* out, float* out_nchw, void* stream);

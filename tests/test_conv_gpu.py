@@ -93,6 +93,39 @@ def test_conv_fwd_nchw_tanh_and_reflect_out():
     assert _relerr(got2, ref2) < 1.2e-2
 
 
+@pytest.mark.parametrize("dtype", [torch.bfloat16, torch.float32])
+@pytest.mark.parametrize("n,cin,cout,h,w,k", [(2, 32, 3, 64, 64, 7), (3, 32, 1, 128, 128, 7), (2, 32, 3, 32, 32, 7),
+                                              (160, 32, 3, 64, 64, 7), (2, 16, 4, 24, 16, 5), (1, 32, 3, 33, 64, 7)])
+def test_conv_tail_filter_column_in_gemm_n(n, cin, cout, h, w, k, dtype):
+    """dtg_conv fold_w = 2 (conv_tail7.cu): the generators' 7x7 tail + tanh (networks.py:187-188, 242-243) with (kw, cout)
+    in GEMM-N and a shift-add epilogue, against torch's fp64 convolution on the same representable operands; 160 images =
+    more tiles than SMs (persistent loop, 4 TMEM buffers wrap), 33 rows = a ragged last tile, 24x16 = 8 rows per tile"""
+    g = torch.Generator().manual_seed(11)
+    x = _q(torch.randn(n, cin, h, w, generator=g), dtype).to(DEV)
+    wt = _q(torch.randn(cout, cin, k, k, generator=g) * 0.05, dtype).to(DEV)
+    b = torch.randn(cout, generator=g).to(DEV) * 0.1
+    xp = ops.PlaneT.from_nchw(x, dtype=dtype)
+    wp = ops.pack_conv_weight(wt, dtype, "fwd_kwn")
+    assert tuple(wp.shape)[:2] == (k, 32)
+    y = torch.full((n, cout, h, w), float("nan"), device=DEV)
+    run = lambda: ops.conv(xp, wp, b, None, kh=k, kw=k, pad=k // 2, act=L.ACT_TANH, cout=cout, out_h=h, out_w=w, out_nchw=y,
+                           fold_w=2)
+    if not ops.tail_kwn_eligible(xp.c, k, cout, w, dtype):       # fp32 at width 128: two 114 KB patch stages do not fit
+        assert dtype == torch.float32 and w == 128
+        with pytest.raises(RuntimeError, match="not eligible"):
+            run()
+        return
+    run()
+    ref = torch.tanh(F.conv2d(x.double(), wt.double(), b.double(), padding=k // 2)).float()
+    assert torch.isfinite(y).all()
+    assert _relerr(y, ref) < 2e-3
+    # identical (up to summation order) to the ordinary tap-per-MMA mapping
+    y2 = torch.empty_like(y)
+    ops.conv(xp, ops.pack_conv_weight(wt, dtype, "fwd"), b, None, kh=k, kw=k, pad=k // 2, act=L.ACT_TANH, cout=cout, out_h=h,
+             out_w=w, out_nchw=y2)
+    assert _relerr(y, y2) < 1e-4
+
+
 DGRAD_CASES = [
     # n, cin, cout, h(in), k, s, pad, ring
     (2, 128, 128, 32, 3, 1, 1, 0),

@@ -20,8 +20,18 @@ WANT = {
     "sm__inst_executed_pipe_tensor.sum": "tensor_pipe_insts",
     "sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_elapsed": "tensor_pipe_active_pct_elapsed",
     "l1tex__m_xbar2l1tex_read_bytes.sum": "l2_to_sm_read_bytes",
+    # tcgen05-aware counters (ncu --query-metrics on the B200 box, profiles/r2_ncu_tensor_metrics.txt)
+    "sm__ops_path_tensor_op_utchmma_src_bf16_dst_fp32.sum": "utchmma_bf16_math_ops",
+    "sm__ops_path_tensor_op_utchmma_src_bf16_dst_fp32.sum.per_second": "utchmma_bf16_math_ops_per_second",
+    "sm__ops_path_tensor_op_utchmma_src_bf16_dst_fp32.avg.pct_of_peak_sustained_elapsed": "utchmma_bf16_pct_of_peak_elapsed",
+    "sm__pipe_tc_cycles_active.avg.pct_of_peak_sustained_elapsed": "pipe_tc_cycles_active_pct_elapsed",
+    "sm__pipe_tensor_subpipe_hmma_cycles_active.avg.pct_of_peak_sustained_elapsed": "pipe_tensor_hmma_cycles_active_pct_elapsed",
+    "sm__sass_inst_executed_op_utcmma.sum": "utcmma_instructions",
+    "sm__inst_executed_pipe_tc.sum": "pipe_tc_instructions",
+    "l1tex__data_pipe_tc_wavefronts_mem_shared_op_utcmma_matrix_a.sum": "smem_wavefronts_utcmma_a",
+    "l1tex__data_pipe_tc_wavefronts_mem_shared_op_utcmma_matrix_b_scope_1cta.sum": "smem_wavefronts_utcmma_b_1cta",
 }
-UNIT = {"Mbyte": 1e6, "Kbyte": 1e3, "Gbyte": 1e9, "byte": 1.0, "us": 1.0, "ms": 1e3, "ns": 1e-3}
+UNIT = {"Tbyte": 1e12, "Mbyte": 1e6, "Kbyte": 1e3, "Gbyte": 1e9, "byte": 1.0, "us": 1.0, "ms": 1e3, "ns": 1e-3}
 out = {}
 for spec in sys.argv[2:]:
     name, rest = spec.split("=", 1)
@@ -37,6 +47,9 @@ for spec in sys.argv[2:]:
                 d[WANT[k]] = float(val.replace(",", "")) * UNIT.get(u, 1.0)
             except ValueError:
                 pass
+    for k in ("workload", "case"):
+        if k in extra:
+            d[k] = extra[k]
     if "flops" in extra:
         d["algorithmic_flops"] = float(extra["flops"])
         d["algorithmic_tflops_under_ncu"] = float(extra["flops"]) / (d["duration_us"] * 1e-6) / 1e12

@@ -27,7 +27,14 @@ N = CASES[case][8] if len(CASES[case]) > 8 else N
 oh = (h + 2 * pad - k) // s + 1
 x = ops.PlaneT(N, h, h, ops.cpad(cin, dt), halo, dt); x.t.normal_()
 w = (torch.randn(cout, cin, k, k, generator=g) * 0.05).cuda()
-if mode == "fwd":
+if mode == "fwd" and os.environ.get("PROF_HEAD"):     # dense fp32 NCHW head + tanh; PROF_HEAD=2: filter column in GEMM-N
+    kwn = os.environ["PROF_HEAD"] == "2"
+    wp = ops.pack_conv_weight(w, dt, "fwd_kwn" if kwn else "fwd")
+    y = torch.empty(N, cout, oh, oh, device="cuda")
+    bias = torch.zeros(cout, device="cuda")
+    f = lambda: ops.conv(x, wp, bias, None, kh=k, kw=k, stride=s, pad=pad, cout=cout, out_h=oh, out_w=oh, act=L.ACT_TANH,
+                         out_nchw=y, fold_w=2 if kwn else 0)
+elif mode == "fwd":
     wp = ops.pack_conv_weight(w, dt, "fwd")
     out = ops.PlaneT(N, oh, oh, ops.cpad(cout, dt), 0, dt)
     bias = torch.zeros(cout, device="cuda") if os.environ.get("PROF_BIAS") else None
