@@ -195,6 +195,47 @@ def test_losses_and_gather():
     assert _rel(bias, b.sum(dim=(0, 2, 3))) < 5e-4
 
 
+def test_loss_fused_equals_the_single_term_kernels():
+    """dtg_loss_fused (north_star (3): one reduction launch per pass, model.py:432-439, 458-505): four segments -- a
+    discriminator's fake / real LSGAN pair, a second pair of another size, an L1 + tanh' term -- must reproduce the
+    single-term kernels in ONE launch: seed-gradient planes bit for bit, the reduced scalars up to the different grouping of
+    the block partials (the fused grid is sized for its largest segment)"""
+    g = torch.Generator().manual_seed(8)
+    n = 6
+    fake = torch.randn(n, 1, 14, 14, generator=g).to(DEV)
+    real = torch.randn(n, 1, 14, 14, generator=g).to(DEV)
+    zf = torch.randn(n, 1, 1, 1, generator=g).to(DEV)
+    pre = torch.randn(n, 3, 32, 32, generator=g).to(DEV)
+    rec, tgt = torch.tanh(pre), (torch.rand(n, 3, 32, 32, generator=g) * 2 - 1).to(DEV)
+    mk = lambda h, c=16: ops.PlaneT(n, h, h, c, 0, torch.float32)
+    # reference: one launch per term
+    s1 = torch.zeros(32, device=DEV)
+    ws1 = torch.zeros(1024, dtype=torch.float32, device=DEV)
+    d1 = [mk(14), mk(14), mk(1), mk(32)]
+    ops.loss_lsgan(fake, 0.0, 0.5, s1, 0, 1, d1[0], ws1)
+    ops.loss_lsgan(real, 1.0, 0.5, s1, 2, 3, d1[1], ws1)
+    ops.loss_lsgan(zf, 1.0, 0.25, s1, 4, 5, d1[2], ws1)
+    ops.loss_l1(rec, tgt, 0.7, True, s1, 6, 7, d1[3], ws1)
+    # fused: one launch
+    s2 = torch.zeros(32, device=DEV)
+    ws2 = torch.zeros(4 * 1024, dtype=torch.float32, device=DEV)
+    d2 = [mk(14), mk(14), mk(1), mk(32)]
+    n0 = L.lib().dtg_launch_count()
+    ops.loss_fused([ops.lsgan_seg(fake, 0.0, 0.5, 0, 1, d2[0]), ops.lsgan_seg(real, 1.0, 0.5, 2, 3, d2[1]),
+                    ops.lsgan_seg(zf, 1.0, 0.25, 4, 5, d2[2]), ops.l1_seg(rec, tgt, 0.7, True, 6, 7, d2[3])], s2, ws2)
+    assert L.lib().dtg_launch_count() - n0 == 1
+    assert torch.allclose(s1, s2, rtol=2e-6, atol=1e-7), (s1[:10], s2[:10])
+    for a, b in zip(d1, d2):
+        assert torch.equal(a.t, b.t)
+    # and against autograd
+    fr = fake.double().requires_grad_(True)
+    l = OF.lsgan(fr, False); (0.5 * l).backward()
+    assert abs(float(s2[0]) - float(l)) < 1e-5 and _rel(d2[0].to_nchw(1), fr.grad.float()) < 5e-4
+    # a second call on the same workspace (self-resetting counters)
+    ops.loss_fused([ops.lsgan_seg(fake, 0.0, 0.5, 0, 1, d2[0]), ops.l1_seg(rec, tgt, 0.7, True, 6, 7, d2[3])], s2, ws2)
+    assert torch.allclose(s1[:2], s2[:2], rtol=2e-6, atol=1e-7) and torch.allclose(s1[6:10], s2[6:10], rtol=2e-6, atol=1e-7)
+
+
 def test_clip_adam_matches_torch():
     g = torch.Generator().manual_seed(3)
     cnt = 100003
