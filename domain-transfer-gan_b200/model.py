@@ -256,7 +256,9 @@ class _FusedCycleModel(object):
         first use for this batch shape; inputs are copied into static buffers).  report=False skips the
         device->host read and returns (None, visuals, None); report="defer" returns (PendingReport, visuals, None):
         the read is enqueued behind the step and resolved by PendingReport.get() -> (losses, gnorms), at most four
-        steps later."""
+        steps later.
+        The visuals (fake_B, rec_A, fake_A, rec_B) are VIEWS of the plan's static head buffers: they are valid until the
+        next forward of the same network (the reference returns fresh tensors); clone what must outlive the step."""
         ins = self._check_inputs(real_A, real_B, prior_z_B)
         visuals = self._run("train", self._step_device, ins, use_graph)
         visuals = OrderedDict(visuals)
@@ -386,6 +388,16 @@ class _FusedCycleModel(object):
             getattr(self, k).load_state_dict(checkpoint[k])
 
     def eval(self):
+        """model.py:298-303 flips the nn.Module flags and so does this.  The fused plans do not have a running-statistics
+        inference mode: the BatchNorm networks (E_B, D_z_B) keep normalising with batch statistics (and keep updating
+        running_mean / running_var) after eval().  No code path of the reference ever calls eval() (train.py,
+        evaluate.py and test.py all run the networks in training mode), so the drop-in behaviour is identical there; a
+        caller that relies on eval() semantics gets a warning instead of silently different numbers."""
+        import warnings
+        if any(isinstance(m, (torch.nn.BatchNorm1d, torch.nn.BatchNorm2d)) for net in self._nets().values()
+               for m in net.modules()):
+            warnings.warn("dtg_b200: eval() does not switch the fused BatchNorm layers to running statistics; E_B / D_z_B "
+                          "keep using batch statistics, exactly as in the reference's own (training-mode) evaluation paths")
         for net in self._nets().values():
             net.eval()
 

@@ -340,13 +340,17 @@ def tail_kwn_eligible(cin_stored, k, cout, w, dtype):
 
 
 _ws_cache = {}
+_ws_retired = []      # outgrown scratch buffers: captured CUDA graphs may still hold their addresses, so they are never freed
 
 
 def workspace(nbytes, device="cuda", tag="default"):
-    """Grow-only scratch buffer per (device, tag); contents are never assumed to persist."""
+    """Grow-only scratch buffer per (device, tag, lane); contents are never assumed to persist.  A buffer that is outgrown
+    is retired, not freed: an earlier captured graph (another batch shape) keeps writing to it on replay."""
     key = (str(device), tag, _LANE)
     t = _ws_cache.get(key)
     if t is None or t.numel() < nbytes:
+        if t is not None:
+            _ws_retired.append(t)
         t = torch.empty(max(nbytes, 1 << 20), dtype=torch.uint8, device=device)
         _ws_cache[key] = t
     return t

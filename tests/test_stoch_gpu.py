@@ -59,13 +59,14 @@ def _stoch_oracle_step(state, opt_kw, a, b, z, prec=None, ignore_noise=False):
 
 
 @pytest.mark.parametrize("prec,size,out_nc,ignore_noise", [("tf32", 64, 3, False), ("bf16", 64, 3, True),
-                                                          ("tf32", 128, 1, False), ("bf16", 128, 1, False)])
+                                                          ("tf32", 128, 1, False), ("bf16", 128, 1, False),
+                                                          ("bf16", 256, 3, False)])     # BASELINE config 4's grid
 def test_stoch_train_instance_matches_oracle(prec, size, out_nc, ignore_noise):
     engine.set_precision(prec)
     kw = dict(output_nc=out_nc)
     state = onets.init_model_state(seed=1234, perturb=0.05, output_nc=out_nc)
     kind = "climate" if out_nc == 1 else "edges2shoes"
-    a, b, z = [t.to(DEV) for t in ostep.synthetic_batch(2 if size > 64 else 4, size=size, seed=4321, output_nc=out_nc, kind=kind)]
+    a, b, z = [t.to(DEV) for t in ostep.synthetic_batch(1 if size > 128 else (2 if size > 64 else 4), size=size, seed=4321, output_nc=out_nc, kind=kind)]
     ours = _load(dmodel.StochCycleGAN(_opt(**kw), ignore_noise=ignore_noise, testing=True), state)
     losses, visuals, gnorms = ours.train_instance(a, b, z)
     got = {name: {k: p.grad.clone() for k, p in net.named_parameters() if p.grad is not None}
