@@ -137,7 +137,8 @@ def _ncu_traffic(workload, kernel):
     for fn in sorted(glob.glob(os.path.join(ROOT, "profiles", "*ncu_summary.json"))):
         try:
             for key, k in json.load(open(fn)).items():
-                if k.get("workload", "aug64") == workload and str(k.get("kernel", key)).split("<")[0].split("::")[-1] in kernel:
+                name = str(k.get("kernel", key)).replace("void ", "").split("<")[0].split("(")[0].split("::")[-1].strip()
+                if k.get("workload", "aug64") == workload and name and name in kernel:
                     best = k["dram_bytes_read"] + k["dram_bytes_write"]
         except Exception:
             continue
