@@ -21,6 +21,7 @@ S2D = os.environ.get("DTG_NO_S2D") is None      # space-to-depth execution of th
 # tensor-core path (fwd 52 vs 44 us, dgrad 49 vs 55 us, wgrad 68 vs 59 us at batch 160; step time unchanged), so the
 # tensor-core path stays the default and this is opt-in
 HEAD1 = os.environ.get("DTG_HEAD1") is not None
+OFFCHAIN_SMALL = os.environ.get("DTG_NO_OFFCHAIN_SMALL") is None      # parameter-gradient reductions of the norm layers on the companion stream
 TAIL_KWN = os.environ.get("DTG_NO_TAIL_KWN") is None      # generators' 7x7 tail forward with (kw, cout) in GEMM-N (conv_tail7.cu)
 
 
@@ -397,7 +398,7 @@ class NetExec:
                 y = c.acts[i + 1] if ly.act != L.ACT_NONE else None
                 if ly.norm == L.NORM_NONE:
                     ops.norm_bwd(dy, dyr, c.nst[i], mode=L.NORM_NONE, act=ly.act, y=y, dy2=dy2,
-                                 d_beta=A.g(ly.conv.bias) if (want_dw and ly.use_bias) else None, defer_channel=True)
+                                 d_beta=A.g(ly.conv.bias) if (want_dw and ly.use_bias) else None, defer_channel=OFFCHAIN_SMALL)
                 elif ly.norm == L.NORM_COND_INSTANCE:
                     gam, bet = c.cin[i]
                     ops.norm_bwd(dy, dyr, c.nst[i], mode=ly.norm, act=ly.act, y=y, x=c.yraw[i], gamma=gam, dy2=dy2,
@@ -409,12 +410,13 @@ class NetExec:
                         else:
                             tg = self._scratch_cin(sc)
                         # parameter / noise gradients of the two 1x1 convs: nothing on the chain reads them
-                        ops.off_chain(functools.partial(ops.cin_affine_bwd, c.z, sc.weight, sh.weight, gam, bet,
-                                                        c.nst[i].sums, *tg, c.dz if want_dz else None))
+                        f = functools.partial(ops.cin_affine_bwd, c.z, sc.weight, sh.weight, gam, bet, c.nst[i].sums, *tg,
+                                              c.dz if want_dz else None)
+                        ops.off_chain(f) if OFFCHAIN_SMALL else f()
                 elif ly.norm == L.NORM_INSTANCE:
                     ops.norm_bwd(dy, dyr, c.nst[i], mode=ly.norm, act=ly.act, y=y, x=c.yraw[i], gamma=nm.scale, dy2=dy2,
                                  d_res=d_res, d_gamma=A.g(nm.scale) if want_dw else None,
-                                 d_beta=A.g(nm.shift) if want_dw else None, defer_channel=True)
+                                 d_beta=A.g(nm.shift) if want_dw else None, defer_channel=OFFCHAIN_SMALL)
                 else:
                     kw = dict(mode=ly.norm, act=ly.act, y=y, x=c.yraw[i], gamma=nm.weight, dy2=dy2, d_res=d_res,
                               d_gamma=A.g(nm.weight) if want_dw else None, d_beta=A.g(nm.bias) if want_dw else None)

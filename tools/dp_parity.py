@@ -92,7 +92,53 @@ def rel(x, y):
     return float((x - y).norm() / y.norm().clamp_min(1e-20))
 
 
+# ---- the BatchNorm exchange in isolation (well conditioned, unlike the encoder at initialisation): one BN2d + ReLU layer,
+# forward and backward, W ranks x N/W samples with the (sum, sum-of-squares) / backward-sum exchange between the two kernel
+# phases (engine.py forward / backward do exactly this) against one rank x N samples
+def bn_unit(sync):
+    from dtg_b200 import _lib as L, ops
+    g = torch.Generator().manual_seed(99)
+    n, c, h = args.batch, 64, 8
+    x_all = (torch.randn(n, c, h, h, generator=g) * 1.5 + 0.7).cuda()
+    dy_all = torch.randn(n, c, h, h, generator=g).cuda()
+    gamma = (torch.rand(c, generator=g) + 0.5).cuda()
+    beta = torch.randn(c, generator=g).cuda()
+
+    def run(x, dy, exchange, world_size):
+        xp = ops.PlaneT.from_nchw(x, dtype=torch.float32)
+        dyp = ops.PlaneT.from_nchw(dy, dtype=torch.float32)
+        out = ops.PlaneT(x.shape[0], h, h, c, 0, torch.float32)
+        dx = ops.PlaneT(x.shape[0], h, h, c, 0, torch.float32)
+        st = ops.NormState(xp)
+        run_stats = torch.stack([torch.zeros(c), torch.ones(c)]).cuda()
+        dg, db = torch.zeros(c, device="cuda"), torch.zeros(c, device="cuda")
+        kw = dict(mode=L.NORM_BATCH, act=L.ACT_RELU, gamma=gamma, beta=beta, bn_running=run_stats)
+        bw = dict(mode=L.NORM_BATCH, act=L.ACT_RELU, y=out, x=xp, gamma=gamma, d_gamma=dg, d_beta=db)
+        if exchange is None:
+            ops.norm_fwd(xp, out, st, **kw)
+            ops.norm_bwd(dyp, dx, st, **bw)
+        else:
+            ops.norm_fwd(xp, out, st, phase=1, **kw)
+            exchange(st.ws[:2 * c])
+            ops.norm_fwd(xp, out, st, phase=2, world_size=world_size, **kw)
+            ops.norm_bwd(dyp, dx, st, phase=1, **bw)
+            exchange(st.ws[:2 * c])
+            ops.norm_bwd(dyp, dx, st, phase=2, world_size=world_size, **bw)
+        torch.cuda.synchronize()
+        return out.to_nchw(c), dx.to_nchw(c), dg, db, run_stats
+
+    full = run(x_all, dy_all, None, 1)
+    plan = parallel.DataParallelPlan(sync_bn=True)
+    ex = plan.sync_bn if sync else (lambda t: None)
+    part = run(x_all[sl].contiguous(), dy_all[sl].contiguous(), ex, world if sync else 1)
+    dgb = torch.stack([part[2], part[3]])
+    dist.all_reduce(dgb)                                     # parameter gradients: summed over ranks like the arenas
+    return {"y": rel(part[0], full[0][sl]), "dx": rel(part[1], full[1][sl]), "d_gamma": rel(dgb[0], full[2]),
+            "d_beta": rel(dgb[1], full[3]), "running": rel(part[4], full[4])}
+
+
 res = {"world": world, "precision": args.precision, "batch": args.batch, "graph": bool(args.graph),
+       "bn_unit": bn_unit(not args.no_sync_bn),
        "sync_bn": not args.no_sync_bn,
        "grad_rel": {n: rel(gpar[n], gone[n]) for n in gone},
        "perm_noise_grad_rel": {n: rel(gperm[n], gone[n]) for n in gone},
