@@ -38,7 +38,6 @@ void count_launch();
 // so data dependencies (RAW and WAR) are still honoured.  DTG_NO_PDL=1 disables the attribute.
 bool pdl_enabled();
 int norm_impl();               // dtg_set_option("norm_impl"): 0 cluster-fused, 1 TMA-staged, 2 two-phase streaming
-bool wgrad_atomic_enabled();   // dtg_set_option("wgrad_atomic")
 #ifdef __CUDACC__
 template <typename... KArgs, typename... Args>
 inline cudaError_t launch_k(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t stream, Args&&... args) {

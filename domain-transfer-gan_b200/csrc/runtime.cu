@@ -28,7 +28,6 @@ static Option g_opts[] = {
     {"pdl", "DTG_NO_PDL", 0, 1, false},
     {"norm_impl", "DTG_NORM_IMPL", 0, 2, true},
     {"smem_cap_kb", "DTG_SMEM_CAP_KB", 0, 227, true},
-    {"wgrad_atomic", "DTG_WGRAD_ATOMIC", 1, 0, false},
 };
 
 static int opt_get(int i) {
@@ -45,7 +44,6 @@ static int opt_get(int i) {
 
 bool pdl_enabled() { return opt_get(0) != 0; }
 int norm_impl() { return opt_get(1); }
-bool wgrad_atomic_enabled() { return opt_get(3) != 0; }
 
 int tensor_smem_budget() {
   int kb = opt_get(2);
