@@ -64,7 +64,7 @@ int try_launch_pconv(const IgemmParams& p, const dtg_plane* in, const void* w, i
 
 // Filter-column-in-GEMM-N tail (conv_tail7.cu, dtg_conv_args.fold_w == 2): DTG_OK after launching, 1 if not eligible.
 int try_launch_tail7(const dtg_conv_args* a, const dtg_plane* in, const void* w, int w_rows, int w_cols, const float* bias,
-                     float* out_nchw, cudaStream_t stream);
+                     const dtg_plane* out, float* out_nchw, cudaStream_t stream);
 
 // ---- TMA-store epilogue ------------------------------------------------------------------------------------
 __device__ __forceinline__ void tma_store_4d(const CUtensorMap* m, const void* smem_src, int c0, int c1, int c2, int c3) {

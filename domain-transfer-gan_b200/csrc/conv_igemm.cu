@@ -304,9 +304,10 @@ extern "C" int dtg_conv(const dtg_conv_args* a, const dtg_plane* in, const void*
   }
   if (a->fold_w == 2) {
     // filter column in GEMM-N (conv_tail7.cu): the weights are packed for that kernel only
-    const int rc = try_launch_tail7(a, in, w, w_rows, w_cols, bias, out_nchw, static_cast<cudaStream_t>(stream));
-    DTG_REQUIRE(rc != 1, "dtg_conv fold_w=2: geometry not eligible (stride-1 odd-kernel 'same' head, cout <= 4, kw * cout <= 28, "
-                         "input halo 0, 32/64/128 bytes per pixel, width a divisor of 128, dense fp32 NCHW output)");
+    const int rc = try_launch_tail7(a, in, w, w_rows, w_cols, bias, out, out_nchw, static_cast<cudaStream_t>(stream));
+    DTG_REQUIRE(rc != 1, "dtg_conv fold_w=2: geometry not eligible (stride-1 odd-kernel 'same' layer, cout <= 4, kw * cout <= 28, "
+                         "input halo 0, 32/64/128 bytes per pixel, width a divisor of 128; FWD: dense fp32 NCHW output; DGRAD: "
+                         "ring == pad into a 16-byte-pixel plane with halo == ring)");
     return rc;
   }
   DTG_REQUIRE(a->stride == 1 || a->stride == 2, "dtg_conv: stride %d unsupported", a->stride);

@@ -37,6 +37,11 @@ struct Tail7Params {
   int nmma;
   unsigned short a_off[kT7MaxMma], b_off[kT7MaxMma];
   int act;
+  int full;              // 1: data gradient of a 7x7 HEAD w.r.t. its padded input ("full" correlation: (H+kh-1) x (W+kw-1)
+                         //    outputs, taps and column shifts mirrored), written as 16-byte pixels of a haloed plane
+  int row_org;           // first patch row relative to the tile's first output row: -pad (forward) / -(kh-1) (full)
+  int OH, OW;            // output rows / columns per image
+  dtg_plane outp;        // full: destination plane (16 bytes per pixel, halo = pad)
   int dbg;               // DTG_T7_DBG experiments: 1 = one MMA per tile, 2 = skip the patch loads, 4 = skip the epilogue body
   const float* bias;
   float* out;            // [N][cout][H][W] fp32
@@ -111,7 +116,7 @@ __global__ void __launch_bounds__(kThreads, 1) tail7_kernel(const __grid_constan
         if (elect_one()) mbar_arrive(&bar_full[stage]);
       } else if (elect_one()) {
         mbar_expect_tx(&bar_full[stage], a_tx);
-        tma_load_4d(sA + stage * p.a_stage_bytes, &p.tmA, &bar_full[stage], 0, 0, th * p.rpt - p.pad, n);
+        tma_load_4d(sA + stage * p.a_stage_bytes, &p.tmA, &bar_full[stage], 0, 0, th * p.rpt + p.row_org, n);
       }
       __syncwarp();
       if (++stage == S) {
@@ -194,28 +199,47 @@ __global__ void __launch_bounds__(kThreads, 1) tail7_kernel(const __grid_constan
       for (int j = 0; j < 12; ++j) mine[16 + j] = __uint_as_float(v1[j]);
       named_bar_sync(1, 128);
       const int oy = th * p.rpt + r;
-      if (oy < p.H) {
+      if (oy < p.OH) {
         // registers only: constant trip counts, runtime bounds as predicates (runtime-indexed arrays would go to local
         // memory: 38 us instead of 14 for 32 -> 3 channels at 64x64 x 80).  A staging row holds 29 floats, so reading four
         // columns from kw * cout is always in bounds; columns >= cout are simply not stored.
-        float a0 = b0, a1 = b1, a2 = b2, a3 = b3;
+        const float* srow = st + (r * p.W) * kT7Pitch;
+        // forward: y[ox] = sum_kw D[ox + kw - pad][kw];   full: dx[o] = sum_kw D[o - kw][kw]  (o = ox, and o = W + ox for the
+        // kw - 1 extra columns of the wider output)
+        for (int o = ox; o < p.OW; o += p.W) {
+          float a0 = b0, a1 = b1, a2 = b2, a3 = b3;
 #pragma unroll
-        for (int kw = 0; kw < 8; ++kw) {
-          const int sx = ox + kw - p.pad;
-          if (kw < p.kw && sx >= 0 && sx < p.W) {
-            const float* src = st + (row + kw - p.pad) * kT7Pitch + kw * p.cout;
-            a0 += src[0];
-            a1 += src[1];
-            a2 += src[2];
-            a3 += src[3];
+          for (int kw = 0; kw < 8; ++kw) {
+            const int sx = p.full ? o - kw : o + kw - p.pad;
+            if (kw < p.kw && sx >= 0 && sx < p.W) {
+              const float* src = srow + sx * kT7Pitch + kw * p.cout;
+              a0 += src[0];
+              a1 += src[1];
+              a2 += src[2];
+              a3 += src[3];
+            }
+          }
+          if (!p.full) {
+            const size_t plane = static_cast<size_t>(p.H) * p.W;
+            float* op = p.out + (static_cast<size_t>(n) * p.cout * p.H + oy) * p.W + o;
+            op[0] = apply_act(a0, p.act);
+            if (p.cout > 1) op[plane] = apply_act(a1, p.act);
+            if (p.cout > 2) op[2 * plane] = apply_act(a2, p.act);
+            if (p.cout > 3) op[3 * plane] = apply_act(a3, p.act);
+          } else {
+            if (p.cout < 2) a1 = 0.f;
+            if (p.cout < 3) a2 = 0.f;
+            if (p.cout < 4) a3 = 0.f;
+            const size_t pix = (static_cast<size_t>(n) * p.OH + oy) * p.OW + o;
+            if (p.outp.dtype == DTG_BF16) {
+              __nv_bfloat162 lo = __floats2bfloat162_rn(a0, a1), hi = __floats2bfloat162_rn(a2, a3);
+              uint4 v = make_uint4(*reinterpret_cast<uint32_t*>(&lo), *reinterpret_cast<uint32_t*>(&hi), 0u, 0u);
+              reinterpret_cast<uint4*>(p.outp.ptr)[pix] = v;
+            } else {
+              reinterpret_cast<float4*>(p.outp.ptr)[pix] = make_float4(round_tf32(a0), round_tf32(a1), round_tf32(a2), round_tf32(a3));
+            }
           }
         }
-        const size_t plane = static_cast<size_t>(p.H) * p.W;
-        float* o = p.out + (static_cast<size_t>(n) * p.cout * p.H + oy) * p.W + ox;
-        o[0] = apply_act(a0, p.act);
-        if (p.cout > 1) o[plane] = apply_act(a1, p.act);
-        if (p.cout > 2) o[2 * plane] = apply_act(a2, p.act);
-        if (p.cout > 3) o[3 * plane] = apply_act(a3, p.act);
       }
       ++it;
     }
@@ -232,11 +256,17 @@ __global__ void __launch_bounds__(kThreads, 1) tail7_kernel(const __grid_constan
 // returns DTG_OK after launching, 1 if the geometry is not eligible (the caller reports an error: the weights are packed
 // for this kernel only)
 int try_launch_tail7(const dtg_conv_args* a, const dtg_plane* in, const void* w, int w_rows, int w_cols, const float* bias,
-                     float* out_nchw, cudaStream_t stream) {
+                     const dtg_plane* out, float* out_nchw, cudaStream_t stream) {
   const int es = elem_size(in->dtype);
   const bool tf32 = in->dtype == DTG_F32;
   const int rb = in->c * es;
-  if (a->mode != DTG_CONV_FWD || a->stride != 1 || in->halo != 0 || !out_nchw) return 1;
+  const bool full = a->mode == DTG_CONV_DGRAD;
+  if (a->stride != 1 || in->halo != 0) return 1;
+  if (!full && !out_nchw) return 1;
+  // full: gradient w.r.t. the padded input of a "same" head (ring == pad): every pixel of the haloed 16-byte-pixel plane
+  if (full && (a->ring != a->pad || !out || !out->ptr || out->halo != a->ring || out->c * es != 16 || out->dtype != in->dtype ||
+               out->n != in->n || out->h != in->h || out->w != in->w || bias != nullptr || a->act != DTG_ACT_NONE))
+    return 1;
   if (rb != 32 && rb != 64 && rb != 128) return 1;
   if (a->cout < 1 || a->cout > 4 || a->kw * a->cout > 28 || a->kh > 8 || w_rows != kT7N || w_cols != in->c) return 1;
   if (a->kh != 2 * a->pad + 1 || a->kw != 2 * a->pad + 1 || a->out_h != in->h || a->out_w != in->w) return 1;
@@ -253,7 +283,13 @@ int try_launch_tail7(const dtg_conv_args* a, const dtg_plane* in, const void* w,
   p.pad = a->pad;
   p.rpt = 128 / W;
   p.PH = p.rpt + a->kh - 1;
-  p.tiles_per_img = (H + p.rpt - 1) / p.rpt;
+  p.full = full ? 1 : 0;
+  p.row_org = full ? -(a->kh - 1) : -a->pad;
+  p.OH = full ? H + a->kh - 1 : H;
+  p.OW = full ? W + a->kw - 1 : W;
+  if (p.OW > 2 * W) return 1;
+  if (full) p.outp = *out;
+  p.tiles_per_img = (p.OH + p.rpt - 1) / p.rpt;
   p.rb = rb;
   p.layout = rb == 128 ? 2 : (rb == 64 ? 4 : 6);
   p.rb_elems = rb / es;
@@ -265,7 +301,8 @@ int try_launch_tail7(const dtg_conv_args* a, const dtg_plane* in, const void* w,
   for (int t = 0; t < a->kh; ++t)
     for (int j = 0; j < ks; ++j) {
       p.a_off[t * ks + j] = static_cast<unsigned short>((t * W * rb + j * 32) >> 4);
-      p.b_off[t * ks + j] = static_cast<unsigned short>((t * p.b_tap_bytes + j * 32) >> 4);
+      // full: patch row t holds dy row (oy - (kh-1) + t), which meets filter row kh-1-t
+      p.b_off[t * ks + j] = static_cast<unsigned short>(((full ? a->kh - 1 - t : t) * p.b_tap_bytes + j * 32) >> 4);
     }
   const int b_bytes = a->kh * p.b_tap_bytes;
   const int fixed = 1024 + ((b_bytes + 1023) & ~1023) + 1024 + 2 * kTileM * kT7Pitch * 4;

@@ -158,6 +158,7 @@ class Layer:
         # fold_out: the OUTPUT gradient is (head with <= fc channels) -> dgrad and wgrad read dy kw-folded
         self.fold_in = self.fold_out = False
         self.tail_kwn, self.w_f_kwn = False, None
+        self.head_kwn_d, self.w_d_kwn = False, None
         # space-to-depth execution of a stride-2 first layer with a <= 64-byte input pixel (decided in
         # NetExec.prepare): the input plane is stored as 2x2 pixel blocks, forward conv and wgrad run as stride-1 3x3
         self.s2d = False
@@ -222,6 +223,10 @@ class NetExec:
                 ly.tail_kwn = (TAIL_KWN and foldable and ly.head and ly.cout <= 4 and ly.k * ly.cout <= 28 and src_halo == 0
                                and ly.src > 0 and rowb in (32, 64, 128) and ops.cpad(ly.cin, dtype) == ly.cin)
                 ly.w_f_kwn = ops.add_packed(self.pack, w4, dtype, "fwd_kwn") if ly.tail_kwn else None
+                # the mirror image: data gradient of the 7x7 HEAD (16-byte-pixel input with a materialised halo == pad)
+                ly.head_kwn_d = (TAIL_KWN and bool(ly.fold_in) and ly.cin <= 4 and ly.k * ly.cin <= 28 and self.in_halo == ly.pad
+                                 and ops.cpad(ly.cout, dtype) == ly.cout)
+                ly.w_d_kwn = ops.add_packed(self.pack, w4, dtype, "dgrad_kwn") if ly.head_kwn_d else None
                 ly.head1 = (HEAD1 and ly.head and ly.cout == 1 and not ly.transposed and ly.stride == 1 and w.dim() == 4 and
                             ly.k * ly.k <= 16 and ly.act == L.ACT_NONE and src_halo == 0 and ly.src > 0 and
                             ly.cin % 8 == 0 and ly.cin <= 512)
@@ -441,6 +446,10 @@ class NetExec:
                 elif ly.transposed:
                     ops.conv(dyr, ly.w_d, None, gin, mode=L.CONV_FWD, kh=ly.k, kw=ly.k, stride=ly.stride, pad=ly.pad,
                              cout=ly.cin, out_h=ih, out_w=iw, cin=ly.cout)
+                elif (ly.head_kwn_d and a_in.halo == ly.pad and gin.halo == ly.pad and gin.c * gin.t.element_size() == 16
+                      and ops.tail_kwn_eligible(dyr.c, ly.k, ly.cin, iw, dyr.dtype)):
+                    ops.conv(dyr, ly.w_d_kwn, None, gin, mode=L.CONV_DGRAD, kh=ly.k, kw=ly.k, stride=1, pad=ly.pad,
+                             ring=a_in.halo, cout=ly.cin, out_h=ih, out_w=iw, cin=ly.cout, fold_w=2)
                 else:
                     ops.conv(dyr, ly.w_d, None, gin, mode=L.CONV_DGRAD, kh=ly.k, kw=ly.k, stride=ly.stride, pad=ly.pad,
                              ring=a_in.halo, cout=ly.cin, out_h=ih, out_w=iw, cin=ly.cout,

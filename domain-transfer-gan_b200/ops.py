@@ -274,6 +274,7 @@ def pack_conv_weight(w, dtype, kind):
           'dgrad' conv weight [co,ci,kh,kw]  -> rows ci, cols co        (Conv2d data gradient)
           'dgrad_fold' same, kw-folded + flipped for a small-channel dy (dtg_conv fold_w, DGRAD)
           'fwd_kwn'    conv weight [co,ci,kh,kw] -> [kh][(kw, co) padded to 32][ci]   (dtg_conv fold_w = 2)
+          'dgrad_kwn'  conv weight [co,ci,kh,kw] -> [kh][(kw, ci) padded to 32][co]   (dtg_conv fold_w = 2, DGRAD)
           'tfwd'  convT weight [ci,co,kh,kw] -> rows co, cols ci        (ConvTranspose2d forward)
           'tdgrad' convT weight [ci,co,kh,kw]-> rows ci, cols co        (ConvTranspose2d data gradient)"""
     tab = PackTable(w.device)
@@ -297,6 +298,8 @@ def add_packed(tab, w, dtype, kind, s2d_cp=0):
         return tab.add(w, d1, d0, kh, 1, d1, dtype, fold_kw=kw, fold_flip=True)
     if kind == "fwd_kwn":              # filter column in GEMM-N (conv_tail7.cu): rows = (kw, dim0), cols = dim1, taps = kh
         return tab.add(w, d0, d1, kh, d1, 1, dtype, fold_kw=kw, fold_flip=2)
+    if kind == "dgrad_kwn":            # the same for the data gradient: rows = (kw, dim1), cols = dim0
+        return tab.add(w, d1, d0, kh, 1, d1, dtype, fold_kw=kw, fold_flip=2)
     raise ValueError(kind)
 
 

@@ -119,7 +119,10 @@ int dtg_pack_weights(const dtg_pack_item* items_dev, int nitems, int max_elems, 
  * per pixel, width a divisor of 128, out_nchw_f32): the filter COLUMN goes into GEMM-N -- `w` is the
  * [kh][32][cin] packing of fold_flip = 2, only the KH filter rows are taps (14 tcgen05.mma per 128-pixel tile
  * instead of 98 for 32 -> 3 channels) and the epilogue adds the KW column partials with their pixel shift.
- * This is the forward of the generators' 7x7 tail + tanh (networks.py:187-188, 242-243).
+ * This is the forward of the generators' 7x7 tail + tanh (networks.py:187-188, 242-243).  With mode DGRAD (ring == pad,
+ * `out` a 16-byte-pixel plane with halo == ring, `w` = [kh][(kw, cin) padded to 32][cout]) the same kernel computes the
+ * data gradient of the generators' 7x7 HEAD w.r.t. its reflect-padded input (networks.py:159-160, 211-212): the "full"
+ * correlation, (h + kh - 1) x (w + kw - 1) outputs per image, taps and column shifts mirrored.
  * ------------------------------------------------------------------------------------------- */
 typedef struct dtg_conv_args {
   int32_t mode; /* DTG_CONV_FWD / DTG_CONV_DGRAD */

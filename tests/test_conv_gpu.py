@@ -126,6 +126,35 @@ def test_conv_tail_filter_column_in_gemm_n(n, cin, cout, h, w, k, dtype):
     assert _relerr(y, y2) < 1e-4
 
 
+@pytest.mark.parametrize("dtype", [torch.bfloat16, torch.float32])
+@pytest.mark.parametrize("n,cin,cout,h,w,k", [(2, 3, 32, 64, 64, 7), (160, 3, 32, 64, 64, 7), (3, 1, 32, 33, 32, 7), (2, 4, 16, 24, 16, 5)])
+def test_conv_head_dgrad_filter_column_in_gemm_n(n, cin, cout, h, w, k, dtype):
+    """dtg_conv fold_w = 2, DGRAD (conv_tail7.cu, full mode): gradient of the generators' 7x7 head (networks.py:159-160,
+    211-212) w.r.t. its reflect-PADDED input -- every pixel of the haloed 16-byte-pixel plane -- against the transposed
+    convolution in fp64, and against the tap-per-MMA mapping"""
+    g = torch.Generator().manual_seed(13)
+    pad = k // 2
+    dy = _q(torch.randn(n, cout, h, w, generator=g), dtype).to(DEV)
+    wt = _q(torch.randn(cout, cin, k, k, generator=g) * 0.05, dtype).to(DEV)
+    dyp = ops.PlaneT.from_nchw(dy, dtype=dtype)
+    cs = ops.cpad_small(cin, dtype)
+    if not ops.tail_kwn_eligible(dyp.c, k, cin, w, dtype):
+        pytest.skip("patch stages do not fit")
+    wp = ops.pack_conv_weight(wt, dtype, "dgrad_kwn")
+    dx = ops.PlaneT(n, h, w, cs, pad, dtype)
+    dx.t.fill_(float("nan"))
+    ops.conv(dyp, wp, None, dx, mode=L.CONV_DGRAD, kh=k, kw=k, pad=pad, ring=pad, cout=cin, out_h=h, out_w=w, fold_w=2)
+    ref = F.conv_transpose2d(dy.double(), wt.double()).float()                     # [n, cin, h + k - 1, w + k - 1]
+    got = dx.t.permute(0, 3, 1, 2).float()
+    assert torch.isfinite(got).all()
+    assert _relerr(got[:, :cin], ref) < _tol(dtype)
+    assert float(got[:, cin:].abs().max()) == 0.0 if cs > cin else True
+    dx2 = ops.PlaneT(n, h, w, cs, pad, dtype)
+    ops.conv(dyp, ops.pack_conv_weight(wt, dtype, "dgrad"), None, dx2, mode=L.CONV_DGRAD, kh=k, kw=k, pad=pad, ring=pad, cout=cin,
+             out_h=h, out_w=w)
+    assert _relerr(got[:, :cin], dx2.t.permute(0, 3, 1, 2).float()[:, :cin]) < (1e-2 if dtype == torch.bfloat16 else 1e-3)   # both outputs are rounded to the plane's precision
+
+
 DGRAD_CASES = [
     # n, cin, cout, h(in), k, s, pad, ring
     (2, 128, 128, 32, 3, 1, 1, 0),
