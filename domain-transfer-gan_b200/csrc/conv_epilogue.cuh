@@ -53,6 +53,7 @@ struct IgemmParams {
   int n_umma;  // = packed weight rows per tap
   int stages;
   int tmem_cols;
+  int flat_dgrad;   // DGRAD whose dy plane carries a zero halo == ring: conv_patch2.cu's flat-raster mode (set by dtg_conv)
   EpiParams e;
 };
 

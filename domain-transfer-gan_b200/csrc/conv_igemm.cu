@@ -389,7 +389,9 @@ extern "C" int dtg_conv(const dtg_conv_args* a, const dtg_plane* in, const void*
     PW = OWl;
     PH = OHl;
   } else if (a->mode == DTG_CONV_DGRAD) {
-    DTG_REQUIRE(hl == 0, "dtg_conv dgrad: input gradient plane must have halo 0");
+    // halo 0, or a ZERO halo ring equal to `ring` (stride 1): the flat-raster path of conv_patch2.cu then reads the ring as
+    // the convolution's padding and tiles the (h + 2 ring) x (w + 2 ring) outputs of all images as one tall image
+    DTG_REQUIRE(hl == 0 || (hl == a->ring && s == 1), "dtg_conv dgrad: input gradient plane must have halo 0 (or a zero halo == ring)");
     DTG_REQUIRE((OHl + 2 * a->pad - a->kh) / s + 1 == in->h && (OWl + 2 * a->pad - a->kw) / s + 1 == in->w,
                 "dtg_conv dgrad: output extent %dx%d inconsistent with dy %dx%d k%d s%d p%d", OHl, OWl, in->h, in->w, a->kh, s, a->pad);
     const int R = a->ring;
@@ -479,6 +481,13 @@ extern "C" int dtg_conv(const dtg_conv_args* a, const dtg_plane* in, const void*
   DTG_REQUIRE(a->act != DTG_ACT_TANH || a->out_nchw_f32, "dtg_conv: tanh is only fused into dense NCHW head outputs");
   if (a->out_reflect && !a->out_nchw_f32)
     DTG_REQUIRE(p.e.out_H >= 2 * p.e.out_halo + 2 && p.e.out_W >= 2 * p.e.out_halo + 2, "dtg_conv: reflect halo %d too wide for %dx%d", p.e.out_halo, p.e.out_H, p.e.out_W);
+  if (a->mode == DTG_CONV_DGRAD && hl > 0 && !a->fold_w) {
+    p.flat_dgrad = 1;
+    const int rc2 = try_launch_pconv2(p, in, w, w_rows, w_cols, a->kh * a->kw, static_cast<cudaStream_t>(stream));
+    DTG_REQUIRE(rc2 != 1, "dtg_conv dgrad: a haloed dy plane needs the flat-raster path (full 128-byte channel chunks, <= 128 "
+                          "output channels, output plane with the same halo, n * (h + 2 halo) * (w + 2 halo) divisible by 8)");
+    return rc2;
+  }
   {
     const int rc = try_launch_pconv(p, in, w, w_rows, w_cols, a->fold_w ? a->kh : a->kh * a->kw, a->fold_w,
                                     static_cast<cudaStream_t>(stream));

@@ -7,6 +7,11 @@
 // patches (one TMA box per tile and 64-channel chunk, every tap a row-shifted UMMA window, as in conv_patch.cu) stay
 // resident while each (chunk, tap) weight block streams through a small ring ONCE and feeds both tiles' accumulators:
 // (2 x 46 KB + 295 KB) / 2 = 194 KB of L2 traffic per tile, under the ceiling for 72 MMAs of 64 clk.
+// Flat-raster mode (the data gradient w.r.t. a reflect-padded input, ring > 0): dy carries a ZERO halo ring equal to the
+// ring, so its buffer [n][h+2r][w+2r][c] has the same raster as the output buffer.  A tile is then 128 CONSECUTIVE buffer
+// pixels of the tall n*(h+2r) x (w+2r) image (722 tiles instead of 1200 for 80 x 34 x 34), its patch the 128 + 2*(w+2r+1)
+// pixels around it (one 2-D TMA box, out-of-range = zero fill), every tap the window shifted by dh*(w+2r) + dw pixels
+// (row wrap-around lands in the zero ring = the padding), 8-row groups contiguous, and the tile leaves as 4 x 32 pixels.
 // Warp roles: warp0 TMA producer, warp1 MMA issuer (+TMEM alloc), warps2-5 epilogue; two TMEM accumulator sets.
 #include <algorithm>
 #include <cstdlib>
@@ -32,6 +37,10 @@ struct Pconv2Params {
   unsigned char tap_w[kMaxTaps];
   int kchunks, n_umma, b_stage_bytes;
   int a_units, b_stages, tmem_cols;
+  int flat;              // flat-raster mode
+  int lead;              // flat: patch starts `lead` pixels before the tile's first pixel
+  int a_tx;              // bytes of one patch unit
+  int a_sbo;             // byte stride between 8-row groups of the A window (patch pitch * 128, flat: 1024)
   int dbg;   // DTG_P2_DBG experiments: 1 skip weight loads, 2 skip patch loads, 4 skip epilogue
   EpiParams e;
 };
@@ -89,7 +98,7 @@ __global__ void __launch_bounds__(kThreads, 1) pconv2_kernel(const __grid_consta
 
   const int tiles_per_img = p.tiles_w * p.tiles_h;
   const int items = p.items;
-  const uint32_t a_tx = static_cast<uint32_t>(p.PW) * p.PH * kRowBytes;
+  const uint32_t a_tx = static_cast<uint32_t>(p.a_tx);
   const uint32_t b_tx = static_cast<uint32_t>(p.b_stage_bytes);
 
   if (warp == 0) {
@@ -110,7 +119,10 @@ __global__ void __launch_bounds__(kThreads, 1) pconv2_kernel(const __grid_consta
             if (elect_one()) mbar_arrive(&bar_afull[au]);
           } else if (elect_one()) {
             mbar_expect_tx(&bar_afull[au], a_tx);
-            tma_load_4d(sA + au * p.a_unit_bytes, &p.tmA, &bar_afull[au], kc * KC, tw * kP2W + p.org_w, th * kP2H + p.org_h, n);
+            if (p.flat)
+              tma_load_2d(sA + au * p.a_unit_bytes, &p.tmA, &bar_afull[au], kc * KC, tile * kTileM - p.lead);
+            else
+              tma_load_4d(sA + au * p.a_unit_bytes, &p.tmA, &bar_afull[au], kc * KC, tw * kP2W + p.org_w, th * kP2H + p.org_h, n);
           }
           __syncwarp();
           if (++au == AU) {
@@ -137,7 +149,7 @@ __global__ void __launch_bounds__(kThreads, 1) pconv2_kernel(const __grid_consta
   } else if (warp == 1) {
     // ===================== MMA issuer (warp-uniform; tcgen05 instructions behind elect.sync) =====================
     const uint32_t idesc = umma_idesc(TF32 ? 2u : 1u, 0u, 0u, kTileM, p.n_umma);
-    const uint32_t a_hi = ((static_cast<uint32_t>(p.PW) * kRowBytes) >> 4) | (1u << 14) | (2u << 29);
+    const uint32_t a_hi = (static_cast<uint32_t>(p.a_sbo) >> 4) | (1u << 14) | (2u << 29);
     const uint32_t b_hi = (1024u >> 4) | (1u << 14) | (2u << 29);
     int au = 0, bs = 0;
     uint32_t aph = 0, bph = 0;
@@ -218,7 +230,9 @@ __global__ void __launch_bounds__(kThreads, 1) pconv2_kernel(const __grid_consta
         const int r = tile - n * tiles_per_img;
         const int th = r / p.tiles_w, tw = r - th * p.tiles_w;
         const uint32_t taddr = tmem_base + (static_cast<uint32_t>(quad * 32) << 16) + (set * 2 + mt) * p.n_umma;
-        if (p.e.use_tma) {
+        if (p.flat) {      // tmOut views the output buffer as [c][8][pixels / 8]: this warp's 32 pixels are 4 rows of it
+          epilogue_tma<TF32>(p.e, taddr, 0, (tile * kTileM + 32 * quad) >> 3, 0, sbase, cnt, lane);
+        } else if (p.e.use_tma) {
           epilogue_tma<TF32>(p.e, taddr, tw * kP2W, th * kP2H + 4 * quad, n, sbase, cnt, lane);
         } else {
           const int a = th * kP2H + ih, b = tw * kP2W + iw;
@@ -266,12 +280,28 @@ int try_launch_pconv2(const IgemmParams& g, const dtg_plane* in, const void* w, 
     dw_min = std::min<int>(dw_min, g.tap_dw[t]);
     dw_max = std::max<int>(dw_max, g.tap_dw[t]);
   }
-  const int PW = kP2W + dw_max - dw_min, PH = kP2H + dh_max - dh_min;
+  const int OHp = g.ph_OH[0], OWp = g.ph_OW[0];
+  // flat-raster mode: dy with a zero halo == ring, output plane with the same halo (identical buffer rasters)
+  const int hd = g.flat_dgrad ? in->halo : 0;
+  const bool flat = g.flat_dgrad != 0;
+  const int Wr = in->w + 2 * hd, Hr = in->h + 2 * hd;
+  const long long flat_px = static_cast<long long>(in->n) * Hr * Wr;
+  int lead = 0;
+  if (flat) {
+    if (g.e.out_nchw || g.e.out_reflect || g.e.act == DTG_ACT_TANH || g.e.out_halo != hd || g.e.out_H != in->h || g.e.out_W != in->w ||
+        g.e.out_C * es % kRowBytes != 0 || OHp != Hr || OWp != Wr || g.ph_oh0[0] != -hd || g.ph_ow0[0] != -hd || flat_px % 8 != 0 ||
+        flat_px > (1ll << 30))
+      return 1;
+    for (int t = 0; t < ntaps; ++t) lead = std::max(lead, std::abs((g.tap_dh[t] + hd) * Wr + g.tap_dw[t] + hd));
+    if (kTileM + 2 * lead > 256) return 1;
+  }
+  const int PW = flat ? 1 : kP2W + dw_max - dw_min, PH = flat ? kTileM + 2 * lead : kP2H + dh_max - dh_min;
   const int a_unit_bytes = (PW * PH * kRowBytes + 1023) & ~1023;
   const int b_stage_bytes = g.n_umma * kRowBytes;
-  const int OHp = g.ph_OH[0], OWp = g.ph_OW[0];
-  if (OWp < kP2W || OHp < 8 || PW > 256 || PH > 256) return 1;
-  if (OWp % kP2W != 0 || OHp % kP2H != 0) return 1;     // ragged 8x16 tilings (e.g. 34x34 ring outputs) waste > 40 % of the MMAs
+  if (!flat) {
+    if (OWp < kP2W || OHp < 8 || PW > 256 || PH > 256) return 1;
+    if (OWp % kP2W != 0 || OHp % kP2H != 0) return 1;     // ragged 8x16 tilings (e.g. 34x34 ring outputs) waste > 40 % of the MMAs
+  }
   const int epi = 4 * std::max(kEpiWarpBytes, kEpiTmaWarpBytes);
   const int budget = tensor_smem_budget() - 1024 - 1024 - epi;
   // ring sizes: at least the 2*kchunks patch units of one item plus one to prefetch; 3-4 weight stages
@@ -291,14 +321,19 @@ int try_launch_pconv2(const IgemmParams& g, const dtg_plane* in, const void* w, 
   p.org_w = dw_min;
   p.tiles_w = (OWp + kP2W - 1) / kP2W;
   p.tiles_h = (OHp + kP2H - 1) / kP2H;
-  p.total_tiles = p.tiles_w * p.tiles_h * g.N;
+  p.total_tiles = flat ? static_cast<int>((flat_px + kTileM - 1) / kTileM) : p.tiles_w * p.tiles_h * g.N;
+  p.flat = flat ? 1 : 0;
+  p.lead = lead;
+  p.a_tx = PW * PH * kRowBytes;
+  p.a_sbo = flat ? 1024 : PW * kRowBytes;
   p.OHp = OHp;
   p.OWp = OWp;
   p.oh0 = g.ph_oh0[0];
   p.ow0 = g.ph_ow0[0];
   p.ntaps = ntaps;
   for (int t = 0; t < ntaps; ++t) {
-    p.a_off[t] = static_cast<unsigned short>((((g.tap_dh[t] - dh_min) * PW + (g.tap_dw[t] - dw_min)) * kRowBytes) >> 4);
+    const int rows = flat ? lead + (g.tap_dh[t] + hd) * Wr + g.tap_dw[t] + hd : (g.tap_dh[t] - dh_min) * PW + (g.tap_dw[t] - dw_min);
+    p.a_off[t] = static_cast<unsigned short>((rows * kRowBytes) >> 4);
     p.tap_w[t] = g.tap_w[t];
   }
   p.kchunks = kchunks;
@@ -315,7 +350,17 @@ int try_launch_pconv2(const IgemmParams& g, const dtg_plane* in, const void* w, 
     const int rowb = std::min(p.e.out_C * es, 128);
     const bool pow2 = rowb == 32 || rowb == 64 || rowb == 128;
     static const bool no_tma_epi = getenv("DTG_NO_TMA_EPI") != nullptr;
-    if (!no_tma_epi && !p.e.out_nchw && !p.e.out_reflect && p.e.act != DTG_ACT_TANH && pow2 && (p.e.out_C * es) % rowb == 0) {
+    if (flat) {
+      // the whole output buffer as [c][8][pixels / 8]: a {row, 8, 4, 1} box is 32 consecutive pixels
+      uint64_t dims[4] = {static_cast<uint64_t>(p.e.out_C), 8ull, static_cast<uint64_t>(flat_px / 8), 1ull};
+      uint64_t strides[3] = {static_cast<uint64_t>(p.e.out_C) * es, static_cast<uint64_t>(p.e.out_C) * es * 8,
+                             static_cast<uint64_t>(p.e.out_C) * es * static_cast<uint64_t>(flat_px)};
+      uint32_t box[4] = {static_cast<uint32_t>(rowb / es), 8u, 4u, 1u};
+      int rc = encode_tiled(&p.e.tmOut, in->dtype, 4, p.e.out, dims, strides, box, 1);
+      if (rc != DTG_OK) return rc;
+      p.e.use_tma = 1;
+      p.e.row_bytes = rowb;
+    } else if (!no_tma_epi && !p.e.out_nchw && !p.e.out_reflect && p.e.act != DTG_ACT_TANH && pow2 && (p.e.out_C * es) % rowb == 0) {
       const int oh_ = p.e.out_halo, Hb_ = p.e.out_H + 2 * oh_, Wb_ = p.e.out_W + 2 * oh_;
       uint8_t* base = reinterpret_cast<uint8_t*>(p.e.out) + (static_cast<size_t>(p.oh0 + oh_) * Wb_ + (p.ow0 + oh_)) * p.e.out_C * es;
       uint64_t dims[4] = {static_cast<uint64_t>(p.e.out_C), static_cast<uint64_t>(OWp), static_cast<uint64_t>(OHp),
@@ -332,7 +377,13 @@ int try_launch_pconv2(const IgemmParams& g, const dtg_plane* in, const void* w, 
 
   const int hl = in->halo;
   const int Hb = in->h + 2 * hl, Wb = in->w + 2 * hl;
-  {
+  if (flat) {
+    uint64_t dims[2] = {static_cast<uint64_t>(in->c), static_cast<uint64_t>(flat_px)};
+    uint64_t strides[1] = {static_cast<uint64_t>(in->c) * es};
+    uint32_t box[2] = {static_cast<uint32_t>(kRowBytes / es), static_cast<uint32_t>(PH)};
+    int rc = encode_tiled(&p.tmA, in->dtype, 2, in->ptr, dims, strides, box, 1);
+    if (rc != DTG_OK) return rc;
+  } else {
     uint64_t dims[4] = {static_cast<uint64_t>(in->c), static_cast<uint64_t>(Wb), static_cast<uint64_t>(Hb), static_cast<uint64_t>(in->n)};
     uint64_t strides[3] = {static_cast<uint64_t>(in->c) * es, static_cast<uint64_t>(Wb) * in->c * es,
                            static_cast<uint64_t>(Hb) * Wb * in->c * es};

@@ -323,7 +323,7 @@ static int make_plan(const dtg_wgrad_args* a, const dtg_plane* pp, const dtg_pla
   DTG_REQUIRE(a->stride == 1 || a->stride == 2, "wgrad: stride");
   const int fold = a->fold;
   DTG_REQUIRE(fold >= 0 && fold <= 2, "wgrad: bad fold mode");
-  DTG_REQUIRE(fold == 2 || pp->halo == 0, "wgrad: p plane must have halo 0");
+  // p (the output gradient) may carry a halo ring (ignored: the tensor map views the interior); fold 2 reads its own zero halo
   if (fold) {
     const int es_ = tf32 ? 4 : 2;
     DTG_REQUIRE(a->stride == 1 && a->kw <= 8, "wgrad fold: stride 1 and kw <= 8 only");
@@ -510,11 +510,13 @@ extern "C" int dtg_conv_wgrad(const dtg_wgrad_args* a, const dtg_plane* pp, cons
     rc = encode_tiled(&p.tmP, pp->dtype, 4, base, dims, strides, box, tf32 ? 2 : 1);
     if (rc != DTG_OK) return rc;
   } else {
+    const int hp = pp->halo, Hp = pp->h + 2 * hp, Wp = pp->w + 2 * hp;      // interior view of a haloed plane
+    uint8_t* base = reinterpret_cast<uint8_t*>(pp->ptr) + (static_cast<size_t>(hp) * Wp + hp) * pp->c * es;
     uint64_t dims[4] = {static_cast<uint64_t>(pp->c), static_cast<uint64_t>(pp->w), static_cast<uint64_t>(pp->h),
                         static_cast<uint64_t>(pp->n)};
-    uint64_t strides[3] = {static_cast<uint64_t>(pp->c) * es, static_cast<uint64_t>(pp->w) * pp->c * es,
-                           static_cast<uint64_t>(pp->h) * pp->w * pp->c * es};
-    rc = encode_tiled(&p.tmP, pp->dtype, 4, pp->ptr, dims, strides, box, tf32 ? 2 : 1);
+    uint64_t strides[3] = {static_cast<uint64_t>(pp->c) * es, static_cast<uint64_t>(Wp) * pp->c * es,
+                           static_cast<uint64_t>(Hp) * Wp * pp->c * es};
+    rc = encode_tiled(&p.tmP, pp->dtype, 4, base, dims, strides, box, tf32 ? 2 : 1);
     if (rc != DTG_OK) return rc;
   }
   const int Hb = q->h + 2 * hl, Wb = q->w + 2 * hl;

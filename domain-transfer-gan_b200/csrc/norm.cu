@@ -523,7 +523,7 @@ extern "C" int dtg_norm_bwd(const dtg_norm_args* a, const dtg_plane* dy, const d
   const int mode = a->mode;
   DTG_REQUIRE(mode == DTG_NORM_NONE || (x && x->ptr && stats && gamma), "dtg_norm_bwd: missing saved tensors");
   DTG_REQUIRE(a->act == DTG_ACT_NONE || (y && y->ptr), "dtg_norm_bwd: activation needs saved output");
-  DTG_REQUIRE(dx->halo == 0 && dx->n == dy->n && dx->h == dy->h && dx->w == dy->w && dx->c == dy->c && dx->dtype == dy->dtype,
+  DTG_REQUIRE(dx->halo >= 0 && dx->n == dy->n && dx->h == dy->h && dx->w == dy->w && dx->c == dy->c && dx->dtype == dy->dtype,
               "dtg_norm_bwd: dx / dy mismatch");
   DTG_REQUIRE(!x || !x->ptr || (x->halo == 0 && x->c == dx->c && x->h == dx->h), "dtg_norm_bwd: x mismatch");
   DTG_REQUIRE(!dy2 || !dy2->ptr || (dy2->c == dx->c && dy2->h == dx->h && dy2->halo == 0), "dtg_norm_bwd: dy2 mismatch");
@@ -564,6 +564,8 @@ extern "C" int dtg_norm_bwd(const dtg_norm_args* a, const dtg_plane* dy, const d
     if (rc == 1) rc = try_norm_bwd_tma(a, dy, dy2, y, &p_x, stats, gamma, sums_buf, dx, d_res, stream);
     if (rc == 1) rc = try_norm_bwd_fused(a, dy, dy2, y, &p_x, stats, gamma, sums_buf, dx, d_res, stream);
     if (rc < 0) return rc;
+    DTG_REQUIRE(rc == 0 || dx->halo == 0, "dtg_norm_bwd: a dx plane with a halo needs the register-resident cluster kernel "
+                                          "(instance / activation-only layer, <= 1024 pixels per slab, norm_impl 0 or 2)");
     if (rc == 0) {
       if (!defer_channel && mode != DTG_NORM_COND_INSTANCE && (d_beta || d_gamma)) {
         DTG_CHECK_CUDA(launch_k(norm_bwd_channel_kernel, (c + 31) / 32, 256, 0, stream, sums_buf, n, c, mode, bnsum, d_gamma, d_beta));
@@ -571,6 +573,7 @@ extern "C" int dtg_norm_bwd(const dtg_norm_args* a, const dtg_plane* dy, const d
       return DTG_OK;
     }
   }
+  DTG_REQUIRE(dx->halo == 0, "dtg_norm_bwd: a dx plane with a halo is not supported for this mode / phase");
   if ((a->phase == 0 || a->phase == 1) && need_reduce) {
     dim3 grid(c / cg, n, splits);
     if (bf)

@@ -317,7 +317,10 @@ __global__ void __launch_bounds__(NT, 512 / NT) norm_bwd_reg_kernel(dtg_plane dy
                              : nullptr;
   const uint8_t* dy2b = dy2.ptr ? reinterpret_cast<const uint8_t*>(dy2.ptr) + (static_cast<size_t>(n) * hw * dy2.c + c) * es
                                 : nullptr;
-  uint8_t* dxb = reinterpret_cast<uint8_t*>(dx.ptr) + (static_cast<size_t>(n) * hw * dx.c + c) * es;
+  // dx may carry a (zero) halo ring that this kernel never writes: the flat-raster dgrad of conv_patch2.cu reads it as padding
+  const int hdx = dx.halo, wdx = dx.w + 2 * hdx;
+  uint8_t* dxb = reinterpret_cast<uint8_t*>(dx.ptr) +
+                 ((static_cast<size_t>(n) * (dx.h + 2 * hdx) * wdx + static_cast<size_t>(hdx) * wdx + hdx) * dx.c + c) * es;
   uint8_t* drb = dres.ptr ? reinterpret_cast<uint8_t*>(dres.ptr) + (static_cast<size_t>(n) * hw * dres.c + c) * es : nullptr;
   if (dbg & 2) drb = nullptr;
 
@@ -451,7 +454,8 @@ __global__ void __launch_bounds__(NT, 512 / NT) norm_bwd_reg_kernel(dtg_plane dy
       float o[V];
 #pragma unroll
       for (int i = 0; i < V; ++i) o[i] = k0[i] * (g[j][i] - kA[i] - xh[j][i] * kB[i]);
-      if (!(dbg & 4)) Vec<T>::store(dxb + p * pitch, o);
+      const size_t po = hdx ? static_cast<size_t>(p / x.w) * wdx + (p % x.w) : static_cast<size_t>(p);
+      if (!(dbg & 4)) Vec<T>::store(dxb + po * pitch, o);
     }
     p += lanes;
   }
@@ -580,6 +584,11 @@ int try_norm_bwd_fused(const dtg_norm_args* a, const dtg_plane* dy, const dtg_pl
   static const int dbgv = getenv("DTG_NORM_DBG") ? atoi(getenv("DTG_NORM_DBG")) : 0;
   const dim3 rgrid(g.reg_cblocks, x->n, g.reg_cs);
   const bool reg_ok = dy->halo == 0 || (dy->halo == 1 && dy->h >= 4 && dy->w >= 4);
+  if (dx->halo > 0 && !(g.reg_cs > 0 && !no_reg && reg_ok)) {
+    set_error("norm_bwd: a dx plane with a halo is only supported by the register-resident kernel (<= %d pixels per slab)",
+              8 * (g.reg_nt / g.reg_nv) * kRegPPT);
+    return DTG_ERR_INVALID;
+  }
 #define DTG_REG_LAUNCH(TT, AA, NTV)                                                                                     \
   do {                                                                                                                  \
     if (hal)                                                                                                            \

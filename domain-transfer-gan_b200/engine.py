@@ -21,6 +21,7 @@ S2D = os.environ.get("DTG_NO_S2D") is None      # space-to-depth execution of th
 # tensor-core path (fwd 52 vs 44 us, dgrad 49 vs 55 us, wgrad 68 vs 59 us at batch 160; step time unchanged), so the
 # tensor-core path stays the default and this is opt-in
 HEAD1 = os.environ.get("DTG_HEAD1") is not None
+FLAT_DGRAD = os.environ.get("DTG_NO_FLAT_DGRAD") is None      # haloed dy planes for the reflect-ring data gradients (conv_patch2.cu flat mode)
 OFFCHAIN_SMALL = os.environ.get("DTG_NO_OFFCHAIN_SMALL") is None      # parameter-gradient reductions of the norm layers on the companion stream
 TAIL_KWN = os.environ.get("DTG_NO_TAIL_KWN") is None      # generators' 7x7 tail forward with (kw, cout) in GEMM-N (conv_tail7.cu)
 
@@ -292,7 +293,16 @@ class NetExec:
                     c.cin[i] = (torch.zeros(n, cs, device=dev), torch.zeros(n, cs, device=dev))
             else:
                 c.nst[i] = ops.NormState(c.acts[i + 1])
-            c.dyraw[i] = ops.PlaneT(n, oh, ow, cs, 0, dt, dev)
+            # gradient w.r.t. the conv output.  For a stride-1 'same' conv over a reflect-padded input (the residual stack)
+            # it gets a ZERO halo ring = the ring of the data gradient: the flat-raster dgrad then reads the ring as padding
+            # (722 instead of 1200 tiles at 80 x 32 x 32).  Its producer must be the register-resident norm backward
+            # (<= 1024 pixels per slab), which leaves the ring untouched; the weight gradient views the interior.
+            src_halo = c.acts[ly.src].halo
+            flat = (FLAT_DGRAD and not ly.transposed and ly.stride == 1 and 2 * ly.pad == ly.k - 1 and ly.pad >= 1 and
+                    src_halo == ly.pad and not (ly.src == 0 and c.s2d_cp) and oh * ow <= 1024 and
+                    ly.norm in (L.NORM_NONE, L.NORM_INSTANCE, L.NORM_COND_INSTANCE) and
+                    ops.flat_dgrad_eligible(n, oh, ow, cs, c.acts[ly.src].c, ly.pad, dt))
+            c.dyraw[i] = ops.PlaneT(n, oh, ow, cs, ly.pad if flat else 0, dt, dev)
         c.dims = dims
         if self.nz:
             c.z = torch.zeros(n, self.nz, dtype=torch.float32, device=dev)

@@ -328,6 +328,22 @@ def conv(x, wp, bias, out, *, mode=L.CONV_FWD, kh, kw, stride=1, pad=0, ring=0, 
     L.check(rc, "conv")
 
 
+def flat_dgrad_eligible(n, h, w, c_dy, c_dx, ring, dtype):
+    """geometry test of the flat-raster data gradient of conv_patch2.cu (dtg_conv DGRAD with a dy plane whose ZERO halo equals
+    the ring): full 128-byte channel chunks on both sides, <= 128 output channels, a patch of 128 + 2 * (w + 2 ring + 1)
+    pixels <= 256, two patch units per chunk plus three weight stages in 227 KB, pixel count divisible by 8"""
+    es = 2 if dtype == torch.bfloat16 else 4
+    wr, hr = w + 2 * ring, h + 2 * ring
+    if ring < 1 or (c_dy * es) % 128 or (c_dx * es) % 128 or c_dx > 128 or (n * hr * wr) % 8:
+        return False
+    rows = 128 + 2 * (wr + 1)
+    if rows > 256:
+        return False
+    unit = (rows * 128 + 1023) // 1024 * 1024
+    kchunks = c_dy * es // 128
+    return 2 * kchunks * unit + 3 * c_dx * 128 + 2048 + 4 * 9 * 1024 <= 227 * 1024
+
+
 def tail_kwn_eligible(cin_stored, k, cout, w, dtype):
     """geometry test of dtg_conv fold_w = 2 (conv_tail7.cu: try_launch_tail7) for a k x k 'same' head on a halo-free plane
     with cin_stored channels and image width w: row bytes 32 / 64 / 128, (kw, cout) <= 28 GEMM columns, the width a divisor

@@ -216,7 +216,9 @@ int dtg_norm_fwd(const dtg_norm_args* a, const dtg_plane* x, const dtg_plane* re
  *   sums   : out [n][c][2] fp32: (sum g, sum g*xhat) per (n,c)  -> COND_INSTANCE d_shift/d_scale;
  *            INSTANCE / BATCH / NONE additionally accumulate d_beta[c] += sum_n, d_gamma[c] += sum_n
  *            (NONE: d_beta only = bias gradient of the preceding conv)
- *   dx     : out plane (halo 0); d_res: optional out plane (halo 0)
+ *   dx     : out plane; halo 0, or (instance / cond-instance / activation-only layers of <= 1024 pixels) a halo whose ring
+ *            is left untouched -- dtg_conv's flat-raster DGRAD reads a zero ring of dy as the convolution's padding;
+ *            d_res: optional out plane (halo 0)
  *   phase  : as in forward (BATCH: 1 leaves per-channel sums in `partial` for all-reduce);
  *            INSTANCE / NONE only: 4 = everything except the d_gamma / d_beta accumulation, 3 = that accumulation
  *            alone from the sums the phase-4 call left (same arguments; lets the caller issue the small

@@ -190,6 +190,33 @@ def test_conv_dgrad(case, dtype):
     assert _relerr(got, ref) < _tol(dtype), (case, _relerr(got, ref))
 
 
+@pytest.mark.parametrize("n,c,h", [(2, 128, 32), (80, 128, 32), (4, 128, 16), (4, 64, 20)])
+def test_conv_dgrad_flat_raster(n, c, h):
+    """dtg_conv DGRAD with a dy plane whose zero halo equals the ring (conv_patch2.cu flat mode): the gradient w.r.t. the
+    reflect-padded input of the residual-stack convs (modules.py:162,180,211,227), all images tiled as one tall image;
+    against autograd in fp64 and against the per-tap kernel on a halo-free dy"""
+    dtype = torch.bfloat16
+    g = torch.Generator().manual_seed(17)
+    dy = _q(torch.randn(n, c, h, h, generator=g), dtype).to(DEV)
+    wt = _q(torch.randn(c, c, 3, 3, generator=g) * 0.05, dtype).to(DEV)
+    wp = ops.pack_conv_weight(wt, dtype, "dgrad")
+    assert ops.flat_dgrad_eligible(n, h, h, c, c, 1, dtype)
+    dyh = ops.PlaneT.from_nchw(dy, halo=1, dtype=dtype, reflect=False)          # zero ring
+    assert float(dyh.t[:, 0].abs().max()) == 0.0 and float(dyh.t[:, :, -1].abs().max()) == 0.0
+    dx = ops.PlaneT(n, h, h, c, 1, dtype)
+    dx.t.fill_(float("nan"))
+    ops.conv(dyh, wp, None, dx, mode=L.CONV_DGRAD, kh=3, kw=3, pad=1, ring=1, cout=c, out_h=h, out_w=h)
+    xin = torch.zeros(n, c, h + 2, h + 2, device=DEV, dtype=torch.float64, requires_grad=True)
+    F.conv2d(xin, wt.double()).backward(dy.double())
+    got = dx.t.permute(0, 3, 1, 2).float()
+    assert torch.isfinite(got).all()
+    assert _relerr(got, xin.grad.float()) < _tol(dtype)
+    dx0 = ops.PlaneT(n, h, h, c, 1, dtype)
+    ops.conv(ops.PlaneT.from_nchw(dy, dtype=dtype), wp, None, dx0, mode=L.CONV_DGRAD, kh=3, kw=3, pad=1, ring=1, cout=c, out_h=h,
+             out_w=h)
+    assert _relerr(dx.t.float(), dx0.t.float()) < 1e-2         # same products, different fp32 summation order, bf16 outputs
+
+
 def test_conv_transpose_forward():
     """ConvTranspose2d(128->64, k3, s2, p1, op1) forward = DGRAD mode with the 'tfwd' packing."""
     dtype = torch.bfloat16

@@ -134,6 +134,45 @@ def test_norm_fwd_bwd(mode, act, residual, halo, shape, dtype, tma):
         assert _rel(dbet, gsum) < gtol
 
 
+@pytest.mark.parametrize("mode,residual", [(L.NORM_INSTANCE, True), (L.NORM_COND_INSTANCE, False), (L.NORM_NONE, False)])
+def test_norm_bwd_into_a_haloed_dx_plane(mode, residual):
+    """dtg_norm_bwd with a dx plane that carries a halo ring (register-resident cluster kernel): the interior equals the
+    halo-free call bit for bit and the ring is left untouched (the flat-raster dgrad reads it as zero padding)"""
+    g = torch.Generator().manual_seed(6)
+    n, c, h, dt = 5, 128, 32, torch.bfloat16
+    x = ops.PlaneT(n, h, h, c, 0, dt); x.t.copy_(torch.randn(n, h, h, c, generator=g))
+    out = ops.PlaneT(n, h, h, c, 1, dt)
+    res = ops.PlaneT(n, h, h, c, 1, dt) if residual else None
+    if res is not None:
+        res.t.copy_(torch.randn(n, h + 2, h + 2, c, generator=g))
+    st = ops.NormState(x)
+    gshape = (n, c) if mode == L.NORM_COND_INSTANCE else (c,)
+    gamma, beta = torch.rand(*gshape, generator=g).to(DEV) + 0.5, torch.randn(*gshape, generator=g).to(DEV)
+    if mode != L.NORM_NONE:
+        ops.norm_fwd(x, out, st, mode=mode, act=L.ACT_RELU, gamma=gamma, beta=beta, residual=res)
+    else:
+        out.t.copy_(torch.randn(n, h + 2, h + 2, c, generator=g))
+    dy = ops.PlaneT(n, h, h, c, 1, dt); dy.t.copy_(torch.randn(n, h + 2, h + 2, c, generator=g))
+    kw = dict(mode=mode, act=L.ACT_RELU, y=out)
+    if mode != L.NORM_NONE:
+        kw.update(x=x, gamma=gamma)
+    outs = []
+    for halo in (0, 1):
+        dx = ops.PlaneT(n, h, h, c, halo, dt)
+        dx.t.fill_(-2.0)
+        dres = ops.PlaneT(n, h, h, c, 0, dt) if residual else None
+        dg, db = torch.zeros(c, device=DEV), torch.zeros(c, device=DEV)
+        extra = dict(d_gamma=dg, d_beta=db) if mode == L.NORM_INSTANCE else (dict(d_beta=db) if mode == L.NORM_NONE else {})
+        ops.norm_bwd(dy, dx, st, d_res=dres, **kw, **extra)
+        torch.cuda.synchronize()
+        outs.append((dx, dg.clone(), db.clone()))
+    d0, d1 = outs[0][0], outs[1][0]
+    assert torch.equal(d1.t[:, 1:-1, 1:-1], d0.t)
+    ring = d1.t.clone(); ring[:, 1:-1, 1:-1] = -2.0
+    assert float((ring + 2.0).abs().max()) == 0.0
+    assert torch.equal(outs[0][1], outs[1][1]) and torch.equal(outs[0][2], outs[1][2])
+
+
 def test_cin_affine():
     g = torch.Generator().manual_seed(1)
     n, c, nz = 7, 128, 16

@@ -56,6 +56,24 @@ def test_conv_wgrad(case, dtype):
     assert err < 2e-3, (case, err)
 
 
+@pytest.mark.parametrize("dtype", [torch.bfloat16, torch.float32])
+def test_conv_wgrad_reads_the_interior_of_a_haloed_dy(dtype):
+    """the output gradient may live in a plane with a (zero) halo ring (the flat-raster dgrad of conv_patch2.cu wants one):
+    the weight gradient views its interior and is bit-identical to the halo-free call"""
+    g = torch.Generator().manual_seed(4)
+    n, c, h = 3, 128, 32
+    x = _q(torch.randn(n, c, h, h, generator=g), dtype).to(DEV)
+    dy = _q(torch.randn(n, c, h, h, generator=g), dtype).to(DEV)
+    xq = ops.PlaneT.from_nchw(x, halo=1, dtype=dtype)
+    dw0, dw1 = torch.zeros(c, c, 3, 3, device=DEV), torch.zeros(c, c, 3, 3, device=DEV)
+    ops.conv_wgrad(ops.PlaneT.from_nchw(dy, dtype=dtype), xq, dw0, kh=3, kw=3, stride=1, pad=1, pa=c, qb=c)
+    dyh = ops.PlaneT.from_nchw(dy, halo=1, dtype=dtype, reflect=False)
+    dyh.t[:, 0].fill_(7.0)          # the ring must be ignored, whatever it holds
+    dyh.t[:, :, 0].fill_(-3.0)
+    ops.conv_wgrad(dyh, xq, dw1, kh=3, kw=3, stride=1, pad=1, pa=c, qb=c)
+    assert torch.equal(dw0, dw1)
+
+
 def test_conv_transpose_wgrad():
     """ConvTranspose2d weight [ci, co, kh, kw]: p = x (low-res, ci), q = dy (high-res, co)."""
     dtype = torch.bfloat16
