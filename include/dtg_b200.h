@@ -105,7 +105,9 @@ int dtg_pack_weights(const dtg_pack_item* items_dev, int nitems, int max_elems, 
  * is always kh*KW+kw of the underlying correlation (no flipping in memory).
  * in.halo > 0 means the padding is materialised in the halo (must be >= pad for FWD).
  * DGRAD `ring`: also compute `ring` halo rings of the output (gradient w.r.t. a reflect-padded
- * input; the consumer folds them back); out.halo must be >= ring.
+ * input; the consumer folds them back); out.halo must be >= ring.  `in` (dy) has halo 0, or -- stride 1, ring > 0,
+ * full 128-byte channel chunks, <= 128 output channels, out.halo == ring, n*(h+2r)*(w+2r) divisible by 8, w + 2r <= 63 -- a
+ * ZERO halo ring == ring: the flat-raster path (conv_patch2.cu) then tiles all images as one tall image.
  * Output: a plane (dtype of `in`), optionally mirrored into its halo (out_reflect, reflection
  * padding for the next conv), or a dense fp32 NCHW tensor [n][cout][oh][ow] (out_nchw_f32 = 1,
  * cout <= 16).
