@@ -122,3 +122,45 @@ def test_data_parallel_plan_gloo_world2():
     for p in procs:
         p.join(timeout=60)
     assert res == [(0, True), (1, True)]
+
+
+def test_kernel_eligibility_predicates():
+    """the host-side geometry predicates that decide (per context) which planes / packings the engine prepares must agree
+    with the conditions stated in include/dtg_b200.h for dtg_conv fold_w = 2 and the flat-raster DGRAD"""
+    from dtg_b200 import ops
+    bf, f32 = torch.bfloat16, torch.float32
+    # 7x7 tail / head gradient with the filter column in GEMM-N: 32 stored channels, cout <= 4, width divides 128
+    assert ops.tail_kwn_eligible(32, 7, 3, 64, bf) and ops.tail_kwn_eligible(32, 7, 1, 128, bf) and ops.tail_kwn_eligible(32, 7, 3, 32, f32)
+    assert not ops.tail_kwn_eligible(32, 7, 3, 128, f32)        # two 114 KB patch stages do not fit
+    assert not ops.tail_kwn_eligible(32, 7, 3, 96, bf)          # width must divide 128
+    assert not ops.tail_kwn_eligible(32, 7, 5, 64, bf)          # (kw, cout) > 28 GEMM columns
+    assert not ops.tail_kwn_eligible(48, 7, 3, 64, bf)          # 96-byte pixels: no matching swizzle
+    assert not ops.tail_kwn_eligible(32, 4, 3, 64, bf)          # even kernel: not a 'same' convolution
+    # flat-raster data gradient of the residual stack: 80 x 32 x 32 x 128 bf16 with ring 1
+    assert ops.flat_dgrad_eligible(80, 32, 32, 128, 128, 1, bf)
+    assert not ops.flat_dgrad_eligible(80, 32, 32, 128, 128, 0, bf)         # no ring: the ordinary tilings are exact
+    assert not ops.flat_dgrad_eligible(80, 64, 64, 128, 128, 1, bf)         # 128 + 2 * 67 rows > one 256-row TMA box
+    assert not ops.flat_dgrad_eligible(3, 16, 16, 128, 128, 1, bf)          # 3 * 18 * 18 pixels not divisible by 8
+    assert not ops.flat_dgrad_eligible(80, 32, 32, 128, 128, 1, f32)        # eight 25 KB patch units do not fit
+    assert not ops.flat_dgrad_eligible(80, 32, 32, 32, 32, 1, bf)           # 64-byte pixels: not full channel chunks
+
+
+def test_n3_extension_module_trees():
+    """N3 on the host: img_size = 64 * 2^k adds k stride-2 stages to LatentEncoder and keeps the reference's
+    keys at 64; honor_n_blocks builds range(n_blocks) residual blocks, the default ignores n_blocks like the reference"""
+    from dtg_b200 import networks
+    bn = networks.get_norm_layer("batch")
+    e64 = networks.LatentEncoder(16, 6, 32, norm_layer=bn)
+    assert [k for k in e64.state_dict() if k.endswith("weight") and "conv_modules" in k][-2:] == ["conv_modules.11.weight", "conv_modules.12.weight"]
+    assert tuple(e64.conv_modules[11].weight.shape) == (256, 256, 4, 4) and e64.n_extra == 0
+    e256 = networks.LatentEncoder(16, 6, 32, norm_layer=bn, img_size=256)
+    assert e256.n_extra == 2 and tuple(e256.conv_modules[11].weight.shape) == (256, 256, 3, 3)
+    assert tuple(e256.conv_modules[17].weight.shape) == (256, 256, 4, 4)
+    with pytest.raises(ValueError):
+        networks.LatentEncoder(16, 6, 32, norm_layer=bn, img_size=96)
+    count = lambda net: len([m for m in net.model if type(m).__name__.endswith("ResnetBlock")])
+    assert count(networks.ResnetGenerator(3, 3, 32, n_blocks=9)) == 3                       # networks.py:225
+    assert count(networks.CINResnetGenerator(16, 3, 3, 32, n_blocks=9)) == 3                # networks.py:173
+    assert count(networks.ResnetGenerator(3, 3, 32, n_blocks=6, honor_n_blocks=True)) == 6
+    g0 = networks.CINResnetGenerator(16, 3, 3, 32, n_blocks=0, honor_n_blocks=True)
+    assert count(g0) == 0 and type(g0.model[10]).__name__ == "ConvTranspose2d"
