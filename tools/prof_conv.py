@@ -42,7 +42,9 @@ elif mode == "fwd":
                          act=int(os.environ.get("PROF_ACT", "0")))
 elif mode == "dgrad":
     wp = ops.pack_conv_weight(w, dt, "dgrad")
-    dy = ops.PlaneT(N, oh, oh, ops.cpad(cout, dt), 0, dt); dy.t.normal_()
+    flat = bool(os.environ.get("PROF_FLAT")) and halo > 0      # dy with a zero halo ring == ring: conv_patch2.cu flat-raster mode
+    dy = ops.PlaneT(N, oh, oh, ops.cpad(cout, dt), halo if flat else 0, dt)
+    dy.interior().normal_() if flat else dy.t.normal_()
     dx = ops.PlaneT(N, h, h, ops.cpad(cin, dt), halo, dt)
     f = lambda: ops.conv(dy, wp, None, dx, mode=L.CONV_DGRAD, kh=k, kw=k, stride=s, pad=pad, ring=halo, cout=cin, out_h=h, out_w=h)
 else:
