@@ -49,7 +49,7 @@ def sig(x):
 
 calls = []
 NAMES = ["conv", "conv_wgrad", "norm_fwd", "norm_bwd", "cin_affine_fwd", "cin_affine_bwd", "pack_nchw", "unpack_nchw",
-         "grad_gather", "channel_sum", "head1_fwd", "head1_dgrad", "head1_wgrad", "s2d_unfold_add", "loss_lsgan", "loss_l1", "grad_sumsq", "adam_clip", "step_increment"]
+         "grad_gather", "channel_sum", "head1_fwd", "head1_dgrad", "head1_wgrad", "s2d_unfold_add", "loss_lsgan", "loss_l1", "loss_fused", "grad_sumsq", "adam_clip", "step_increment"]
 orig = {n: getattr(ops, n) for n in NAMES}
 
 
