@@ -457,15 +457,17 @@ def main():
     barrier()
     e2.record()
     staged = trainer.StagedBatches(host_batches(K), opt.nlatent)
-    pending = None
+    import collections
+    pending = collections.deque()
     for batch in staged:
         # every step's packed loss vector is read back (D2H) inside the timed region; the read of step k is resolved
-        # after step k+1 has been issued, so the host wait does not leave the GPU idle between steps
-        nxt = m.train_instance(*batch, use_graph=graph_ok, report="defer")[0]
-        if pending is not None:
-            last = pending.get()
-        pending = nxt
-    last = pending.get()
+        # after step k+2 has been issued (PendingReport allows four), so neither the host wait nor the host's issue
+        # latency leaves the GPU idle between steps
+        pending.append(m.train_instance(*batch, use_graph=graph_ok, report="defer")[0])
+        if len(pending) > 2:
+            last = pending.popleft().get()
+    while pending:
+        last = pending.popleft().get()
     e3.record()
     barrier()
     ms_e2e = max_over_ranks(e2.elapsed_time(e3))
